@@ -1,0 +1,227 @@
+/*
+ * pymes_b200.h -- C ABI of the B200-native coupled-cluster contraction engine.
+ *
+ * This is the drop-in boundary for the amplitude-equation hot path of
+ * nickirk/pymes (reference commit 734974a).  The reference has no FFI: its
+ * backend seam is the per-module alias `einsum = partial(np.einsum, optimize=True)`
+ * (pymes/solver/ccsd.py:11, eom_ccsd.py:9, feast_eom_ccsd.py:16, mp2.py:5,
+ * model/ueg.py:10) plus bare `np.einsum` in pymes/solver/ccd.py and
+ * pymes/mixer/diis.py.  Every entry point below replaces a family of those
+ * einsum / elementwise numpy call sites; the reference lines are cited per
+ * function.  INTEGRATION.md shows the ctypes stub a pymes maintainer would add.
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers to float64 unless stated otherwise;
+ *   - strides are in ELEMENTS (not bytes);
+ *   - every call is asynchronous on the given CUDA stream (pass 0 for the
+ *     legacy default stream) and returns 0 on success, a cudaError_t value
+ *     (> 0) for CUDA failures, or a negative PMB_E_* code for bad arguments;
+ *   - the library never allocates persistent device memory: scratch space is
+ *     handed in by the caller (`ws`, `ws_bytes`); query sizes with the
+ *     *_workspace functions.
+ */
+#ifndef PYMES_B200_H
+#define PYMES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMB_MAX_DIMS 4   /* indices per index group (M, N or K)            */
+#define PMB_MAX_TERMS 8  /* A.B products accumulated into one output       */
+
+#define PMB_E_BADARG (-1)
+#define PMB_E_WORKSPACE (-2)
+#define PMB_E_UNSUPPORTED (-3)
+
+typedef void *pmb_stream_t; /* cudaStream_t */
+
+/* ------------------------------------------------------------------------ */
+/* library / device information                                             */
+/* ------------------------------------------------------------------------ */
+int pmb_version(void);
+/* sm count, compute capability (major*10+minor), total global memory bytes  */
+int pmb_device_info(int *sm_count, int *cc, size_t *global_mem);
+/* number of kernels this library has launched since load (or last reset)   */
+long long pmb_launch_count(void);
+void pmb_launch_count_reset(void);
+const char *pmb_error_string(int code);
+
+/* ------------------------------------------------------------------------ */
+/* generic binary tensor contraction on FP64 tensor cores (DMMA)             */
+/*                                                                          */
+/*   C[m, n] = beta * C[m, n] + sum_t alpha_t * sum_k A_t[m, k] * B_t[k, n]  */
+/*                                                                          */
+/* m, n and k are COMPOSITE indices: each is a group of up to PMB_MAX_DIMS   */
+/* tensor indices, listed fastest-varying first, with one extent per index   */
+/* and one stride per index per operand.  An arbitrary index permutation of  */
+/* a 4-index tensor is therefore described by strides only and is fused into */
+/* the tile loads -- nothing is transposed in memory.                        */
+/*                                                                          */
+/* Replaces every two-operand einsum of the hot path, e.g.                   */
+/*   pp ladder   "abcd,cdij->abij"  pymes/solver/ccd.py:187, eom_ccsd.py:383  */
+/*   hh ladder   "klij,abkl->abij"  ccd.py:186 ; I_klij build ccd.py:180      */
+/*   ring terms  ccd.py:190-191,202-204,233-235,238-240                       */
+/*   X_ac / X_ki ccd.py:213-221,231-232                                       */
+/*   T1 dressing ccsd.py:257-286,322-419 ; singles residual ccsd.py:428-436   */
+/*   EOM sigma   eom_ccsd.py:288-308,332-383                                  */
+/* ------------------------------------------------------------------------ */
+typedef struct {
+    const double *A;
+    const double *B;
+    int32_t nk;                      /* number of contracted indices (>= 0)  */
+    int32_t _pad;
+    int64_t k_ext[PMB_MAX_DIMS];     /* extents of the contracted indices    */
+    int64_t a_kstr[PMB_MAX_DIMS];    /* strides of A along them              */
+    int64_t b_kstr[PMB_MAX_DIMS];    /* strides of B along them              */
+    int64_t a_mstr[PMB_MAX_DIMS];    /* strides of A along the M indices     */
+    int64_t b_nstr[PMB_MAX_DIMS];    /* strides of B along the N indices     */
+    double alpha;
+} pmb_term_t;
+
+typedef struct {
+    int32_t nm, nn, nterms, _pad;
+    int64_t m_ext[PMB_MAX_DIMS];
+    int64_t n_ext[PMB_MAX_DIMS];
+    int64_t c_mstr[PMB_MAX_DIMS];
+    int64_t c_nstr[PMB_MAX_DIMS];
+    double *C;
+    double beta;                     /* 0: C is overwritten and never read   */
+    pmb_term_t terms[PMB_MAX_TERMS];
+} pmb_contract_t;
+
+/* bytes of scratch needed for `d` (split-K partial sums; 0 if not split)    */
+size_t pmb_contract_workspace(const pmb_contract_t *d);
+int pmb_contract(const pmb_contract_t *d, void *ws, size_t ws_bytes,
+                 pmb_stream_t stream);
+/* tuning/diagnostic knobs: force a tile configuration (-1 = heuristic) and   */
+/* a split-K factor (0 = heuristic).                                         */
+void pmb_contract_set_tuning(int tile_config, int split_k);
+
+/* ------------------------------------------------------------------------ */
+/* HBM-bound elementwise / reduction kernels                                 */
+/* All 4-index tensors below are addressed as X[a,b,i,j] with explicit       */
+/* element strides s[4] so that views of V_pqrs can be passed directly.      */
+/* ------------------------------------------------------------------------ */
+
+/* out[a,b,i,j] = alpha * in[a,b,i,j] (+ beta * out[a,b,i,j] if beta != 0).   */
+/* `in` may be any permuted / sliced view.  Replaces the `.copy()` and        */
+/* `+= V_block` statements of ccd.py:178,185 and ccsd.py:323-415.             */
+int pmb_axpby4(const int64_t ext[4], double alpha, const double *in,
+               const int64_t in_str[4], double beta, double *out,
+               const int64_t out_str[4], pmb_stream_t stream);
+
+/* T2[a,b,i,j] = V_abij[a,b,i,j] / (e_i + e_j - e_a - e_b + shift)            */
+/* pymes/solver/mp2.py:16-18                                                 */
+int pmb_mp2_amplitudes(int no, int nv, const double *eps_i, const double *eps_a,
+                       double shift, const double *V_abij,
+                       const int64_t v_str[4], double *T2, pmb_stream_t stream);
+
+/* dT = R * (1 / (e_i + e_j - e_a - e_b + shift)); T += delta * dT;          */
+/* scal[0] += sum dT^2.   ccd.py:123-124,138 ; ccsd.py:152-156,177-179,197   */
+int pmb_update_doubles(int no, int nv, const double *eps_i, const double *eps_a,
+                       double shift, double delta, const double *R, double *dT,
+                       double *T2, double *scal, void *ws, size_t ws_bytes,
+                       pmb_stream_t stream);
+/* same for singles: dT1 = R1 / (e_i - e_a + shift); T1 += delta * dT1       */
+int pmb_update_singles(int no, int nv, const double *eps_i, const double *eps_a,
+                       double shift, double delta, const double *R1, double *dT1,
+                       double *T1, pmb_stream_t stream);
+
+/* scal[0] = 2 sum tau[a,b,i,j] V[i,j,a,b]; scal[1] = - sum tau[a,b,i,j] V[i,j,b,a]; */
+/* scal[2] = sum T2^2,   tau = T2 + T1 (x) T1 (T1 may be NULL).               */
+/* ccd.py:256-262,137 ; ccsd.py:458-466,196 ; mp2.py:19-20 (exchange written  */
+/* there as V[j,i,a,b]: set mp2_form = 1).                                   */
+int pmb_energy_doubles(int no, int nv, const double *T2, const double *T1,
+                       const double *V_ijab, const int64_t v_str[4],
+                       int mp2_form, double *scal, void *ws, size_t ws_bytes,
+                       pmb_stream_t stream);
+
+/* Tt[a,b,i,j] = 2 T[a,b,i,j] - T[b,a,i,j]          ccd.py:199                */
+/* (swap_ij = 1:  2 T[a,b,i,j] - T[a,b,j,i]          ccsd.py:430)             */
+int pmb_tilde(int no, int nv, const double *T2, double *Tt, int swap_ij,
+              pmb_stream_t stream);
+
+/* R[a,b,i,j] (+)= Ex[a,b,i,j] + Ex[b,a,j,i]                                 */
+/* ccd.py:249-252 ; eom_ccsd.py:254,377.  accumulate = 0 overwrites R.        */
+int pmb_sym_baji(int no, int nv, const double *Ex, double *R, int accumulate,
+                 pmb_stream_t stream);
+
+/* out[k] = sum_x X_k[x] * Y[x], k = 0..nvec-1     diis.py:65-78;             */
+/* eom_ccsd.py:103-109 ; feast_eom_ccsd.py:137-146                            */
+int pmb_dots(int nvec, const double *const *X, const double *Y, int64_t n,
+             double *out, void *ws, size_t ws_bytes, pmb_stream_t stream);
+
+/* out[x] = sum_k c[k] * X_k[x] (+ beta*out)       diis.py:97-103;            */
+/* eom_ccsd.py:122-147 ; feast_eom_ccsd.py:151-164                            */
+int pmb_lincomb(int nvec, const double *c_host, const double *const *X,
+                int64_t n, double beta, double *out, pmb_stream_t stream);
+
+size_t pmb_reduce_workspace(void);
+
+/* ------------------------------------------------------------------------ */
+/* UEG momentum-conserving two-electron integrals  pymes/model/ueg.py:265-596 */
+/*                                                                          */
+/* The reference's triple Python loop (ueg.py:384-507) evaluates, for every  */
+/* (p, r, q'), s = map[k_q' - (k_r - k_p)] and a weight that depends only on */
+/* the pair (p, r) plus -- for the non-hermitian TC term -- a dot product    */
+/* with (k_r - k_s).  The build is therefore split into                      */
+/*   1. pmb_ueg_umat        : u_mat(q) for every distinct transfer q          */
+/*   2. pmb_ueg_pair_tables : W0[p,r], W1[p,r] for one of the nine branches   */
+/*   3. pmb_ueg_build_block : the HBM-bound dense write of any V sub-block    */
+/*      V[p,q,r,s] = delta(s, s*) * ( W0a[p,r] + W1a[p,r]*(k_r-k_s).(k_r-k_p) */
+/*                                   + 1/2 (W0s[p,r] + W0s[q,s]) )            */
+/*      (W0s carries the (pq)(rs)<->(qp)(sr) symmetrised effective two-body   */
+/*      term of ueg.py:509-513), so each rank of a sharded run generates      */
+/*      only its own rows and V_pqrs never has to exist as one array.         */
+/* ------------------------------------------------------------------------ */
+typedef struct {
+    int32_t n_orb;            /* number of plane waves nP                      */
+    int32_t imax;             /* index-map half width (ueg.py:119-125,153)     */
+    int32_t n_occ;            /* n_ele / 2                                     */
+    int32_t n_ele;
+    double omega;             /* cell volume (ueg.py:69)                       */
+    const double *u_table;    /* correlator u tabulated over n2 = |k_int|^2:   */
+    int32_t u_table_len;      /*   u_table[n2] = u(n2 (2 pi/L)^2); the host    */
+    int32_t _pad;             /*   evaluates any of ueg.py:740-956 once        */
+    const int32_t *kvec;      /* [nP][3] integer k vectors (device)            */
+    const double *kp;         /* [nP][3] (k + shift) 2 pi / L (device)         */
+    const int32_t *index_map; /* [(2 imax+1)^3] orbital index or -1 (device)   */
+} pmb_ueg_t;
+
+/* branches of eval_2b_integrals, in the order of ueg.py:411-504             */
+#define PMB_UEG_COULOMB 0
+#define PMB_UEG_RPA 1
+#define PMB_UEG_ONLY_2B 2
+#define PMB_UEG_ONLY_HERMI_2B 3
+#define PMB_UEG_ONLY_NON_HERMI_2B 4
+#define PMB_UEG_EFFECT_2B 5
+#define PMB_UEG_EXCHANGE_1 6
+#define PMB_UEG_EXCHANGE_2 7
+#define PMB_UEG_EXCHANGE_3 8
+
+/* out[n] = sum_{k' in [-cutoff,cutoff]^3} (k1.k2) u(k1^2) u(k2^2) / Omega,     */
+/* k1 = 2 pi k'/L (L = box_len), k2 = 2 pi q_n/L - k1, for nq integer transfer  */
+/* vectors q (device, int32 [nq][3]).                                          */
+/* ueg.py:581-596 (cutoff = 30 there).  One CTA per q, fixed-order reduction.  */
+int pmb_ueg_umat(const pmb_ueg_t *u, double box_len, int cutoff, int nq,
+                 const int32_t *qvec, double *out, pmb_stream_t stream);
+
+/* W0[p*nP+r], W1[p*nP+r] for `mode`; umat_pr[p*nP+r] = u_mat(k_r - k_p) is     */
+/* needed by modes 2 and 3 only (may be NULL otherwise).                       */
+int pmb_ueg_pair_tables(const pmb_ueg_t *u, int mode, const double *umat_pr,
+                        double *W0, double *W1, pmb_stream_t stream);
+
+/* Dense block out[np][nq][nr][ns] of V for p in [lo[0], lo[0]+ext[0]) etc.    */
+/* W1a and W0s may be NULL.                                                    */
+int pmb_ueg_build_block(const pmb_ueg_t *u, const double *W0a, const double *W1a,
+                        const double *W0s, const int32_t lo[4], const int32_t ext[4],
+                        double *out, pmb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYMES_B200_H */

@@ -1,0 +1,384 @@
+"""CPU oracle for the coupled-cluster amplitude-equation hot path.
+
+TEST INFRASTRUCTURE ONLY.  This is a numpy restatement of the reference
+algorithm (nickirk/pymes @ 734974a) and exists so that the CUDA path can be
+checked against it.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  The
+product package ``pymes_b200`` never does.
+
+Parity status: PINNED.  ``tests/test_oracle_golden.py`` checks every function
+here against fixtures produced by importing the reference itself
+(``tests/golden/make_golden.py``) and against the constants typed into the
+reference's own tests (LiH/3-21G HF/CCD/CCSD, UEG 14e CCD/DCD, TC-UEG).
+
+Every contraction is written as a row ``(coef, subscripts, operand names)`` in a
+table; each table cites the reference lines it restates.  All arithmetic is
+float64 ``numpy.einsum`` exactly like the reference (``optimize=True`` for the
+multi-operand products, as in ``ccsd.py:11``).
+"""
+import string
+
+import numpy as np
+
+_OCC = "ijklmn"
+
+
+def _es(sub, *ops):
+    return np.einsum(sub.replace(" ", ""), *ops, optimize=True)
+
+
+# --------------------------------------------------------------------------
+# integral partition -- reference pymes/integral/partition.py:4-39
+# --------------------------------------------------------------------------
+BLOCK_KEYS = ("abci iabj iajk aijk klij aibj ijak abic iajb abcd iabc aijb "
+              "ijka aibc ijab abij").split()
+
+
+def partition(no, V):
+    """16 zero-copy views of V_pqrs named by their index pattern."""
+    def sl(ch):
+        return slice(0, no) if ch in _OCC else slice(no, None)
+    return {key: V[tuple(sl(ch) for ch in key)] for key in BLOCK_KEYS}
+
+
+# --------------------------------------------------------------------------
+# Hartree-Fock helpers -- reference pymes/mean_field/hf.py:5-18
+# --------------------------------------------------------------------------
+def hf_energy(no, e_core, h, V):
+    occ = V[:no, :no, :no, :no]
+    return (2.0 * np.trace(h[:no, :no]) + 2.0 * _es("jiji->", occ)
+            - _es("ijji->", occ) + e_core)
+
+
+def hf_fock(no, h, V):
+    f = h.copy()
+    f += 2.0 * _es("piqi->pq", V[:, :no, :, :no])
+    f -= _es("piiq->pq", V[:, :no, :no, :])
+    return f
+
+
+# --------------------------------------------------------------------------
+# denominators and MP2 -- reference pymes/solver/mp2.py:9-22, ccsd.py:152-156
+# --------------------------------------------------------------------------
+def denominators(eps_i, eps_a, shift=0.0):
+    d2 = (eps_i[None, None, :, None] + eps_i[None, None, None, :]
+          - eps_a[:, None, None, None] - eps_a[None, :, None, None])
+    d1 = eps_i[None, :] - eps_a[:, None]
+    return d1 + shift, d2 + shift
+
+
+def mp2(eps_i, eps_a, V_ijab, V_abij, shift=0.0):
+    _, d2 = denominators(eps_i, eps_a, shift)
+    T2 = V_abij / d2
+    e = 2.0 * _es("abij,ijab->", T2, V_ijab) - _es("abij,jiab->", T2, V_ijab)
+    return e, T2
+
+
+# --------------------------------------------------------------------------
+# doubles residual -- reference pymes/solver/ccd.py:164-254
+# --------------------------------------------------------------------------
+def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj,
+                     V_abcd, is_dcd=False, is_bruekner=False):
+    """R_abij of the distinguishable-cluster / coupled-cluster doubles equation.
+
+    Rows flagged ``ccd_only`` are dropped for DCD/DCSD (``ccd.py:179,189,218,237``).
+    No hermiticity of V is assumed anywhere (``ccd.py:172,244-249``).
+    """
+    ccd = not is_dcd
+    fab, fij = fock[no:, no:], fock[:no, :no]
+    Tt = 2.0 * T2 - T2.transpose(1, 0, 2, 3)                    # ccd.py:199
+
+    I = V_klij.copy()                                           # ccd.py:178-180
+    if ccd:
+        I = I + _es("klcd,cdij->klij", V_ijab, T2)
+    R = V_abij + _es("klij,abkl->abij", I, T2)                  # ccd.py:185-186
+    R = R + _es("abcd,cdij->abij", V_abcd, T2)                  # ccd.py:187
+    if ccd:                                                     # ccd.py:189-191
+        R = R + _es("alcj,cbil->abij", _es("klcd,adkj->alcj", V_ijab, T2), T2)
+    R = R + _es("acik,cbkj->abij", Tt,
+                _es("klcd,dblj->cbkj", V_ijab, Tt))             # ccd.py:202-204
+
+    if is_bruekner:                                             # ccd.py:209-211
+        Xac, Xki = fab.copy(), fij.copy()
+    else:                                                       # ccd.py:213-216
+        Xac = fab - 0.5 * _es("adkl,lkdc->ac", Tt, V_ijab)
+        Xki = fij + 0.5 * _es("cdil,lkdc->ki", Tt, V_ijab)
+    if ccd:                                                     # ccd.py:218-221
+        Xac = Xac - 0.5 * _es("adkl,lkdc->ac", Tt, V_ijab)
+        Xki = Xki + 0.5 * _es("cdil,lkdc->ki", Tt, V_ijab)
+
+    ops = {"Xac": Xac, "Xki": Xki, "T": T2, "Tt": Tt, "iajb": V_iajb,
+           "iabj": V_iabj}
+    ex_rows = [                                                 # ccd.py:231-235
+        (+1.0, "ac,cbij->abij", "Xac", "T", False),
+        (-1.0, "ki,abkj->abij", "Xki", "T", False),
+        (-1.0, "kaic,cbkj->abij", "iajb", "T", False),
+        (-1.0, "kbic,ackj->abij", "iajb", "T", False),
+        (+1.0, "acik,kbcj->abij", "Tt", "iabj", False),
+        (-1.0, "alci,cblj->abij", "Xp", "T", True),             # ccd.py:239
+        (+1.0, "alci,bclj->abij", "Xp", "T", True),             # ccd.py:240
+    ]
+    if ccd:
+        ops["Xp"] = _es("klcd,daki->alci", V_ijab, T2)          # ccd.py:238
+    Ex = np.zeros_like(R)
+    for coef, sub, a, b, ccd_only in ex_rows:
+        if ccd_only and not ccd:
+            continue
+        Ex += coef * _es(sub, ops[a], ops[b])
+    return R + Ex + Ex.transpose(1, 0, 3, 2)                    # ccd.py:249-252
+
+
+def ccd_energy(T2, V_ijab):
+    """(direct, exchange) -- reference ccd.py:256-262."""
+    return (2.0 * _es("abij,ijab->", T2, V_ijab),
+            -1.0 * _es("abij,ijba->", T2, V_ijab))
+
+
+def ccsd_energy(f_ia, T1, T2, V_ijab):
+    """(one-body, direct, exchange) -- reference ccsd.py:458-466."""
+    tau = T2 + _es("ai,bj->abij", T1, T1)
+    d, x = ccd_energy(tau, V_ijab)
+    return 2.0 * _es("ia,ai->", f_ia, T1), d, x
+
+
+# --------------------------------------------------------------------------
+# T1 dressing -- reference pymes/solver/ccsd.py:226-421
+# Each row: (coef, subscripts, source block, number of T1 factors)
+# --------------------------------------------------------------------------
+_FOCK_ROWS = {
+    # target block : rows (coef, subscripts, operands); "t" = T1, f?? = fock blocks
+    "ov": [(+2.0, "bj,jabi->ia", ("t", "iabj")),                # ccsd.py:257-258
+           (-1.0, "bj,jiab->ia", ("t", "ijab"))],
+    "vo": [(-1.0, "ji,aj->ai", ("foo", "t")),                   # ccsd.py:260-272
+           (+1.0, "ab,bi->ai", ("fvv", "t")),
+           (-1.0, "jb,bi,aj->ai", ("fov", "t", "t")),
+           (+2.0, "bj,jabi->ai", ("t", "iabj")),
+           (-2.0, "bj,jkbi,ak->ai", ("t", "ijak", "t")),
+           (+2.0, "bj,jabc,ci->ai", ("t", "iabc", "t")),
+           (-2.0, "bj,jkbc,ci,ak->ai", ("t", "ijab", "t", "t")),
+           (-1.0, "bj,jaib->ai", ("t", "iajb")),
+           (+1.0, "bj,jkib,ak->ai", ("t", "ijka", "t")),
+           (-1.0, "bj,jacb,ci->ai", ("t", "iabc", "t")),
+           (+1.0, "bj,jkcb,ci,ak->ai", ("t", "ijab", "t", "t"))],
+    "oo": [(+2.0, "ck,kicj->ij", ("t", "ijak")),                # ccsd.py:275-279
+           (-1.0, "ck,kijc->ij", ("t", "ijka")),
+           (+1.0, "ib,bj->ij", ("fov", "t")),
+           (+2.0, "ck,kicb,bj->ij", ("t", "ijab", "t")),
+           (-1.0, "ck,kibc,bj->ij", ("t", "ijab", "t"))],
+    "vv": [(+2.0, "ci,iacb->ab", ("t", "iabc")),                # ccsd.py:282-286
+           (-1.0, "ci,iabc->ab", ("t", "iabc")),
+           (-1.0, "ib,ai->ab", ("fov", "t")),
+           (-2.0, "ck,klcb,al->ab", ("t", "ijab", "t")),
+           (+1.0, "ck,kibc,ai->ab", ("t", "ijab", "t"))],
+}
+
+
+def dressed_fock(no, fock, T1, dV):
+    """T1-dressed Fock matrix; every source is the undressed input."""
+    src = dict(dV)
+    src.update(t=T1, foo=fock[:no, :no], fvv=fock[no:, no:], fov=fock[:no, no:])
+    out = fock.copy()
+    where = {"ov": (slice(0, no), slice(no, None)),
+             "vo": (slice(no, None), slice(0, no)),
+             "oo": (slice(0, no), slice(0, no)),
+             "vv": (slice(no, None), slice(no, None))}
+    for blk, rows in _FOCK_ROWS.items():
+        acc = np.zeros_like(out[where[blk]])
+        for coef, sub, names in rows:
+            acc += coef * _es(sub, *[src[n] for n in names])
+        out[where[blk]] += acc
+    return out
+
+
+_V_ROWS = {
+    "abij": [(-1.0, "kbij,ak->abij", "iajk", 1),                # ccsd.py:322-343
+             (+1.0, "abcj,ci->abij", "abci", 1),
+             (-1.0, "kbcj,ak,ci->abij", "iabj", 2),
+             (-1.0, "alij,bl->abij", "aijk", 1),
+             (+1.0, "klij,ak,bl->abij", "klij", 2),
+             (-1.0, "alcj,ci,bl->abij", "aibj", 2),
+             (+1.0, "klcj,ak,ci,bl->abij", "ijak", 3),
+             (+1.0, "abid,dj->abij", "abic", 1),
+             (-1.0, "kbid,ak,dj->abij", "iajb", 2),
+             (+1.0, "abcd,ci,dj->abij", "abcd", 2),
+             (-1.0, "kbcd,ak,ci,dj->abij", "iabc", 3),
+             (-1.0, "alid,bl,dj->abij", "aijb", 2),
+             (+1.0, "klid,ak,bl,dj->abij", "ijka", 3),
+             (-1.0, "alcd,ci,bl,dj->abij", "aibc", 3),
+             (+1.0, "klcd,ak,ci,bl,dj->abij", "ijab", 4)],
+    "klij": [(+1.0, "klaj,ai->klij", "ijak", 1),                # ccsd.py:346-352
+             (+1.0, "klib,bj->klij", "ijka", 1),
+             (+1.0, "klab,ai,bj->klij", "ijab", 2)],
+    "ijab": [],                                                 # ccsd.py:355-357
+    "ijka": [(+1.0, "ijba,bk->ijka", "ijab", 1)],               # ccsd.py:359-362
+    "ijak": [(+1.0, "ijab,bk->ijak", "ijab", 1)],               # ccsd.py:364-367
+    "iajb": [(+1.0, "iacb,cj->iajb", "iabc", 1),                # ccsd.py:370-375
+             (-1.0, "ikjb,ak->iajb", "ijka", 1),
+             (-1.0, "ikcb,cj,ak->iajb", "ijab", 2)],
+    "iabj": [(-1.0, "ikbj,ak->iabj", "ijak", 1),                # ccsd.py:378-383
+             (+1.0, "iabc,cj->iabj", "iabc", 1),
+             (-1.0, "ikbc,ak,cj->iabj", "ijab", 2)],
+    "iabc": [(-1.0, "ijbc,aj->iabc", "ijab", 1)],               # ccsd.py:385-388
+    "abic": [(-1.0, "jbic,aj->abic", "iajb", 1),                # ccsd.py:390-399
+             (+1.0, "abdc,di->abic", "abcd", 1),
+             (-1.0, "jbdc,aj,di->abic", "iabc", 2),
+             (-1.0, "ajic,bj->abic", "aijb", 1),
+             (+1.0, "kjic,ak,bj->abic", "ijka", 2),
+             (-1.0, "ajdc,di,bj->abic", "aibc", 2),
+             (+1.0, "kjdc,ak,di,bj->abic", "ijab", 3)],
+    "iajk": [(-1.0, "iljk,al->iajk", "klij", 1),                # ccsd.py:402-411
+             (+1.0, "iajb,bk->iajk", "iajb", 1),
+             (-1.0, "iljb,al,bk->iajk", "ijka", 2),
+             (+1.0, "iabk,bj->iajk", "iabj", 1),
+             (-1.0, "ilbk,bj,al->iajk", "ijak", 2),
+             (+1.0, "iabc,bj,ck->iajk", "iabc", 2),
+             (-1.0, "ilbc,bj,al,ck->iajk", "ijab", 3)],
+    "abcd": [(-1.0, "jbcd,aj->abcd", "iabc", 1),                # ccsd.py:414-419
+             (-1.0, "aicd,bi->abcd", "aibc", 1),
+             (+1.0, "jicd,aj,bi->abcd", "ijab", 2)],
+}
+DRESSED_KEYS = tuple(_V_ROWS)
+
+
+def dressed_V(T1, dV, keys=None):
+    """Dict of T1-dressed V blocks; keys not dressed by the reference stay None
+    (``dict.fromkeys(dict_t_V, None)``, ccsd.py:316-317)."""
+    out = dict.fromkeys(dV, None)
+    for key in (DRESSED_KEYS if keys is None else keys):
+        blk = dV[key].copy()
+        for coef, sub, src, nt in _V_ROWS[key]:
+            blk += coef * _es(sub, dV[src], *([T1] * nt))
+        out[key] = blk
+    return out
+
+
+def singles_residual(no, fock_dressed, T1, T2, dV):
+    """R_ai -- reference ccsd.py:423-438 (dressed Fock, undressed V)."""
+    Tt = 2.0 * T2 - T2.transpose(0, 1, 3, 2)
+    R = fock_dressed[no:, :no].copy()
+    R += _es("jb,abij->ai", fock_dressed[:no, no:], Tt)
+    R += _es("ajbc,bcij->ai", dV["aibc"], Tt)
+    R -= _es("kjbc,ak,bcij->ai", dV["ijab"], T1, Tt)
+    R -= _es("jkib,abjk->ai", dV["ijka"], Tt)
+    R -= _es("jkcb,ci,abjk->ai", dV["ijab"], T1, Tt)
+    return R
+
+
+# --------------------------------------------------------------------------
+# DIIS -- reference pymes/mixer/diis.py:9-112 (bookkeeping quirk included)
+# --------------------------------------------------------------------------
+class DIIS:
+    def __init__(self, dim_space=5):
+        self.dim_space = dim_space
+        self.L = np.zeros((1, 1))
+        self.errs, self.amps = [], []
+
+    def mix(self, error, amplitude):
+        full = len(self.errs) == self.dim_space
+        if full:
+            self.errs.pop(0)
+            self.amps.pop(0)
+        self.errs.append(error)
+        self.amps.append(amplitude)
+        n = len(self.errs)
+        L = np.zeros((n + 1, n + 1))
+        L[-1, :-1] = -1.0
+        L[:-1, -1] = -1.0
+        if full:
+            # diis.py:59-60 -- one row/column too few is carried over; the
+            # overlaps of the second-newest vector are left at zero.
+            L[:-3, :-3] = self.L[1:-2, 1:-2]
+        else:
+            L[:-2, :-2] = self.L[:-1, :-1]
+        for i in range(n):
+            for e_i, e_new in zip(self.errs[i], self.errs[-1]):
+                L[i, -2] += np.real(np.sum(e_i * e_new))        # diis.py:74-78
+        L[-2, :] = L[:, -2]
+        self.L = L.copy()
+        rhs = np.zeros(n + 1)
+        rhs[-1] = -1.0
+        w, U = np.linalg.eigh(self.L)
+        if np.any(np.abs(w) < 1e-12):                           # diis.py:87-93
+            ok = np.abs(w) > 1e-12
+            c = (U[:, ok] * (1.0 / w[ok])) @ (U[:, ok].T.conj() @ rhs)
+        else:
+            c = np.linalg.inv(self.L).dot(rhs)
+        self.last_c = c
+        out = [np.zeros_like(x) for x in self.amps[0]]
+        for a in range(n):
+            for i in range(len(out)):
+                out[i] += self.amps[a][i] * c[a]
+        return out
+
+
+# --------------------------------------------------------------------------
+# ground-state drivers -- reference ccd.py:24-162, ccsd.py:47-224
+# --------------------------------------------------------------------------
+def ccd_solve(no, fock, V, level_shift=0.0, is_dcd=False, is_diis=True,
+              delta_e=1e-8, max_iter=50, amps=None, trace=None):
+    dV = partition(no, V)
+    eps_i, eps_a = fock.diagonal()[:no], fock.diagonal()[no:]
+    e_mp2, T2 = mp2(eps_i, eps_a, dV["ijab"], dV["abij"], level_shift)
+    if amps is not None:
+        T2 = amps
+    _, d2 = denominators(eps_i, eps_a, level_shift)
+    mixer = DIIS(6) if is_diis else None
+    dE, e_last, e, it = abs(e_mp2), e_mp2, 0.0, 0
+    while abs(dE) > delta_e and it <= max_iter:
+        it += 1
+        R = doubles_residual(no, fock, T2, dV["klij"], dV["ijab"], dV["abij"],
+                             dV["iajb"], dV["iabj"], dV["abcd"], is_dcd)
+        dT = R / d2
+        T2 += dT
+        if mixer is not None:
+            T2 = mixer.mix([dT], [T2])[0]
+        ed, ex = ccd_energy(T2, dV["ijab"])
+        e = ed + ex
+        dE, e_last = e - e_last, e
+        if trace is not None:
+            trace.append(dict(e=e, t2=T2.copy(), dt2_norm=np.linalg.norm(dT),
+                              t2_norm=np.linalg.norm(T2)))
+    return {"e": e, "t2": T2, "dE": dE, "iterations": it, "e_mp2": e_mp2}
+
+
+def ccsd_solve(no, fock, V, level_shift=0.0, is_dcsd=False, is_diis=True,
+               delta_e=1e-8, max_iter=50, amps=None, trace=None):
+    nv = fock.shape[0] - no
+    dV = partition(no, V)
+    eps_i, eps_a = fock.diagonal()[:no].copy(), fock.diagonal()[no:].copy()
+    e_mp2, T2 = mp2(eps_i, eps_a, dV["ijab"], dV["abij"], level_shift)
+    T1 = np.zeros((nv, no))
+    if amps is not None:
+        T1, T2 = amps
+    d1, d2 = denominators(eps_i, eps_a, level_shift)
+    mixer = DIIS(6) if is_diis else None
+    dE, e_last, e, it = abs(e_mp2), e_mp2, 0.0, 0
+    while abs(dE) > delta_e and it <= max_iter:
+        it += 1
+        ft = dressed_fock(no, fock, T1, dV)
+        dVt = dressed_V(T1, dV)
+        R1 = singles_residual(no, ft, T1, T2, dV)               # ccsd.py:167-168
+        R2 = doubles_residual(no, ft, T2, dVt["klij"], dVt["ijab"], dVt["abij"],
+                              dVt["iajb"], dVt["iabj"], dVt["abcd"], is_dcsd)
+        dT1, dT2 = R1 / d1, R2 / d2
+        T1 = T1 + dT1
+        T2 = T2 + dT2
+        if mixer is not None:
+            T1, T2 = mixer.mix([dT1, dT2], [T1, T2])
+        e1, ed, ex = ccsd_energy(fock[:no, no:], T1, T2, dV["ijab"])
+        e = e1 + ed + ex
+        dE, e_last = e - e_last, e
+        if trace is not None:
+            trace.append(dict(e=e, t1=T1.copy(), t2=T2.copy(),
+                              dt2_norm=np.linalg.norm(dT2),
+                              t2_norm=np.linalg.norm(T2)))
+    return {"e": e, "t1": T1, "t2": T2, "dE": dE, "iterations": it,
+            "e_mp2": e_mp2}
+
+
+def flops_doubles_residual(no, nv, is_dcd=False):
+    """Algorithmic flop count of one residual (SURVEY 8d / BASELINE.md 3)."""
+    o, v = float(no), float(nv)
+    if is_dcd:
+        return 2*o**2*v**4 + 10*o**3*v**3 + 2*o**4*v**2 + 4*o**2*v**3 + 4*o**3*v**2
+    return 2*o**2*v**4 + 20*o**3*v**3 + 4*o**4*v**2 + 4*o**2*v**3 + 4*o**3*v**2

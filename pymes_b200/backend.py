@@ -1,0 +1,429 @@
+"""Device backend: the replacement for the reference's ``einsum`` seam.
+
+The reference funnels every tensor operation through
+``einsum = partial(np.einsum, optimize=True)`` (pymes/solver/ccsd.py:11 and the
+other solver modules).  Here the same role is played by :func:`contract`, which
+parses a two-operand einsum string into M / N / K index groups and hands a
+stride-only description of the operands to the DMMA kernel behind
+``pmb_contract`` -- index permutations are never materialised.
+
+PyTorch is used for device memory and streams only.  Every arithmetic kernel is
+in ``libpymes_b200.so``; there is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+F64 = torch.float64
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("pymes_b200 needs a CUDA device (built for sm_100a / B200); "
+                           "there is no CPU fallback")
+
+
+def device():
+    require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def asdev(x):
+    """numpy array / torch tensor -> float64 CUDA tensor (views keep their strides)."""
+    if isinstance(x, torch.Tensor):
+        if x.dtype != F64:
+            x = x.to(F64)
+        return x if x.is_cuda else x.to(device())
+    a = np.asarray(x, dtype=np.float64)
+    if not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a)
+    return torch.from_numpy(a).to(device())
+
+
+def tonumpy(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+def empty(*shape):
+    return torch.empty(shape, dtype=F64, device=device())
+
+
+def zeros(*shape):
+    return torch.zeros(shape, dtype=F64, device=device())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _device_key():
+    return torch.cuda.current_device()
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class _Scratch:
+    """Per-device scratch handed to the library (it never allocates itself)."""
+
+    def __init__(self):
+        self.reduce = None
+        self.splitk = None
+
+    def reduce_ws(self):
+        if self.reduce is None:
+            n = _lib.load().pmb_reduce_workspace()
+            self.reduce = torch.empty(n // 8, dtype=F64, device=device())
+        return self.reduce
+
+    def splitk_ws(self, nbytes):
+        if self.splitk is None or self.splitk.numel() * 8 < nbytes:
+            self.splitk = torch.empty((nbytes + 7) // 8, dtype=F64, device=device())
+        return self.splitk
+
+
+_scratch = {}
+
+
+def scratch():
+    d = _device_key()
+    if d not in _scratch:
+        _scratch[d] = _Scratch()
+    return _scratch[d]
+
+
+def launch_count():
+    return int(_lib.load().pmb_launch_count())
+
+
+# --------------------------------------------------------------------------
+# contraction front end
+# --------------------------------------------------------------------------
+def _parse(spec):
+    lhs, out = spec.replace(" ", "").split("->")
+    a, b = lhs.split(",")
+    return a, b, out
+
+
+def _fill(arr, vals):
+    for i, v in enumerate(vals):
+        arr[i] = int(v)
+
+
+def describe_contraction(out_sub, terms, out=None, beta=0.0, conv=None, alloc=None):
+    """Build the ``pmb_contract_t`` descriptor for ``contract_terms`` (pure host logic:
+    index classification, operand swaps, group ordering, strides).  Returns
+    ``(descriptor, out, operands)``; ``conv``/``alloc`` default to the device versions
+    (the CPU tests substitute host tensors to check this logic without a GPU)."""
+    conv = asdev if conv is None else conv
+    alloc = empty if alloc is None else alloc
+    if not 1 <= len(terms) <= _lib.MAX_TERMS:
+        raise ValueError("1..%d terms per contraction" % _lib.MAX_TERMS)
+    ext = {}
+    norm = []
+    for alpha, sa, A, sb, B in terms:
+        A, B = conv(A), conv(B)
+        if A.dim() != len(sa) or B.dim() != len(sb):
+            raise ValueError("subscripts %s,%s do not match operand ranks" % (sa, sb))
+        for s, t in ((sa, A), (sb, B)):
+            if len(set(s)) != len(s):
+                raise ValueError("repeated index in %s is not supported" % s)
+            for ch, n in zip(s, t.shape):
+                if ext.setdefault(ch, int(n)) != int(n):
+                    raise ValueError("extent mismatch for index %s" % ch)
+        norm.append([float(alpha), sa, A, sb, B])
+    if len(set(out_sub)) != len(out_sub):
+        raise ValueError("repeated output index")
+    # split of the output indices fixed by the first term
+    m_set = frozenset(ch for ch in out_sub if ch in norm[0][1])
+    n_set = frozenset(ch for ch in out_sub if ch in norm[0][3])
+    if m_set & n_set or (m_set | n_set) != frozenset(out_sub):
+        raise ValueError("batch / broadcast indices are not supported: %s" % out_sub)
+    for t in norm:
+        in_a = frozenset(ch for ch in out_sub if ch in t[1])
+        if in_a == m_set and frozenset(ch for ch in out_sub if ch in t[3]) == n_set:
+            continue
+        if in_a == n_set and frozenset(ch for ch in out_sub if ch in t[3]) == m_set:
+            t[1], t[2], t[3], t[4] = t[3], t[4], t[1], t[2]
+            continue
+        raise ValueError("terms split the output indices differently")
+    for t in norm:
+        ka = set(t[1]) - m_set
+        kb = set(t[3]) - n_set
+        if ka != kb:
+            raise ValueError("indices %s appear in one operand only" % sorted(ka ^ kb))
+        if len(ka) > _lib.MAX_DIMS:
+            raise ValueError("too many contracted indices")
+    shape = tuple(ext[ch] for ch in out_sub)
+    if out is None:
+        if beta != 0.0:
+            raise ValueError("beta != 0 needs an output tensor")
+        out = alloc(*shape)
+    elif tuple(out.shape) != shape:
+        raise ValueError("output shape %s != %s" % (tuple(out.shape), shape))
+    cstr = dict(zip(out_sub, out.stride()))
+    # keep the output's unit-stride index in the N group (coalesced epilogue)
+    if out_sub and min(out_sub, key=lambda ch: (cstr[ch], -ext[ch])) in m_set and n_set:
+        m_set, n_set = n_set, m_set
+        for t in norm:
+            t[1], t[2], t[3], t[4] = t[3], t[4], t[1], t[2]
+    if len(m_set) > _lib.MAX_DIMS or len(n_set) > _lib.MAX_DIMS:
+        raise ValueError("too many indices in one group")
+    a0 = dict(zip(norm[0][1], norm[0][2].stride()))
+    m_ord = sorted(m_set, key=lambda ch: (a0[ch], ch))
+    n_ord = sorted(n_set, key=lambda ch: (cstr[ch], ch))
+
+    d = _lib.Contract()
+    d.nm, d.nn, d.nterms = len(m_ord), len(n_ord), len(norm)
+    _fill(d.m_ext, [ext[ch] for ch in m_ord])
+    _fill(d.n_ext, [ext[ch] for ch in n_ord])
+    _fill(d.c_mstr, [cstr[ch] for ch in m_ord])
+    _fill(d.c_nstr, [cstr[ch] for ch in n_ord])
+    d.C = out.data_ptr()
+    d.beta = float(beta)
+    for i, (alpha, sa, A, sb, B) in enumerate(norm):
+        astr = dict(zip(sa, A.stride()))
+        bstr = dict(zip(sb, B.stride()))
+        ks = [ch for ch in sa if ch not in m_set]
+        a_min = min(sa, key=lambda ch: astr[ch]) if sa else None
+        b_min = min(sb, key=lambda ch: bstr[ch]) if sb else None
+        if a_min in ks or b_min not in ks:
+            k_ord = sorted(ks, key=lambda ch: (astr[ch], ch))
+        else:
+            k_ord = sorted(ks, key=lambda ch: (bstr[ch], ch))
+        t = d.terms[i]
+        t.A, t.B, t.nk, t.alpha = A.data_ptr(), B.data_ptr(), len(k_ord), alpha
+        _fill(t.k_ext, [ext[ch] for ch in k_ord])
+        _fill(t.a_kstr, [astr[ch] for ch in k_ord])
+        _fill(t.b_kstr, [bstr[ch] for ch in k_ord])
+        _fill(t.a_mstr, [astr[ch] for ch in m_ord])
+        _fill(t.b_nstr, [bstr[ch] for ch in n_ord])
+    return d, out, norm
+
+
+def contract_terms(out_sub, terms, out=None, beta=0.0):
+    """out[out_sub] = beta*out + sum_t alpha_t * einsum(subA_t, subB_t -> out_sub).
+
+    ``terms`` is a list of ``(alpha, subA, A, subB, B)``.  All terms must split the
+    output indices between their two operands in the same way (operands are
+    swapped automatically when needed); contracted indices may differ per term.
+    One kernel launch accumulates every term in registers.
+    """
+    lib = _lib.load()
+    d, out, _operands = describe_contraction(out_sub, terms, out, beta)
+    need = lib.pmb_contract_workspace(C.byref(d))
+    ws = scratch().splitk_ws(need) if need else None
+    rc = lib.pmb_contract(C.byref(d), _ptr(ws) if ws is not None else None, need, _stream())
+    _lib.check(rc, "pmb_contract")
+    return out
+
+
+def contract(spec, A, B, out=None, alpha=1.0, beta=0.0):
+    """Two-operand einsum on the DMMA engine: out = beta*out + alpha*einsum(spec, A, B)."""
+    sa, sb, so = _parse(spec)
+    return contract_terms(so, [(alpha, sa, asdev(A), sb, asdev(B))], out=out, beta=beta)
+
+
+# --------------------------------------------------------------------------
+# elementwise / reduction wrappers
+# --------------------------------------------------------------------------
+def _pad4(vals, fill):
+    vals = list(vals)
+    return [fill] * (4 - len(vals)) + vals
+
+
+def axpby(alpha, src, beta=0.0, out=None):
+    """out = alpha*src + beta*out for tensors of rank <= 4; ``src`` may be any view."""
+    lib = _lib.load()
+    src = asdev(src)
+    if src.dim() > 4:
+        raise ValueError("rank <= 4 only")
+    if out is None:
+        if beta != 0.0:
+            raise ValueError("beta != 0 needs an output tensor")
+        out = empty(*src.shape)
+    if tuple(out.shape) != tuple(src.shape):
+        raise ValueError("shape mismatch")
+    ext = _lib.I64x4(*_pad4(src.shape, 1))
+    si = _lib.I64x4(*_pad4(src.stride(), 0))
+    so = _lib.I64x4(*_pad4(out.stride(), 0))
+    _lib.check(lib.pmb_axpby4(ext, float(alpha), _ptr(src), si, float(beta), _ptr(out), so, _stream()),
+               "pmb_axpby4")
+    return out
+
+
+def copy(src):
+    return axpby(1.0, src)
+
+
+def mp2_amplitudes(eps_i, eps_a, shift, V_abij):
+    lib = _lib.load()
+    no, nv = eps_i.numel(), eps_a.numel()
+    T2 = empty(nv, nv, no, no)
+    _lib.check(lib.pmb_mp2_amplitudes(no, nv, _ptr(eps_i), _ptr(eps_a), float(shift), _ptr(V_abij),
+                                      _lib.I64x4(*V_abij.stride()), _ptr(T2), _stream()),
+               "pmb_mp2_amplitudes")
+    return T2
+
+
+def update_doubles(eps_i, eps_a, shift, delta, R, T2, scal):
+    """dT = R/D, T2 += delta*dT (in place); scal[0] = |dT|^2.  Returns dT."""
+    lib = _lib.load()
+    no, nv = eps_i.numel(), eps_a.numel()
+    dT = torch.empty_like(T2)
+    ws = scratch().reduce_ws()
+    _lib.check(lib.pmb_update_doubles(no, nv, _ptr(eps_i), _ptr(eps_a), float(shift), float(delta), _ptr(R),
+                                      _ptr(dT), _ptr(T2), _ptr(scal), _ptr(ws), ws.numel() * 8, _stream()),
+               "pmb_update_doubles")
+    return dT
+
+
+def update_singles(eps_i, eps_a, shift, delta, R1, T1):
+    lib = _lib.load()
+    no, nv = eps_i.numel(), eps_a.numel()
+    dT1 = torch.empty_like(T1)
+    _lib.check(lib.pmb_update_singles(no, nv, _ptr(eps_i), _ptr(eps_a), float(shift), float(delta), _ptr(R1),
+                                      _ptr(dT1), _ptr(T1), _stream()), "pmb_update_singles")
+    return dT1
+
+
+def energy_doubles(T2, V_ijab, scal, T1=None, mp2_form=False):
+    """scal[0:3] = (E_direct, E_exchange, |T2|^2) on the device."""
+    lib = _lib.load()
+    nv, no = T2.shape[0], T2.shape[2]
+    ws = scratch().reduce_ws()
+    _lib.check(lib.pmb_energy_doubles(no, nv, _ptr(T2), _ptr(T1) if T1 is not None else None, _ptr(V_ijab),
+                                      _lib.I64x4(*V_ijab.stride()), int(mp2_form), _ptr(scal), _ptr(ws),
+                                      ws.numel() * 8, _stream()), "pmb_energy_doubles")
+    return scal
+
+
+def tilde(T2, swap_ij=False):
+    lib = _lib.load()
+    nv, no = T2.shape[0], T2.shape[2]
+    Tt = torch.empty_like(T2)
+    _lib.check(lib.pmb_tilde(no, nv, _ptr(T2), _ptr(Tt), int(swap_ij), _stream()), "pmb_tilde")
+    return Tt
+
+
+def sym_baji(Ex, R=None, accumulate=True):
+    """R (+)= Ex + Ex^{baji}."""
+    lib = _lib.load()
+    nv, no = Ex.shape[0], Ex.shape[2]
+    if R is None:
+        R, accumulate = torch.empty_like(Ex), False
+    _lib.check(lib.pmb_sym_baji(no, nv, _ptr(Ex), _ptr(R), int(accumulate), _stream()), "pmb_sym_baji")
+    return R
+
+
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def dots(xs, y, out=None):
+    """out[k] = <xs[k], y> (plain products, no conjugation) for contiguous tensors."""
+    lib = _lib.load()
+    for t in list(xs) + [y]:
+        if not t.is_contiguous():
+            raise ValueError("dots needs contiguous tensors")
+    if out is None:
+        out = empty(len(xs))
+    ws = scratch().reduce_ws()
+    _lib.check(lib.pmb_dots(len(xs), _ptr_array(xs), _ptr(y), y.numel(), _ptr(out), _ptr(ws), ws.numel() * 8,
+                            _stream()), "pmb_dots")
+    return out
+
+
+def lincomb(coefs, xs, out=None, beta=0.0):
+    """out = beta*out + sum_k coefs[k]*xs[k] for contiguous tensors of one shape."""
+    lib = _lib.load()
+    for t in xs:
+        if not t.is_contiguous():
+            raise ValueError("lincomb needs contiguous tensors")
+    if out is None:
+        out = torch.empty_like(xs[0])
+    done = 0
+    while done < len(xs):
+        chunk = xs[done:done + 16]
+        c = (C.c_double * len(chunk))(*[float(v) for v in coefs[done:done + 16]])
+        _lib.check(lib.pmb_lincomb(len(chunk), c, _ptr_array(chunk), out.numel(),
+                                   float(beta) if done == 0 else 1.0, _ptr(out), _stream()), "pmb_lincomb")
+        done += len(chunk)
+    return out
+
+
+# --------------------------------------------------------------------------
+# N-operand einsum (pairwise evaluation on the DMMA engine)
+# --------------------------------------------------------------------------
+def _pair_result(sa, sb, shared):
+    """Subscripts of contract(sa, sb): keep the bigger operand's order and put the
+    other operand's surviving indices where the first contracted index was."""
+    keep_b = [ch for ch in sb if ch not in shared]
+    out, placed = [], False
+    for ch in sa:
+        if ch in shared:
+            if not placed:
+                out += keep_b
+                placed = True
+        else:
+            out.append(ch)
+    if not placed:
+        out += keep_b
+    return "".join(out)
+
+
+def einsum(spec, *ops, out=None, alpha=1.0, beta=0.0):
+    """out = beta*out + alpha * einsum(spec, *ops) for the class of expressions the
+    coupled-cluster equations use: every index appears exactly twice (in two
+    operands, or in one operand and the output).  Products of more than two
+    operands are evaluated pairwise, smallest intermediate first -- the device
+    counterpart of the reference's ``einsum(..., optimize=True)``."""
+    lhs, so = spec.replace(" ", "").split("->")
+    subs = lhs.split(",")
+    if len(subs) != len(ops):
+        raise ValueError("operand count does not match %s" % spec)
+    items = [[s, asdev(t)] for s, t in zip(subs, ops)]
+    count = {}
+    for s in subs + [so]:
+        for ch in s:
+            count[ch] = count.get(ch, 0) + 1
+    if any(v != 2 for v in count.values()):
+        raise ValueError("every index must appear exactly twice: %s" % spec)
+    ext = {}
+    for s, t in items:
+        for ch, n in zip(s, t.shape):
+            ext[ch] = int(n)
+    if len(items) == 1:
+        s, t = items[0]
+        src = t.permute(*[s.index(ch) for ch in so])
+        return axpby(alpha, src, beta, out)
+    while len(items) > 2:
+        best = None
+        for i in range(len(items)):
+            for j in range(i + 1, len(items)):
+                shared = set(items[i][0]) & set(items[j][0])
+                if not shared:
+                    continue
+                size = 1
+                for ch in (set(items[i][0]) | set(items[j][0])) - shared:
+                    size *= ext[ch]
+                if best is None or size < best[0]:
+                    best = (size, i, j, shared)
+        if best is None:
+            raise ValueError("disconnected product in %s" % spec)
+        _, i, j, shared = best
+        (sa, ta), (sb, tb) = items[i], items[j]
+        if tb.numel() > ta.numel():
+            sa, ta, sb, tb = sb, tb, sa, ta
+        res = _pair_result(sa, sb, shared)
+        tmp = contract_terms(res, [(1.0, sa, ta, sb, tb)])
+        items = [it for n, it in enumerate(items) if n not in (i, j)] + [[res, tmp]]
+    (sa, ta), (sb, tb) = items
+    return contract_terms(so, [(alpha, sa, ta, sb, tb)], out=out, beta=beta)

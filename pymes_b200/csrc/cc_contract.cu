@@ -1,0 +1,480 @@
+// Generic strided binary tensor contraction on the FP64 tensor cores of B200.
+//
+//   C[m,n] = beta*C[m,n] + sum_t alpha_t * sum_k A_t[m,k] * B_t[k,n]
+//
+// m, n, k are composite indices (groups of up to 4 tensor indices each, with
+// per-operand element strides), so every index permutation that the coupled-
+// cluster equations need is expressed by strides and is fused into the tile
+// loads: nothing is ever transposed in HBM.
+//
+// sm_100a has no tcgen05 kind for f64, so FP64 tensor work is issued as
+// warp-level mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).  One DMMA per SM
+// sub-partition every 16 cycles is the hardware peak (64 FMA/clk/SM), which
+// leaves ample issue slots for the gather loads; the kernel is organised so
+// that the DMMA pipe is the only thing that can be busy:
+//   * CTA tile 128x128x16 (8 warps, warp tile 32x64 -> 32 independent
+//     accumulator fragments per warp, no dependent-issue stalls),
+//   * global -> register -> shared double buffering (one __syncthreads per
+//     k-tile), loads for tile t+1 are in flight while tile t is multiplied,
+//   * shared tiles stored [k][x] with a +4 pad so that both the stores (either
+//     thread mapping) and the DMMA fragment loads are bank-conflict free,
+//   * thread->element mapping of the loads follows the operand's unit-stride
+//     direction (x-fast or k-fast) so global accesses stay coalesced to full
+//     32 B sectors for any permutation.
+#include "common.cuh"
+
+namespace pmb {
+
+constexpr int BK = 16;
+constexpr int SPAD = 4;
+
+struct TermDev {
+    const double *A;
+    const double *B;
+    int nk, K;
+    int k_ext[PMB_MAX_DIMS];
+    long long a_kstr[PMB_MAX_DIMS], b_kstr[PMB_MAX_DIMS];
+    long long a_mstr[PMB_MAX_DIMS], b_nstr[PMB_MAX_DIMS];
+    double alpha;
+    int a_kfast, b_kfast;
+    int kt_begin, nkt;
+};
+
+struct Params {
+    int nm, nn, nterms;
+    int M, N;
+    int m_ext[PMB_MAX_DIMS], n_ext[PMB_MAX_DIMS];
+    long long c_mstr[PMB_MAX_DIMS], c_nstr[PMB_MAX_DIMS];
+    double *C;
+    double beta;
+    int tiles_m, tiles_n;
+    int total_ktiles, ktiles_per_split, nsplit;
+    double *ws;
+    TermDev t[PMB_MAX_TERMS];
+};
+
+__device__ __forceinline__ long long decomp(int idx, int nd, const int *ext,
+                                            const long long *str) {
+    long long off = 0;
+#pragma unroll
+    for (int d = 0; d < PMB_MAX_DIMS; ++d) {
+        if (d < nd) {
+            const int e = ext[d];
+            const int q = idx / e;
+            off += (long long)(idx - q * e) * str[d];
+            idx = q;
+        }
+    }
+    return off;
+}
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm volatile(
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c[0]), "+d"(c[1])
+        : "d"(a), "d"(b));
+}
+
+// Load one [BK][BX] operand tile from global memory into registers.
+//   x-fast: consecutive threads walk x (the operand is unit-stride along m/n)
+//   k-fast: every 4 lanes read 4 consecutive k (one 32 B sector), 8 x per warp
+template <int BX, int NT>
+__device__ __forceinline__ void gload(double (&r)[BX * BK / NT], const double *__restrict__ G,
+                                      const long long *s_x, const long long *s_k, int xrem,
+                                      int krem, bool kfast, double alpha, int tid) {
+    constexpr int PER = BX * BK / NT;
+    if (!kfast) {
+        const int x = tid % BX;
+        const int kb = tid / BX;
+        const bool xok = x < xrem;
+        const long long gx = s_x[x];
+#pragma unroll
+        for (int it = 0; it < PER; ++it) {
+            const int kk = it * (NT / BX) + kb;
+            double v = 0.0;
+            if (xok && kk < krem) v = alpha * __ldg(G + gx + s_k[kk]);
+            r[it] = v;
+        }
+    } else {
+        const int lane = tid & 31, warp = tid >> 5;
+        constexpr int KQ = BK / 4;
+        constexpr int NW = NT / 32;
+        static_assert(NW % KQ == 0, "warps must tile the k quads");
+        const int kk = (warp % KQ) * 4 + (lane & 3);
+        const bool kok = kk < krem;
+        const long long gk = s_k[kk];
+#pragma unroll
+        for (int it = 0; it < PER; ++it) {
+            const int x = ((it * NW + warp) / KQ) * 8 + (lane >> 2);
+            double v = 0.0;
+            if (kok && x < xrem) v = alpha * __ldg(G + s_x[x] + gk);
+            r[it] = v;
+        }
+    }
+}
+
+template <int BX, int NT>
+__device__ __forceinline__ void sstore(const double (&r)[BX * BK / NT], double *S, bool kfast,
+                                       int tid) {
+    constexpr int PER = BX * BK / NT;
+    constexpr int LD = BX + SPAD;
+    if (!kfast) {
+        const int x = tid % BX;
+        const int kb = tid / BX;
+#pragma unroll
+        for (int it = 0; it < PER; ++it) S[(it * (NT / BX) + kb) * LD + x] = r[it];
+    } else {
+        const int lane = tid & 31, warp = tid >> 5;
+        constexpr int KQ = BK / 4;
+        constexpr int NW = NT / 32;
+        const int kk = (warp % KQ) * 4 + (lane & 3);
+#pragma unroll
+        for (int it = 0; it < PER; ++it) {
+            const int x = ((it * NW + warp) / KQ) * 8 + (lane >> 2);
+            S[kk * LD + x] = r[it];
+        }
+    }
+}
+
+template <int BM, int BN, int WARPS_M, int WARPS_N, int MINB>
+__global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
+    contract_kernel(const __grid_constant__ Params p) {
+    constexpr int NT = WARPS_M * WARPS_N * 32;
+    constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
+    constexpr int MT = WM / 8, NTL = WN / 8;
+    constexpr int LDA = BM + SPAD, LDB = BN + SPAD;
+    static_assert(NT % BM == 0 && NT % BN == 0, "x-fast mapping needs NT % BX == 0");
+    static_assert((BM * BK) % NT == 0 && (BN * BK) % NT == 0, "tile/threads");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *As = reinterpret_cast<double *>(smem_raw);   // [2][BK][LDA]
+    double *Bs = As + 2 * BK * LDA;                       // [2][BK][LDB]
+    long long *s_am = reinterpret_cast<long long *>(Bs + 2 * BK * LDB);  // [BM]
+    long long *s_bn = s_am + BM;                          // [BN]
+    long long *s_ka = s_bn + BN;                          // [2][BK]
+    long long *s_kb = s_ka + 2 * BK;                      // [2][BK]
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int warp_m = warp % WARPS_M, warp_n = warp / WARPS_M;
+    const int tile_n = blockIdx.x % p.tiles_n, tile_m = blockIdx.x / p.tiles_n;
+    const int m0 = tile_m * BM, n0 = tile_n * BN;
+    const int mrem = p.M - m0, nrem = p.N - n0;
+    const int kt_lo = blockIdx.y * p.ktiles_per_split;
+    const int kt_hi = min(kt_lo + p.ktiles_per_split, p.total_ktiles);
+
+    double acc[MT][NTL][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int ti = 0; ti < p.nterms; ++ti) {
+        const TermDev &t = p.t[ti];
+        const int lo = max(kt_lo, t.kt_begin) - t.kt_begin;
+        const int hi = min(kt_hi, t.kt_begin + t.nkt) - t.kt_begin;
+        if (lo >= hi) continue;  // uniform over the CTA
+        const bool akf = t.a_kfast != 0, bkf = t.b_kfast != 0;
+
+        auto koffs = [&](int kt, int buf) {
+            if (tid < 2 * BK) {
+                const int kk = tid & (BK - 1);
+                const int k = kt * BK + kk;
+                const bool isb = tid >= BK;
+                long long off = 0;
+                if (k < t.K) off = decomp(k, t.nk, t.k_ext, isb ? t.b_kstr : t.a_kstr);
+                (isb ? s_kb : s_ka)[buf * BK + kk] = off;
+            }
+        };
+
+        __syncthreads();  // previous term no longer reads the offset arrays
+        for (int i = tid; i < BM; i += NT)
+            s_am[i] = (i < mrem) ? decomp(m0 + i, p.nm, p.m_ext, t.a_mstr) : 0;
+        for (int i = tid; i < BN; i += NT)
+            s_bn[i] = (i < nrem) ? decomp(n0 + i, p.nn, p.n_ext, t.b_nstr) : 0;
+        koffs(lo, 0);
+        __syncthreads();
+
+        double ra[BM * BK / NT], rb[BN * BK / NT];
+        gload<BM, NT>(ra, t.A, s_am, s_ka, mrem, t.K - lo * BK, akf, t.alpha, tid);
+        gload<BN, NT>(rb, t.B, s_bn, s_kb, nrem, t.K - lo * BK, bkf, 1.0, tid);
+        sstore<BM, NT>(ra, As, akf, tid);
+        sstore<BN, NT>(rb, Bs, bkf, tid);
+        if (lo + 1 < hi) koffs(lo + 1, 1);
+        __syncthreads();
+
+        for (int kt = lo; kt < hi; ++kt) {
+            const int cur = (kt - lo) & 1;
+            const bool more = kt + 1 < hi;
+            if (more) {
+                const int krem = t.K - (kt + 1) * BK;
+                gload<BM, NT>(ra, t.A, s_am, s_ka + (cur ^ 1) * BK, mrem, krem, akf, t.alpha, tid);
+                gload<BN, NT>(rb, t.B, s_bn, s_kb + (cur ^ 1) * BK, nrem, krem, bkf, 1.0, tid);
+            }
+            const double *a = As + cur * BK * LDA + warp_m * WM + (lane >> 2);
+            const double *b = Bs + cur * BK * LDB + warp_n * WN + (lane >> 2);
+#pragma unroll
+            for (int ks = 0; ks < BK / 4; ++ks) {
+                const int row = ks * 4 + (lane & 3);
+                double af[MT], bf[NTL];
+#pragma unroll
+                for (int i = 0; i < MT; ++i) af[i] = a[row * LDA + i * 8];
+#pragma unroll
+                for (int j = 0; j < NTL; ++j) bf[j] = b[row * LDB + j * 8];
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < NTL; ++j) dmma(acc[i][j], af[i], bf[j]);
+            }
+            if (more) {
+                sstore<BM, NT>(ra, As + (cur ^ 1) * BK * LDA, akf, tid);
+                sstore<BN, NT>(rb, Bs + (cur ^ 1) * BK * LDB, bkf, tid);
+                if (kt + 2 < hi) koffs(kt + 2, cur);
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- epilogue -------------------------------------------------------
+    // DMMA C fragment: row = lane/4, cols = 2*(lane%4) + {0,1}
+    if (p.nsplit > 1) {
+        double *ws = p.ws + (size_t)blockIdx.y * (size_t)p.M * (size_t)p.N;
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const int ml = warp_m * WM + i * 8 + (lane >> 2);
+            if (ml >= mrem) continue;
+            double *row = ws + (size_t)(m0 + ml) * (size_t)p.N + n0;
+#pragma unroll
+            for (int j = 0; j < NTL; ++j) {
+                const int nl = warp_n * WN + j * 8 + (lane & 3) * 2;
+                if (nl < nrem) row[nl] = acc[i][j][0];
+                if (nl + 1 < nrem) row[nl + 1] = acc[i][j][1];
+            }
+        }
+        return;
+    }
+    __syncthreads();
+    for (int i = tid; i < BM; i += NT)
+        s_am[i] = (i < mrem) ? decomp(m0 + i, p.nm, p.m_ext, p.c_mstr) : 0;
+    for (int i = tid; i < BN; i += NT)
+        s_bn[i] = (i < nrem) ? decomp(n0 + i, p.nn, p.n_ext, p.c_nstr) : 0;
+    __syncthreads();
+    const bool rd = p.beta != 0.0;
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const int ml = warp_m * WM + i * 8 + (lane >> 2);
+        if (ml >= mrem) continue;
+        double *crow = p.C + s_am[ml];
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) {
+            const int nl = warp_n * WN + j * 8 + (lane & 3) * 2;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (nl + c < nrem) {
+                    double *dst = crow + s_bn[nl + c];
+                    double v = acc[i][j][c];
+                    if (rd) v += p.beta * (*dst);
+                    *dst = v;
+                }
+            }
+        }
+    }
+}
+
+// C[m,n] = beta*C + sum_s ws[s][m][n]  (split-K second stage, fixed order)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constant__ Params p) {
+    const size_t MN = (size_t)p.M * (size_t)p.N;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < MN;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int m = (int)(idx / (size_t)p.N), n = (int)(idx - (size_t)m * p.N);
+        double s = 0.0;
+        for (int k = 0; k < p.nsplit; ++k) s += p.ws[(size_t)k * MN + idx];
+        double *dst = p.C + decomp(m, p.nm, p.m_ext, p.c_mstr) + decomp(n, p.nn, p.n_ext, p.c_nstr);
+        if (p.beta != 0.0) s += p.beta * (*dst);
+        *dst = s;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct TileCfg {
+    int bm, bn, threads;
+    double eff;
+};
+static const TileCfg kCfg[] = {
+    {128, 128, 256, 1.00}, {128, 64, 256, 0.95}, {64, 64, 128, 0.70}, {64, 32, 128, 0.55}};
+constexpr int kNumCfg = 4;
+
+static int g_force_cfg = -1;
+static int g_force_split = 0;
+
+template <int BM, int BN>
+constexpr size_t smem_bytes() {
+    return sizeof(double) * 2 * BK * (BM + SPAD + BN + SPAD) + sizeof(long long) * (BM + BN + 4 * BK);
+}
+
+template <int BM, int BN, int WMW, int WNW, int MINB>
+static int launch_cfg(const Params &p, dim3 grid, cudaStream_t s) {
+    auto kern = contract_kernel<BM, BN, WMW, WNW, MINB>;
+    constexpr size_t sm = smem_bytes<BM, BN>();
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    kern<<<grid, WMW * WNW * 32, sm, s>>>(p);
+    count_launch();
+    return cuda_status();
+}
+
+static bool prod_fits(const int64_t *ext, int n, int64_t *out) {
+    int64_t v = 1;
+    for (int i = 0; i < n; ++i) {
+        if (ext[i] <= 0) return false;
+        v *= ext[i];
+        if (v >= (1LL << 31)) return false;
+    }
+    *out = v;
+    return true;
+}
+
+static int choose_cfg(int64_t M, int64_t N) {
+    if (g_force_cfg >= 0 && g_force_cfg < kNumCfg) return g_force_cfg;
+    int best = 0;
+    double best_cost = 1e300;
+    for (int c = 0; c < kNumCfg; ++c) {
+        const double tiles = (double)((M + kCfg[c].bm - 1) / kCfg[c].bm) * (double)((N + kCfg[c].bn - 1) / kCfg[c].bn);
+        const double per_sm = (kCfg[c].threads == 128) ? 3.0 : 1.0;  // co-resident CTAs
+        const double waves = (double)(int64_t)((tiles + kSmCount * per_sm - 1) / (kSmCount * per_sm));
+        const double cost = waves * per_sm * kCfg[c].bm * kCfg[c].bn / kCfg[c].eff;
+        if (cost < best_cost * 0.999) {
+            best_cost = cost;
+            best = c;
+        }
+    }
+    return best;
+}
+
+static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
+    if (!d || d->nterms < 1 || d->nterms > PMB_MAX_TERMS) return PMB_E_BADARG;
+    if (d->nm < 0 || d->nm > PMB_MAX_DIMS || d->nn < 0 || d->nn > PMB_MAX_DIMS) return PMB_E_BADARG;
+    if (!d->C) return PMB_E_BADARG;
+    int64_t M, N;
+    if (!prod_fits(d->m_ext, d->nm, &M) || !prod_fits(d->n_ext, d->nn, &N)) return PMB_E_BADARG;
+    p.nm = d->nm;
+    p.nn = d->nn;
+    p.nterms = d->nterms;
+    p.M = (int)M;
+    p.N = (int)N;
+    for (int i = 0; i < PMB_MAX_DIMS; ++i) {
+        p.m_ext[i] = i < d->nm ? (int)d->m_ext[i] : 1;
+        p.n_ext[i] = i < d->nn ? (int)d->n_ext[i] : 1;
+        p.c_mstr[i] = i < d->nm ? d->c_mstr[i] : 0;
+        p.c_nstr[i] = i < d->nn ? d->c_nstr[i] : 0;
+    }
+    p.C = d->C;
+    p.beta = d->beta;
+    int kt = 0;
+    for (int ti = 0; ti < d->nterms; ++ti) {
+        const pmb_term_t &s = d->terms[ti];
+        TermDev &t = p.t[ti];
+        if (!s.A || !s.B || s.nk < 0 || s.nk > PMB_MAX_DIMS) return PMB_E_BADARG;
+        int64_t K;
+        if (!prod_fits(s.k_ext, s.nk, &K)) return PMB_E_BADARG;
+        t.A = s.A;
+        t.B = s.B;
+        t.nk = s.nk;
+        t.K = (int)K;
+        for (int i = 0; i < PMB_MAX_DIMS; ++i) {
+            t.k_ext[i] = i < s.nk ? (int)s.k_ext[i] : 1;
+            t.a_kstr[i] = i < s.nk ? s.a_kstr[i] : 0;
+            t.b_kstr[i] = i < s.nk ? s.b_kstr[i] : 0;
+            t.a_mstr[i] = i < d->nm ? s.a_mstr[i] : 0;
+            t.b_nstr[i] = i < d->nn ? s.b_nstr[i] : 0;
+        }
+        t.alpha = s.alpha;
+        // follow the unit-stride direction of each operand
+        auto kfast = [](int nk, const int64_t *kstr, const int64_t *kext, int nx, const int64_t *xstr) {
+            if (nk == 0) return 0;
+            const int64_t ks = kstr[0] < 0 ? -kstr[0] : kstr[0];
+            if (nx == 0) return 1;
+            const int64_t xs = xstr[0] < 0 ? -xstr[0] : xstr[0];
+            if (ks == 1 && kext[0] > 1) return (xs == 1) ? 0 : 1;
+            return ks < xs ? 1 : 0;
+        };
+        t.a_kfast = kfast(s.nk, s.a_kstr, s.k_ext, d->nm, s.a_mstr);
+        t.b_kfast = kfast(s.nk, s.b_kstr, s.k_ext, d->nn, s.b_nstr);
+        t.kt_begin = kt;
+        t.nkt = (t.K + BK - 1) / BK;
+        kt += t.nkt;
+    }
+    p.total_ktiles = kt;
+    cfg = choose_cfg(M, N);
+    p.tiles_m = (int)((M + kCfg[cfg].bm - 1) / kCfg[cfg].bm);
+    p.tiles_n = (int)((N + kCfg[cfg].bn - 1) / kCfg[cfg].bn);
+    // split-K when the output has too few tiles to fill the machine
+    int nsplit = 1;
+    const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
+    if (g_force_split > 0) {
+        nsplit = g_force_split;
+    } else if (tiles * 2 <= kSmCount && kt >= 8) {
+        nsplit = (int)((kSmCount + tiles - 1) / tiles);
+        if (nsplit > kt / 4) nsplit = kt / 4;
+        if (nsplit > 64) nsplit = 64;
+    }
+    if (nsplit > kt) nsplit = kt;
+    if (nsplit < 1) nsplit = 1;
+    p.ktiles_per_split = (kt + nsplit - 1) / nsplit;
+    p.nsplit = (kt + p.ktiles_per_split - 1) / p.ktiles_per_split;
+    p.ws = nullptr;
+    return 0;
+}
+
+}  // namespace pmb
+
+using namespace pmb;
+
+extern "C" void pmb_contract_set_tuning(int tile_config, int split_k) {
+    g_force_cfg = tile_config;
+    g_force_split = split_k;
+}
+
+extern "C" size_t pmb_contract_workspace(const pmb_contract_t *d) {
+    Params p;
+    int cfg;
+    if (build_params(d, p, cfg) != 0) return 0;
+    if (p.nsplit <= 1) return 0;
+    return sizeof(double) * (size_t)p.nsplit * (size_t)p.M * (size_t)p.N;
+}
+
+extern "C" int pmb_contract(const pmb_contract_t *d, void *ws, size_t ws_bytes, pmb_stream_t stream) {
+    Params p;
+    int cfg;
+    int rc = build_params(d, p, cfg);
+    if (rc != 0) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p.nsplit > 1) {
+        const size_t need = sizeof(double) * (size_t)p.nsplit * (size_t)p.M * (size_t)p.N;
+        if (!ws || ws_bytes < need) return PMB_E_WORKSPACE;
+        p.ws = (double *)ws;
+    }
+    dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)p.nsplit, 1);
+    switch (cfg) {
+        case 0: rc = launch_cfg<128, 128, 4, 2, 1>(p, grid, s); break;
+        case 1: rc = launch_cfg<128, 64, 4, 2, 1>(p, grid, s); break;
+        case 2: rc = launch_cfg<64, 64, 2, 2, 3>(p, grid, s); break;
+        default: rc = launch_cfg<64, 32, 2, 2, 3>(p, grid, s); break;
+    }
+    if (rc != 0) return rc;
+    if (p.nsplit > 1) {
+        const size_t MN = (size_t)p.M * p.N;
+        int blocks = (int)((MN + 255) / 256);
+        if (blocks > 4 * kSmCount) blocks = 4 * kSmCount;
+        splitk_reduce_kernel<<<blocks, 256, 0, s>>>(p);
+        count_launch();
+        rc = cuda_status();
+    }
+    return rc;
+}

@@ -1,0 +1,372 @@
+// HBM-bound elementwise / reduction kernels of the coupled-cluster iteration:
+// MP2 start amplitudes, fused amplitude update, energy, T-tilde, the
+// Ex + Ex^{baji} permutation-add, DIIS dot products and linear combinations.
+// All of them are one pass over T2-sized data with coalesced accesses along the
+// fastest (ij) index; reductions are deterministic (two fixed-order stages).
+#include "common.cuh"
+
+namespace pmb {
+
+long long g_launch_count = 0;
+
+__global__ void finish_reduce_kernel(const double *ws, int nblocks, int ns, double *out,
+                                     int accumulate) {
+    __shared__ double sh[kMaxScalars][kReduceThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = 0; k < ns; ++k) {
+        double x = 0.0;
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) x += ws[(size_t)b * ns + k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) sh[k][warp] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < ns) {
+        double x = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) x += sh[threadIdx.x][w];
+        out[threadIdx.x] = accumulate ? out[threadIdx.x] + x : x;
+    }
+}
+
+int finish_reduce(const double *ws, int nblocks, int ns, double *out, int accumulate,
+                  cudaStream_t s) {
+    finish_reduce_kernel<<<1, kReduceThreads, 0, s>>>(ws, nblocks, ns, out, accumulate);
+    count_launch();
+    return cuda_status();
+}
+
+static inline int grid_for(size_t n, int threads, int cap) {
+    size_t b = (n + threads - 1) / threads;
+    if (b > (size_t)cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// ---------------------------------------------------------------------------
+struct Str4 {
+    long long e[4];
+    long long si[4];
+    long long so[4];
+};
+
+__global__ void __launch_bounds__(256) axpby4_kernel(Str4 g, double alpha, const double *__restrict__ in,
+                                                     double beta, double *out) {
+    const size_t n = (size_t)g.e[0] * g.e[1] * g.e[2] * g.e[3];
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        size_t r = idx;
+        const long long i3 = r % g.e[3];
+        r /= g.e[3];
+        const long long i2 = r % g.e[2];
+        r /= g.e[2];
+        const long long i1 = r % g.e[1];
+        const long long i0 = r / g.e[1];
+        const double v = alpha * in[i0 * g.si[0] + i1 * g.si[1] + i2 * g.si[2] + i3 * g.si[3]];
+        double *d = out + i0 * g.so[0] + i1 * g.so[1] + i2 * g.so[2] + i3 * g.so[3];
+        *d = (beta != 0.0) ? v + beta * (*d) : v;
+    }
+}
+
+// T2 = V_abij / (e_i + e_j - e_a - e_b + shift)
+__global__ void __launch_bounds__(256)
+    mp2_kernel(int no, int nv, const double *__restrict__ ei, const double *__restrict__ ea, double shift,
+               const double *__restrict__ V, Str4 g, double *__restrict__ T2) {
+    const size_t n = (size_t)nv * nv * no * no;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        size_t r = idx;
+        const int j = r % no;
+        r /= no;
+        const int i = r % no;
+        r /= no;
+        const int b = r % nv;
+        const int a = (int)(r / nv);
+        const double d = ei[i] + ei[j] - ea[a] - ea[b] + shift;
+        T2[idx] = V[a * g.si[0] + b * g.si[1] + i * g.si[2] + j * g.si[3]] / d;
+    }
+}
+
+// dT = R * (1/D); T += delta*dT; partial sum of dT^2
+__global__ void __launch_bounds__(kReduceThreads)
+    update_doubles_kernel(int no, int nv, const double *__restrict__ ei, const double *__restrict__ ea,
+                          double shift, double delta, const double *__restrict__ R, double *__restrict__ dT,
+                          double *__restrict__ T2, double *ws) {
+    const size_t n = (size_t)nv * nv * no * no;
+    double s[1] = {0.0};
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        size_t r = idx;
+        const int j = r % no;
+        r /= no;
+        const int i = r % no;
+        r /= no;
+        const int b = r % nv;
+        const int a = (int)(r / nv);
+        const double dinv = 1.0 / (ei[i] + ei[j] - ea[a] - ea[b] + shift);
+        const double d = R[idx] * dinv;
+        dT[idx] = d;
+        T2[idx] += delta * d;
+        s[0] += d * d;
+    }
+    block_reduce_store<1>(s, ws);
+}
+
+__global__ void __launch_bounds__(256)
+    update_singles_kernel(int no, int nv, const double *__restrict__ ei, const double *__restrict__ ea,
+                          double shift, double delta, const double *__restrict__ R1, double *__restrict__ dT1,
+                          double *__restrict__ T1) {
+    const int n = nv * no;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const int i = idx % no, a = idx / no;
+        const double d = R1[idx] * (1.0 / (ei[i] - ea[a] + shift));
+        dT1[idx] = d;
+        T1[idx] += delta * d;
+    }
+}
+
+// energy: one CTA handles a set of (a,b) pairs; for each pair the o x o block
+// of T2 is contiguous, V[i,j,a,b] and V[i,j,b,a] are gathered.
+__global__ void __launch_bounds__(kReduceThreads)
+    energy_kernel(int no, int nv, const double *__restrict__ T2, const double *__restrict__ T1,
+                  const double *__restrict__ V, Str4 g, int mp2_form, double *ws) {
+    const size_t n = (size_t)nv * nv * no * no;
+    double s[3] = {0.0, 0.0, 0.0};
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        size_t r = idx;
+        const int j = r % no;
+        r /= no;
+        const int i = r % no;
+        r /= no;
+        const int b = r % nv;
+        const int a = (int)(r / nv);
+        const double t = T2[idx];
+        double tau = t;
+        if (T1) tau += T1[a * no + i] * T1[b * no + j];
+        const double vd = V[i * g.si[0] + j * g.si[1] + a * g.si[2] + b * g.si[3]];
+        // exchange: ccd.py:261 uses V[i,j,b,a]; mp2.py:20 uses V[j,i,a,b]
+        const double vx = mp2_form ? V[j * g.si[0] + i * g.si[1] + a * g.si[2] + b * g.si[3]]
+                                   : V[i * g.si[0] + j * g.si[1] + b * g.si[2] + a * g.si[3]];
+        s[0] += tau * vd;
+        s[1] += tau * vx;
+        s[2] += t * t;
+    }
+    block_reduce_store<3>(s, ws);
+}
+
+__global__ void scale3_kernel(double *scal) {
+    if (threadIdx.x == 0) {
+        scal[0] *= 2.0;
+        scal[1] *= -1.0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    tilde_kernel(int no, int nv, const double *__restrict__ T2, double *__restrict__ Tt, int swap_ij) {
+    const size_t n = (size_t)nv * nv * no * no;
+    const size_t oo = (size_t)no * no;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t ij = idx % oo;
+        const size_t ab = idx / oo;
+        size_t src;
+        if (swap_ij) {
+            const size_t i = ij / no, j = ij % no;
+            src = ab * oo + j * no + i;
+        } else {
+            const size_t a = ab / nv, b = ab % nv;
+            src = (b * nv + a) * oo + ij;
+        }
+        Tt[idx] = 2.0 * T2[idx] - T2[src];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    sym_baji_kernel(int no, int nv, const double *__restrict__ Ex, double *__restrict__ R, int accumulate) {
+    const size_t n = (size_t)nv * nv * no * no;
+    const size_t oo = (size_t)no * no;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t ij = idx % oo, ab = idx / oo;
+        const size_t i = ij / no, j = ij % no;
+        const size_t a = ab / nv, b = ab % nv;
+        const double v = Ex[idx] + Ex[(b * nv + a) * oo + j * no + i];
+        R[idx] = accumulate ? R[idx] + v : v;
+    }
+}
+
+constexpr int kMaxVec = 16;
+struct VecList {
+    const double *p[kMaxVec];
+    double c[kMaxVec];
+};
+
+template <int NV>
+__global__ void __launch_bounds__(kReduceThreads)
+    dots_kernel(VecList L, const double *__restrict__ Y, size_t n, double *ws) {
+    double s[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s[k] = 0.0;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const double y = Y[idx];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) s[k] += L.p[k][idx] * y;
+    }
+    block_reduce_store<NV>(s, ws);
+}
+
+__global__ void __launch_bounds__(256)
+    lincomb_kernel(VecList L, int nvec, size_t n, double beta, double *__restrict__ out) {
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        double v = (beta != 0.0) ? beta * out[idx] : 0.0;
+        for (int k = 0; k < nvec; ++k) v += L.c[k] * L.p[k][idx];
+        out[idx] = v;
+    }
+}
+
+static Str4 make_str(const int64_t ext[4], const int64_t in_str[4], const int64_t out_str[4]) {
+    Str4 g;
+    for (int d = 0; d < 4; ++d) {
+        g.e[d] = ext ? ext[d] : 0;
+        g.si[d] = in_str ? in_str[d] : 0;
+        g.so[d] = out_str ? out_str[d] : 0;
+    }
+    return g;
+}
+
+}  // namespace pmb
+
+using namespace pmb;
+
+extern "C" size_t pmb_reduce_workspace(void) {
+    return sizeof(double) * (size_t)kReduceBlocks * kMaxVec;
+}
+
+extern "C" int pmb_axpby4(const int64_t ext[4], double alpha, const double *in, const int64_t in_str[4],
+                          double beta, double *out, const int64_t out_str[4], pmb_stream_t stream) {
+    if (!ext || !in || !out || !in_str || !out_str) return PMB_E_BADARG;
+    size_t n = 1;
+    for (int d = 0; d < 4; ++d) {
+        if (ext[d] <= 0) return PMB_E_BADARG;
+        n *= (size_t)ext[d];
+    }
+    axpby4_kernel<<<grid_for(n, 256, 16 * kSmCount), 256, 0, (cudaStream_t)stream>>>(
+        make_str(ext, in_str, out_str), alpha, in, beta, out);
+    count_launch();
+    return cuda_status();
+}
+
+extern "C" int pmb_mp2_amplitudes(int no, int nv, const double *eps_i, const double *eps_a, double shift,
+                                  const double *V_abij, const int64_t v_str[4], double *T2,
+                                  pmb_stream_t stream) {
+    if (no <= 0 || nv <= 0 || !eps_i || !eps_a || !V_abij || !v_str || !T2) return PMB_E_BADARG;
+    const size_t n = (size_t)nv * nv * no * no;
+    mp2_kernel<<<grid_for(n, 256, 16 * kSmCount), 256, 0, (cudaStream_t)stream>>>(
+        no, nv, eps_i, eps_a, shift, V_abij, make_str(nullptr, v_str, nullptr), T2);
+    count_launch();
+    return cuda_status();
+}
+
+extern "C" int pmb_update_doubles(int no, int nv, const double *eps_i, const double *eps_a, double shift,
+                                  double delta, const double *R, double *dT, double *T2, double *scal,
+                                  void *ws, size_t ws_bytes, pmb_stream_t stream) {
+    if (no <= 0 || nv <= 0 || !eps_i || !eps_a || !R || !dT || !T2 || !scal) return PMB_E_BADARG;
+    if (!ws || ws_bytes < pmb_reduce_workspace()) return PMB_E_WORKSPACE;
+    const size_t n = (size_t)nv * nv * no * no;
+    const int blocks = grid_for(n, kReduceThreads, kReduceBlocks);
+    update_doubles_kernel<<<blocks, kReduceThreads, 0, (cudaStream_t)stream>>>(
+        no, nv, eps_i, eps_a, shift, delta, R, dT, T2, (double *)ws);
+    count_launch();
+    int rc = cuda_status();
+    if (rc) return rc;
+    return finish_reduce((double *)ws, blocks, 1, scal, 0, (cudaStream_t)stream);
+}
+
+extern "C" int pmb_update_singles(int no, int nv, const double *eps_i, const double *eps_a, double shift,
+                                  double delta, const double *R1, double *dT1, double *T1,
+                                  pmb_stream_t stream) {
+    if (no <= 0 || nv <= 0 || !eps_i || !eps_a || !R1 || !dT1 || !T1) return PMB_E_BADARG;
+    update_singles_kernel<<<grid_for((size_t)nv * no, 256, kSmCount), 256, 0, (cudaStream_t)stream>>>(
+        no, nv, eps_i, eps_a, shift, delta, R1, dT1, T1);
+    count_launch();
+    return cuda_status();
+}
+
+extern "C" int pmb_energy_doubles(int no, int nv, const double *T2, const double *T1, const double *V_ijab,
+                                  const int64_t v_str[4], int mp2_form, double *scal, void *ws,
+                                  size_t ws_bytes, pmb_stream_t stream) {
+    if (no <= 0 || nv <= 0 || !T2 || !V_ijab || !v_str || !scal) return PMB_E_BADARG;
+    if (!ws || ws_bytes < pmb_reduce_workspace()) return PMB_E_WORKSPACE;
+    const size_t n = (size_t)nv * nv * no * no;
+    const int blocks = grid_for(n, kReduceThreads, kReduceBlocks);
+    energy_kernel<<<blocks, kReduceThreads, 0, (cudaStream_t)stream>>>(
+        no, nv, T2, T1, V_ijab, make_str(nullptr, v_str, nullptr), mp2_form, (double *)ws);
+    count_launch();
+    int rc = cuda_status();
+    if (rc) return rc;
+    rc = finish_reduce((double *)ws, blocks, 3, scal, 0, (cudaStream_t)stream);
+    if (rc) return rc;
+    scale3_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scal);
+    count_launch();
+    return cuda_status();
+}
+
+extern "C" int pmb_tilde(int no, int nv, const double *T2, double *Tt, int swap_ij, pmb_stream_t stream) {
+    if (no <= 0 || nv <= 0 || !T2 || !Tt || T2 == Tt) return PMB_E_BADARG;
+    const size_t n = (size_t)nv * nv * no * no;
+    tilde_kernel<<<grid_for(n, 256, 16 * kSmCount), 256, 0, (cudaStream_t)stream>>>(no, nv, T2, Tt, swap_ij);
+    count_launch();
+    return cuda_status();
+}
+
+extern "C" int pmb_sym_baji(int no, int nv, const double *Ex, double *R, int accumulate,
+                            pmb_stream_t stream) {
+    if (no <= 0 || nv <= 0 || !Ex || !R || Ex == R) return PMB_E_BADARG;
+    const size_t n = (size_t)nv * nv * no * no;
+    sym_baji_kernel<<<grid_for(n, 256, 16 * kSmCount), 256, 0, (cudaStream_t)stream>>>(no, nv, Ex, R, accumulate);
+    count_launch();
+    return cuda_status();
+}
+
+extern "C" int pmb_dots(int nvec, const double *const *X, const double *Y, int64_t n, double *out,
+                        void *ws, size_t ws_bytes, pmb_stream_t stream) {
+    if (nvec < 1 || nvec > kMaxVec || !X || !Y || n <= 0 || !out) return PMB_E_BADARG;
+    if (!ws || ws_bytes < pmb_reduce_workspace()) return PMB_E_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int blocks = grid_for((size_t)n, kReduceThreads, kReduceBlocks);
+    int done = 0;
+    while (done < nvec) {  // chunks of up to 4 vectors share one pass over Y
+        VecList L;
+        const int c = (nvec - done >= 4) ? 4 : (nvec - done);
+        for (int k = 0; k < c; ++k) L.p[k] = X[done + k];
+        switch (c) {
+            case 4: dots_kernel<4><<<blocks, kReduceThreads, 0, s>>>(L, Y, (size_t)n, (double *)ws); break;
+            case 3: dots_kernel<3><<<blocks, kReduceThreads, 0, s>>>(L, Y, (size_t)n, (double *)ws); break;
+            case 2: dots_kernel<2><<<blocks, kReduceThreads, 0, s>>>(L, Y, (size_t)n, (double *)ws); break;
+            default: dots_kernel<1><<<blocks, kReduceThreads, 0, s>>>(L, Y, (size_t)n, (double *)ws); break;
+        }
+        count_launch();
+        int rc = cuda_status();
+        if (rc) return rc;
+        rc = finish_reduce((double *)ws, blocks, c, out + done, 0, s);
+        if (rc) return rc;
+        done += c;
+    }
+    return 0;
+}
+
+extern "C" int pmb_lincomb(int nvec, const double *c_host, const double *const *X, int64_t n, double beta,
+                           double *out, pmb_stream_t stream) {
+    if (nvec < 1 || nvec > kMaxVec || !c_host || !X || n <= 0 || !out) return PMB_E_BADARG;
+    VecList L;
+    for (int k = 0; k < nvec; ++k) {
+        L.p[k] = X[k];
+        L.c[k] = c_host[k];
+    }
+    lincomb_kernel<<<grid_for((size_t)n, 256, 16 * kSmCount), 256, 0, (cudaStream_t)stream>>>(
+        L, nvec, (size_t)n, beta, out);
+    count_launch();
+    return cuda_status();
+}

@@ -1,0 +1,336 @@
+"""3D uniform electron gas: plane-wave basis and momentum-conserving integrals.
+
+Call surface of the reference ``pymes.model.ueg.UEG`` (pymes/model/ueg.py:12-516):
+``UEG(n_ele, n_alpha, n_beta, rs)``, ``init_single_basis(cutoff, k_shift)``,
+``eval_2b_integrals(correlator, is_*..., dtype, sp)``, the attributes ``basis_fns, L,
+Omega, gamma, k_cutoff, imax, basis_indices_map, correlator`` and the correlators
+as bound methods.
+
+The basis is generated on the host in the reference's floating-point arithmetic
+(shell membership at the cutoff and the order inside degenerate shells depend
+on it).  The integral build runs on the device in three steps
+(``pmb_ueg_umat`` -> ``pmb_ueg_pair_tables`` -> ``pmb_ueg_build_block``), see
+include/pymes_b200.h; ``eval_2b_blocks`` builds named sub-blocks directly so that
+V_pqrs never has to exist for systems where it would not fit.
+"""
+import ctypes as C
+import time
+import warnings
+
+import numpy as np
+import torch
+from scipy import special
+
+from .. import _lib
+from .. import backend as bk
+from ..basis_set import planewave
+from ..integral.partition import OCCUPIED
+from ..log import print_logging_info
+
+MODES = {"coulomb": 0, "rpa": 1, "only_2b": 2, "only_hermi_2b": 3, "only_non_hermi_2b": 4,
+         "effect_2b": 5, "exchange_1": 6, "exchange_2": 7, "exchange_3": 8}
+
+
+class UEG:
+    def __init__(self, n_ele, n_alpha, n_beta, rs):
+        if n_ele % 2 != 0 or int(n_alpha) != int(n_beta):
+            warnings.warn("The number of electrons is not even, currently only "
+                          "closed shell systems are supported!")
+        self.n_ele = int(n_ele)
+        self.n_alpha = int(n_alpha)
+        self.n_beta = int(n_beta)
+        self.rs = rs
+        self.L = self.rs * ((4 * np.pi * self.n_ele) / 3) ** (1.0 / 3.0)     # ueg.py:66
+        self.Omega = self.L ** 3
+        self.basis_fns = None
+        self.imax = 0
+        self.cutoff = 0.
+        self.basis_indices_map = None
+        self.kPrime = None
+        self.correlator = None
+        self.k_cutoff = None
+        self.gamma = None
+        self._dev = None
+
+    # ------------------------------------------------------------------ basis
+    def is_k_in_basis(self, ke):
+        return bool(ke <= self.cutoff * (2 * np.pi / self.L) ** 2 / 2.)      # ueg.py:100-103
+
+    def init_basis_indices_map(self):
+        n = self.imax * 2 + 1
+        table = -1 * np.ones(n ** 3).astype(int)
+        for i in range(len(self.basis_fns) // 2):
+            k = self.basis_fns[2 * i].k
+            table[n * n * (k[0] + self.imax) + n * (k[1] + self.imax) + k[2] + self.imax] = i
+        self.basis_indices_map = table
+
+    def init_single_basis(self, cutoff, k_shift=[0., 0., 0.]):
+        k_shift = np.array(k_shift)
+        imax = int(np.ceil(np.sqrt(cutoff + k_shift.dot(k_shift)))) + 1      # ueg.py:153
+        self.cutoff = cutoff
+        self.imax = imax
+        fns = []
+        rng = range(-imax, imax + 1)
+        for i in rng:
+            for j in rng:
+                for k in rng:
+                    up = planewave.BasisFunc(i, j, k, self.L, 1, k_shift)
+                    if self.is_k_in_basis(up.kinetic):
+                        fns.append(up)
+                        fns.append(planewave.BasisFunc(i, j, k, self.L, -1, k_shift))
+        fns.sort()                                   # stable, key = kinetic (planewave.py:25-26)
+        self.basis_fns = tuple(fns)
+        self.init_basis_indices_map()
+        self._dev = None
+        return self.basis_fns
+
+    @property
+    def n_orb(self):
+        return len(self.basis_fns) // 2
+
+    def k_int(self):
+        return np.array([self.basis_fns[2 * i].k for i in range(self.n_orb)], dtype=np.int32)
+
+    def k_float(self):
+        return np.array([self.basis_fns[2 * i].kp for i in range(self.n_orb)], dtype=np.float64)
+
+    def kinetic(self):
+        return np.array([self.basis_fns[2 * i].kinetic for i in range(self.n_orb)])
+
+    # --------------------------------------------------------- device build
+    def _device_state(self):
+        if self._dev is None:
+            dev = bk.device()
+            self._dev = dict(
+                kvec=torch.from_numpy(self.k_int().reshape(-1)).to(dev),
+                kp=torch.from_numpy(self.k_float().reshape(-1)).to(dev),
+                imap=torch.from_numpy(self.basis_indices_map.astype(np.int32)).to(dev))
+        return self._dev
+
+    def _descriptor(self, u_table=None):
+        st = self._device_state()
+        d = _lib.Ueg()
+        d.n_orb, d.imax, d.n_occ, d.n_ele = self.n_orb, self.imax, self.n_ele // 2, self.n_ele
+        d.omega = self.Omega
+        d.u_table = u_table.data_ptr() if u_table is not None else None
+        d.u_table_len = u_table.numel() if u_table is not None else 0
+        d.kvec, d.kp, d.index_map = st["kvec"].data_ptr(), st["kp"].data_ptr(), st["imap"].data_ptr()
+        return d
+
+    def _correlator_table(self, correlator, lattice_cutoff):
+        """u(n2 (2 pi/L)^2) for every integer n2 = |k|^2 the build can ask for."""
+        kmax = int(np.abs(self.k_int()).max())
+        reach = lattice_cutoff + 3 * kmax + 1
+        n2 = np.arange(3 * reach * reach + 1, dtype=np.float64)
+        vals = np.asarray(correlator(n2 * (2 * np.pi / self.L) ** 2), dtype=np.float64)
+        return torch.from_numpy(np.ascontiguousarray(vals)).to(bk.device())
+
+    def pair_tables(self, mode, correlator=None, lattice_cutoff=30):
+        """(W0, W1, descriptor keep-alives) for one branch of ueg.py:411-504."""
+        lib = _lib.load()
+        nP = self.n_orb
+        u_table = None
+        if mode != "coulomb":
+            if correlator is None:
+                raise ValueError("mode %s needs a correlator" % mode)
+            self.correlator = correlator
+            u_table = self._correlator_table(correlator, lattice_cutoff)
+        desc = self._descriptor(u_table)
+        umat_pr = None
+        if mode in ("only_2b", "only_hermi_2b"):
+            k = self.k_int().astype(np.int64)
+            q = (k[None, :, :] - k[:, None, :]).reshape(-1, 3)          # q[p*nP+r] = k_r - k_p
+            uniq, inverse = np.unique(q, axis=0, return_inverse=True)
+            qdev = torch.from_numpy(uniq.astype(np.int32).reshape(-1)).to(bk.device())
+            umat_q = bk.empty(len(uniq))
+            _lib.check(lib.pmb_ueg_umat(C.byref(desc), float(self.L), int(lattice_cutoff), len(uniq),
+                                        bk._ptr(qdev), bk._ptr(umat_q), bk._stream()), "pmb_ueg_umat")
+            idx = torch.from_numpy(inverse.reshape(-1).astype(np.int64)).to(bk.device())
+            umat_pr = umat_q[idx].contiguous()
+        W0, W1 = bk.empty(nP * nP), bk.empty(nP * nP)
+        _lib.check(lib.pmb_ueg_pair_tables(C.byref(desc), MODES[mode],
+                                           bk._ptr(umat_pr) if umat_pr is not None else None,
+                                           bk._ptr(W0), bk._ptr(W1), bk._stream()), "pmb_ueg_pair_tables")
+        return W0, W1
+
+    def build_block(self, lo, ext, W0a=None, W1a=None, W0s=None, out=None):
+        """Dense block V[lo:lo+ext] from pair tables (device tensor [ext0,ext1,ext2,ext3])."""
+        lib = _lib.load()
+        if out is None:
+            out = bk.empty(*ext)
+        desc = self._descriptor()
+        p = lambda t: bk._ptr(t) if t is not None else None
+        _lib.check(lib.pmb_ueg_build_block(C.byref(desc), p(W0a), p(W1a), p(W0s), _lib.I32x4(*lo),
+                                           _lib.I32x4(*ext), bk._ptr(out), bk._stream()),
+                   "pmb_ueg_build_block")
+        return out
+
+    def _mode_of(self, correlator, is_rpa_approx, is_only_2b, is_only_non_hermi_2b, is_only_hermi_2b,
+                 is_effect_2b, is_exchange_1, is_exchange_2, is_exchange_3):
+        if correlator is None:
+            return "coulomb"
+        for flag, name in ((is_rpa_approx, "rpa"), (is_only_2b, "only_2b"),
+                           (is_only_hermi_2b, "only_hermi_2b"),
+                           (is_only_non_hermi_2b, "only_non_hermi_2b"), (is_effect_2b, "effect_2b"),
+                           (is_exchange_1, "exchange_1"), (is_exchange_2, "exchange_2"),
+                           (is_exchange_3, "exchange_3")):
+            if flag:                       # same precedence as the elif chain ueg.py:411-504
+                return name
+        return None
+
+    def eval_2b_integrals(self, correlator=None, is_rpa_approx=False, is_only_2b=False,
+                          is_only_non_hermi_2b=False, is_only_hermi_2b=False, is_effect_2b=False,
+                          is_exchange_1=False, is_exchange_2=False, is_exchange_3=False,
+                          dtype=np.float64, sp=1, device=False):
+        """Dense V_pqrs [nP,nP,nP,nP] (numpy by default, CUDA tensor with ``device=True``)."""
+        t0 = time.time()
+        print_logging_info(__name__, level=0)
+        if self.basis_fns is None:
+            raise ValueError("Basis functions not initialized!")
+        if correlator is not None:
+            self.correlator = correlator
+            print_logging_info("Using TC method", level=1)
+            print_logging_info("Using correlator: ", correlator.__name__, level=1)
+        mode = self._mode_of(correlator, is_rpa_approx, is_only_2b, is_only_non_hermi_2b,
+                             is_only_hermi_2b, is_effect_2b, is_exchange_1, is_exchange_2, is_exchange_3)
+        nP = self.n_orb
+        if mode is None:                   # correlator given but no branch selected: all zeros
+            V = bk.zeros(nP, nP, nP, nP)
+        else:
+            W0, W1 = self.pair_tables(mode, correlator)
+            if mode == "effect_2b":        # symmetrised under (pq)(rs)<->(qp)(sr), ueg.py:509-513
+                V = self.build_block((0,) * 4, (nP,) * 4, W0s=W0)
+            else:
+                V = self.build_block((0,) * 4, (nP,) * 4, W0a=W0, W1a=W1)
+        if correlator is not None:
+            if self.k_cutoff is not None:
+                print_logging_info("k_cutoff in correlator = {:.8f}".format(self.k_cutoff), level=1)
+            if self.gamma is not None:
+                print_logging_info("Gamma in correlator = {:.8f}".format(self.gamma), level=1)
+        out = V if device else V.cpu().numpy().astype(dtype, copy=False)
+        print_logging_info("{:.3f} s spent on ".format(time.time() - t0) + __name__, level=1)
+        return out
+
+    def eval_2b_blocks(self, no, keys, parts):
+        """Named sub-blocks (partition.py keys, e.g. "abcd") of a SUM of integral kinds,
+        built directly on the device: ``parts`` is a list of ``(mode, correlator)``;
+        ``effect_2b`` parts enter symmetrised exactly as in
+        test_symmetrised_2body_integral.py:141-145.  Returns ``{key: cuda tensor}``."""
+        nP = self.n_orb
+        tabs = []
+        for mode, corr in parts:
+            W0, W1 = self.pair_tables(mode, corr)
+            tabs.append((mode, W0, W1))
+        plain = [t for t in tabs if t[0] != "effect_2b"]
+        sym = [t for t in tabs if t[0] == "effect_2b"]
+        W0a = W1a = W0s = None
+        if plain:
+            W0a = plain[0][1] if len(plain) == 1 else bk.lincomb([1.0] * len(plain), [t[1] for t in plain])
+            W1a = plain[0][2] if len(plain) == 1 else bk.lincomb([1.0] * len(plain), [t[2] for t in plain])
+        if sym:
+            W0s = sym[0][1] if len(sym) == 1 else bk.lincomb([1.0] * len(sym), [t[1] for t in sym])
+        out = {}
+        for key in keys:
+            lo = tuple(0 if ch in OCCUPIED else no for ch in key)
+            ext = tuple(no if ch in OCCUPIED else nP - no for ch in key)
+            out[key] = self.build_block(lo, ext, W0a=W0a, W1a=W1a, W0s=W0s)
+        return out
+
+    # ------------------------------------------------- 3-body mean-field parts
+    def _occupied_k(self):
+        return self.k_float()[: self.n_ele // 2]
+
+    def triple_contractions_in_3_body(self):
+        """Scalar mean-field energy of the 3-body operator (ueg.py:598-630)."""
+        ki = self._occupied_k()
+        d = ki[:, None, :] - ki[None, :, :]
+        d2 = np.einsum("pqi,pqi->pq", d, d)
+        u = self.correlator(d2.copy())
+        direct = np.sum(u ** 2 * d2) * self.n_ele / 2 / self.Omega ** 2 * 2
+        dots = np.einsum("poi,pqi->pqo", d, d)
+        exch = -2 * 2 * np.einsum("pqo,pq,po->", dots, u, u) / 2. / self.Omega ** 2
+        return direct + exch
+
+    def double_contractions_in_3_body(self):
+        """One-body energies from doubly contracted 3-body terms (ueg.py:632-733)."""
+        kp, ki = self.k_float(), self._occupied_k()
+        dpi = kp[:, None, :] - ki[None, :, :]                    # p - i
+        dpi2 = np.einsum("pij,pij->pi", dpi, dpi)
+        upi = self.correlator(dpi2.copy())
+        perl = 2.0 * self.n_ele / self.Omega ** 2 / 2 * np.sum(upi ** 2 * dpi2, axis=1)
+        wave = -np.einsum("pik,pjk,pi,pj->p", dpi, dpi, upi, upi) * 2 / self.Omega ** 2 / 2
+        dij = ki[:, None, :] - ki[None, :, :]
+        dij2 = np.einsum("ijk,ijk->ij", dij, dij)
+        uij = self.correlator(dij2.copy())
+        shield = np.ones(len(kp)) * np.sum(uij ** 2 * dij2) * 2 / 2 / self.Omega ** 2
+        frog = -np.einsum("ijk,pik,ij,pi->p", dij, -dpi, uij, upi) * 4 / self.Omega ** 2 / 2
+        return perl + wave + shield + frog
+
+    # ------------------------------------------------------------ correlators
+    # u(k^2); scalar or array argument.  ueg.py:740-956
+    def _defaults(self, gamma):
+        if self.k_cutoff is None:
+            self.k_cutoff = int(np.ceil(np.sqrt(self.cutoff)))
+        if self.gamma is None:
+            self.gamma = gamma
+
+    def trunc(self, kSquare):
+        """-4 pi gamma / k^4 for k > k_c, else 0 (ueg.py:772-800)."""
+        self._defaults(1.0)
+        kc2 = (self.k_cutoff * 2 * np.pi / self.L) ** 2
+        k2 = np.array(kSquare, dtype=np.float64, copy=True)
+        k2[k2 <= kc2 * (1 + 0.00001)] = 0.
+        res = np.divide(-4. * np.pi, k2 ** 2, out=np.zeros_like(k2), where=(k2 > 1e-12)) * self.gamma
+        return res if isinstance(kSquare, np.ndarray) else float(res)
+
+    def coulomb(self, kSquare, multiply_by_k_square=False):
+        g = 1. if self.gamma is None else self.gamma
+        k2 = np.asarray(kSquare, dtype=np.float64)
+        return np.divide(-4. * np.pi * g, k2, out=np.zeros_like(k2), where=k2 > 1e-12)
+
+    def smooth(self, kSquare, multiply_by_k_square=False):
+        self._defaults(0.01)
+        kc = np.sqrt((self.k_cutoff * 2 * np.pi / self.L) ** 2)
+        k2 = np.asarray(kSquare, dtype=np.float64)
+        num = -4. * np.pi * (1. + special.erf((np.sqrt(k2) - kc) / (kc * self.gamma))) / 2.
+        return np.divide(num, k2 ** 2, out=np.zeros_like(k2), where=k2 > (kc * self.gamma) ** 2)
+
+    def yukawa(self, kSquare, multiply_by_k_square=False):
+        g0 = np.sqrt(self.n_ele / self.Omega / 4. * np.pi)
+        g = g0 if self.gamma is None else self.gamma * g0
+        floor = 1e-12 if self.k_cutoff is None else self.k_cutoff * (2 * np.pi / self.L) ** 2 + g
+        b = np.asarray(kSquare, dtype=np.float64) + g
+        return np.divide(-4. * np.pi, b, out=np.zeros_like(b), where=np.abs(b) > floor)
+
+    def stg(self, kSquare, multiply_by_k_square=False):
+        g = np.sqrt(4. * np.pi * self.n_ele / self.Omega) if self.gamma is None else self.gamma
+        floor = 1e-12 if self.k_cutoff is None else (self.k_cutoff * (2 * np.pi / self.L) ** 2 + g ** 2) ** 2
+        b = (np.asarray(kSquare, dtype=np.float64) + g ** 2) ** 2
+        return np.divide(-4. * np.pi / g, b, out=np.zeros_like(b), where=np.abs(b) > floor)
+
+    def yukawa_coulomb(self, kSquare, multiply_by_k_square=False):
+        g = 1.5 if self.gamma is None else self.gamma
+        A = g / np.sqrt(self.Omega / (4.0 * np.pi * self.n_ele))
+        floor = 1e-12 if self.k_cutoff is None else self.k_cutoff * (2 * np.pi / self.L) ** 2 + A
+        k2 = np.asarray(kSquare, dtype=np.float64)
+        b = (k2 + A) * k2
+        return np.divide(-4. * np.pi, b, out=np.zeros_like(b), where=np.abs(b) > floor)
+
+    def gaskell(self, kSquare, multiply_by_k_square=False):
+        mu = np.sqrt(4. * np.pi * self.Omega / self.n_ele) * (1. if self.gamma is None else self.gamma)
+        kf = self.basis_fns[(self.n_ele // 2) * 2].kp
+        kf2 = kf.dot(kf)
+        kc2 = 4. * kf2 if self.k_cutoff is None else self.k_cutoff ** 2 * kf2
+        k2 = np.asarray(kSquare, dtype=np.float64)
+        res = np.divide(mu, k2, out=np.zeros_like(k2), where=(k2 > 1e-12))
+        if k2.ndim == 0:
+            return -float(res) if (1e-12 < k2 < kc2) else -0.0
+        res[k2 > kc2] = 0.
+        return -res
+
+    def gaskell_modified(self, kSquare, multiply_by_k_square=False):
+        kc2 = 2 if self.k_cutoff is None else (self.k_cutoff * (2 * np.pi / self.L)) ** 2
+        k2 = np.asarray(kSquare, dtype=np.float64)
+        if k2.ndim == 0:
+            return -0.0 if (1e-12 < k2 < kc2) else -(4 * np.pi / float(k2) ** 2)
+        return -np.divide(4 * np.pi, k2 ** 2, out=np.zeros_like(k2), where=(k2 >= kc2))

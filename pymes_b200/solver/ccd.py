@@ -1,0 +1,217 @@
+"""CCD / DCD doubles solver on the B200 contraction engine.
+
+Call surface of the reference ``pymes.solver.ccd.CCD`` (pymes/solver/ccd.py:10-262):
+same constructor, ``solve`` / ``get_residual`` / ``get_energy`` signatures, the
+same returned dict keys and the same log lines.  Inputs may be numpy arrays
+(copied to the device once, results returned as numpy) or CUDA tensors.
+
+The doubles residual (ccd.py:164-254) is evaluated as a short list of strided
+DMMA contractions (``backend.contract_terms``) in which every index permutation
+lives in the operand strides, plus three HBM-bound elementwise kernels.  Terms
+that share an output layout are accumulated inside one launch:
+
+    R   = V_abij + T.I + V_abcd.T                 hh + pp ladder   (one launch)
+    R  += X1.T, Tt.Xai                            quadratic ring terms
+    Ex  = Xac.T - Xki.T                           Fock-like terms
+    Ex += -V_iajb.T + Tt.V_iabj - Xp.T + Xp.T'    four ring terms  (one launch)
+    Ex += -V_iajb.T                               (permuted output, own launch)
+    R  += Ex + Ex^{baji}                          no hermiticity assumed
+
+No symmetrisation shortcut is taken anywhere: V_klij != V_ijkl and Ex != Ex^{baji}
+for transcorrelated integrals (ccd.py:172,244-249).
+"""
+import time
+
+import numpy as np
+import torch
+
+from .. import backend as bk
+from ..log import print_logging_info
+from ..mixer import diis
+from . import mp2
+
+
+def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abcd,
+                     is_dcd=False, is_bruekner=False, pp_ladder=None):
+    """R_abij for device tensors (reference ccd.py:164-254).
+
+    ``pp_ladder``: optional callable ``(T2, R) -> None`` adding V_abcd.T2 into R; used by
+    CCSD (dressed ladder without forming the dressed V_abcd) and by sharded runs.
+    """
+    nv = T2.shape[0]
+    ccd = not is_dcd
+    ct = bk.contract_terms
+
+    # I_klij = V_klij (+ V_ijab.T)                                   ccd.py:178-180
+    I = bk.copy(V_klij)
+    if ccd:
+        ct("klij", [(1.0, "klcd", V_ijab, "cdij", T2)], out=I, beta=1.0)
+
+    # R = V_abij + I.T (hh ladder) + V_abcd.T (pp ladder)             ccd.py:185-187
+    R = bk.copy(V_abij)
+    ladder = [(1.0, "abkl", T2, "klij", I)]
+    if pp_ladder is None:
+        ladder.append((1.0, "abcd", V_abcd, "cdij", T2))
+    ct("abij", ladder, out=R, beta=1.0)
+    if pp_ladder is not None:
+        pp_ladder(T2, R)
+
+    if ccd:                                                          # ccd.py:189-191
+        X1 = ct("alcj", [(1.0, "klcd", V_ijab, "adkj", T2)])
+        ct("abij", [(1.0, "alcj", X1, "cbil", T2)], out=R, beta=1.0)
+        del X1
+
+    Tt = bk.tilde(T2)                                                # ccd.py:199
+    Xai = ct("cbkj", [(1.0, "klcd", V_ijab, "dblj", Tt)])            # ccd.py:202
+    ct("abij", [(1.0, "acik", Tt, "cbkj", Xai)], out=R, beta=1.0)    # ccd.py:204
+    del Xai
+
+    # Fock-like intermediates; the reference adds the same product twice for CCD
+    # (ccd.py:213-221): X_ac = f_ab - c.Tt.V, X_ki = f_ij + c.Tt.V, c = 1/2 (DCD) or 1
+    Xac = bk.copy(fock[no:, no:])
+    Xki = bk.copy(fock[:no, :no])
+    if not is_bruekner:
+        c = 1.0 if ccd else 0.5
+        ct("ac", [(-c, "adkl", Tt, "lkdc", V_ijab)], out=Xac, beta=1.0)
+        ct("ki", [(+c, "cdil", Tt, "lkdc", V_ijab)], out=Xki, beta=1.0)
+    elif ccd:
+        ct("ac", [(-0.5, "adkl", Tt, "lkdc", V_ijab)], out=Xac, beta=1.0)
+        ct("ki", [(+0.5, "cdil", Tt, "lkdc", V_ijab)], out=Xki, beta=1.0)
+
+    Ex = ct("abij", [(1.0, "ac", Xac, "cbij", T2)])                  # ccd.py:231
+    ct("abij", [(-1.0, "ki", Xki, "abkj", T2)], out=Ex, beta=1.0)    # ccd.py:232
+    ring = [(-1.0, "kaic", V_iajb, "cbkj", T2),                      # ccd.py:233
+            (+1.0, "acik", Tt, "kbcj", V_iabj)]                      # ccd.py:235
+    if ccd:                                                          # ccd.py:238-240
+        Xp = ct("alci", [(1.0, "klcd", V_ijab, "daki", T2)])
+        ring += [(-1.0, "alci", Xp, "cblj", T2), (+1.0, "alci", Xp, "bclj", T2)]
+    ct("abij", ring, out=Ex, beta=1.0)
+    ct("abij", [(-1.0, "kbic", V_iajb, "ackj", T2)], out=Ex, beta=1.0)   # ccd.py:234
+
+    bk.sym_baji(Ex, R, accumulate=True)                              # ccd.py:249-252
+    return R
+
+
+class CCD:
+    def __init__(self, no, delta_e=1.e-8, is_dcd=False, is_diis=True, is_dr_ccd=False,
+                 is_bruekner=False):
+        self.is_dcd = is_dcd
+        self.is_diis = is_diis
+        self.is_dr_ccd = is_dr_ccd
+        self.is_bruekner = is_bruekner
+        self.no = no
+        self.delta_e = delta_e
+        self.max_iter = 50
+        if self.is_diis:
+            self.mixer = diis.DIIS(dim_space=6)
+        if is_dr_ccd:
+            raise NotImplementedError("direct-ring CCD is outside the accelerated hot path "
+                                      "(SURVEY.md 8f)")
+
+    # ------------------------------------------------------------------
+    def get_residual(self, t_fock_pq, t_T_abij, t_V_klij, t_V_ijab, t_V_abij, t_V_iajb, t_V_iabj,
+                     t_V_abcd):
+        want_numpy = not isinstance(t_T_abij, torch.Tensor)
+        R = doubles_residual(self.no, bk.asdev(t_fock_pq), bk.asdev(t_T_abij).contiguous(),
+                             bk.asdev(t_V_klij), bk.asdev(t_V_ijab), bk.asdev(t_V_abij),
+                             bk.asdev(t_V_iajb), bk.asdev(t_V_iabj), bk.asdev(t_V_abcd),
+                             is_dcd=self.is_dcd, is_bruekner=self.is_bruekner)
+        return bk.tonumpy(R) if want_numpy else R
+
+    def get_energy(self, t_T_abij, t_V_ijab):
+        """(direct, exchange) contributions, ccd.py:256-262."""
+        scal = bk.zeros(8)
+        bk.energy_doubles(bk.asdev(t_T_abij).contiguous(), bk.asdev(t_V_ijab), scal)
+        s = scal.cpu().numpy()
+        return float(s[0]), float(s[1])
+
+    # ------------------------------------------------------------------
+    def solve(self, t_fock_pq, t_V_pqrs, level_shift=0., sp=0, amps=None, **kwargs):
+        algo_name = "ccd.solve"
+        t_start = time.time()
+        no = self.no
+        max_iter = kwargs.get("max_iter", self.max_iter)
+        delta_e = kwargs.get("delta_e", self.delta_e)
+        delta = 1.0
+        want_numpy = not isinstance(t_V_pqrs, torch.Tensor)
+
+        fock_host = bk.tonumpy(t_fock_pq)
+        eps_i_host = fock_host.diagonal()[:no].copy()
+        eps_a_host = fock_host.diagonal()[no:].copy()
+        fock = bk.asdev(fock_host)
+        eps_i, eps_a = bk.asdev(eps_i_host), bk.asdev(eps_a_host)
+        V = bk.asdev(t_V_pqrs)
+        V_iabj = V[:no, no:, no:, :no]
+        V_ijab = V[:no, :no, no:, no:]
+        V_klij = V[:no, :no, :no, :no]
+        V_iajb = V[:no, no:, :no, no:]
+        V_abij = V[no:, no:, :no, :no]
+        V_abcd = V[no:, no:, no:, no:]
+
+        print_logging_info(algo_name)
+        print_logging_info("Using DCD: ", self.is_dcd, level=1)
+        print_logging_info("Using dr-CCD: ", self.is_dr_ccd, level=1)
+        print_logging_info("Solving doubles amplitude equation", level=1)
+        print_logging_info("Using data type %s" % str(V.dtype).replace("torch.", ""), level=1)
+        print_logging_info("Using DIIS mixer: ", self.is_diis, level=1)
+        print_logging_info("Using Bruekner quasi-particle energy: ", self.is_bruekner, level=1)
+        print_logging_info("Iteration = 0", level=1)
+        e_mp2, T2 = mp2.solve_device(eps_i, eps_a, V_ijab, V_abij, level_shift)
+        print("MP2 energy = ", e_mp2)
+        amps_host = None
+        if amps is not None:
+            if isinstance(amps, torch.Tensor):
+                T2 = bk.asdev(amps)          # aliased: updated in place like the reference
+            else:
+                amps_host = amps
+                T2 = bk.asdev(amps).contiguous()
+
+        scal = bk.zeros(8)
+        dE = abs(e_mp2)
+        iteration = 0
+        e_last = e_mp2
+        e_ccd = e_dir = e_ex = 0.0
+        while abs(dE) > delta_e and iteration <= max_iter:
+            iteration += 1
+            R = doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abcd,
+                                 is_dcd=self.is_dcd, is_bruekner=self.is_bruekner)
+            if self.is_bruekner:
+                eps_i, eps_a = self._bruekner_energies(eps_i, eps_a, T2, V_ijab)
+            dT = bk.update_doubles(eps_i, eps_a, level_shift, delta, R, T2, scal[3:4])
+            del R
+            if amps_host is not None and (iteration == 1 or not self.is_diis):
+                amps_host[...] = bk.tonumpy(T2)      # the reference mutates `amps` in place
+            if self.is_diis:
+                T2 = self.mixer.mix([dT], [T2])[0]
+            bk.energy_doubles(T2, V_ijab, scal)
+            s = scal.cpu().numpy()
+            e_dir, e_ex = float(s[0]), float(s[1])
+            e_ccd = e_dir + e_ex
+            dE = e_ccd - e_last
+            e_last = e_ccd
+            t2_norm, res_norm = float(np.sqrt(s[2])), float(np.sqrt(s[3]))
+            if iteration <= max_iter:
+                print_logging_info("Iteration = ", iteration, level=1)
+                print_logging_info("Correlation Energy = {:.12f}".format(e_ccd), level=2)
+                print_logging_info("dE = {:.12e}".format(dE), level=2)
+                print_logging_info("L1 Norm of T2 = {:.12f}".format(t2_norm), level=2)
+                print_logging_info("Norm Residual = {:.12f}".format(res_norm), level=2)
+            else:
+                print_logging_info("A converged solution is not found!", level=1)
+
+        print_logging_info("Direct contribution = {:.12f}".format(e_dir), level=1)
+        print_logging_info("Exchange contribution = {:.12f}".format(e_ex), level=1)
+        print_logging_info("CCD correlation energy = {:.12f}".format(e_ccd), level=1)
+        print_logging_info("{:.3f} seconds spent on CCD".format(time.time() - t_start), level=1)
+        self.iterations = iteration
+        if want_numpy:
+            return {"ccd e": e_ccd, "t2 amp": bk.tonumpy(T2), "hole e": bk.tonumpy(eps_i),
+                    "particle e": bk.tonumpy(eps_a), "dE": dE}
+        return {"ccd e": e_ccd, "t2 amp": T2, "hole e": eps_i, "particle e": eps_a, "dE": dE}
+
+    def _bruekner_energies(self, eps_i, eps_a, T2, V_ijab):
+        """Amplitude-dependent quasi-particle energies, ccd.py:104-121."""
+        Tt = bk.tilde(T2)
+        di = bk.contract_terms("i", [(0.5, "ilcd", V_ijab, "cdil", Tt)])
+        da = bk.contract_terms("a", [(-0.5, "klad", V_ijab, "adkl", Tt)])
+        return eps_i + di, eps_a + da

@@ -1,0 +1,295 @@
+"""CCSD / DCSD through the T1-dressed Hamiltonian, on the B200 contraction engine.
+
+Call surface of the reference ``pymes.solver.ccsd.CCSD`` (pymes/solver/ccsd.py:22-466):
+constructor, ``solve``, ``get_T1_dressed_fock``, ``get_T1_dressed_V``,
+``get_singles_residual``, ``get_doubles_residual``, ``get_energy``, the returned
+dict keys, ``self.t_T_ai`` / ``self.t_T_abij`` and the log lines.
+
+Design differences (results agree to round-off, see tests/test_ccsd_gpu.py):
+
+* Every dressing product (ccsd.py:257-286, 322-419) is a row of a term table that
+  is evaluated pairwise on the DMMA engine (``backend.einsum``); sources are always
+  the undressed blocks, exactly as in the reference.
+* ``solve`` never forms the dressed V_abcd (a v^4 copy plus three o.v^4
+  contractions per sweep in the reference, ccsd.py:414-419).  All terms in which
+  V_abcd, V_iabc, V_aibc or V_ijab meet two virtual-contracted amplitudes collapse
+  onto one particle-particle ladder applied to tau = T2 + T1 (x) T1:
+
+      W  = V_abcd.tau                       W1 = V_iabc.tau   (k b i j)
+      W2 = V_aibc.tau  (a l i j)            W3 = V_ijab.tau   (k l i j)
+      R += W - t_ak W1_kbij - t_bl (W2 - t_ak W3)_alij
+
+  which reproduces the four tau-type rows of the dressed V_abij (ccsd.py:334-343)
+  together with the dressed-V_abcd ladder of ccd.py:187.  The public
+  ``get_T1_dressed_V`` still returns every dressed block (EOM-CCSD consumes them).
+"""
+import time
+
+import numpy as np
+import torch
+
+from .. import backend as bk
+from ..integral.partition import part_2_body_int
+from ..log import print_logging_info
+from ..mixer import diis
+from . import ccd, mp2
+
+# (coef, subscripts, operand names); "t" = T1, "foo"/"fvv"/"fov" = Fock blocks,
+# anything else = key of the undressed integral dictionary.
+FOCK_TERMS = {
+    "ov": [(+2.0, "bj,jabi->ia", "t iabj"), (-1.0, "bj,jiab->ia", "t ijab")],
+    "vo": [(-1.0, "ji,aj->ai", "foo t"), (+1.0, "ab,bi->ai", "fvv t"),
+           (-1.0, "jb,bi,aj->ai", "fov t t"),
+           (+2.0, "bj,jabi->ai", "t iabj"), (-2.0, "bj,jkbi,ak->ai", "t ijak t"),
+           (+2.0, "bj,jabc,ci->ai", "t iabc t"), (-2.0, "bj,jkbc,ci,ak->ai", "t ijab t t"),
+           (-1.0, "bj,jaib->ai", "t iajb"), (+1.0, "bj,jkib,ak->ai", "t ijka t"),
+           (-1.0, "bj,jacb,ci->ai", "t iabc t"), (+1.0, "bj,jkcb,ci,ak->ai", "t ijab t t")],
+    "oo": [(+2.0, "ck,kicj->ij", "t ijak"), (-1.0, "ck,kijc->ij", "t ijka"),
+           (+1.0, "ib,bj->ij", "fov t"),
+           (+2.0, "ck,kicb,bj->ij", "t ijab t"), (-1.0, "ck,kibc,bj->ij", "t ijab t")],
+    "vv": [(+2.0, "ci,iacb->ab", "t iabc"), (-1.0, "ci,iabc->ab", "t iabc"),
+           (-1.0, "ib,ai->ab", "fov t"),
+           (-2.0, "ck,klcb,al->ab", "t ijab t"), (+1.0, "ck,kibc,ai->ab", "t ijab t")],
+}
+
+# rows marked True are the tau-type terms folded into the pp ladder by `solve`
+V_TERMS = {
+    "abij": [(-1.0, "kbij,ak->abij", "iajk", False), (+1.0, "abcj,ci->abij", "abci", False),
+             (-1.0, "kbcj,ak,ci->abij", "iabj", False), (-1.0, "alij,bl->abij", "aijk", False),
+             (+1.0, "klij,ak,bl->abij", "klij", False), (-1.0, "alcj,ci,bl->abij", "aibj", False),
+             (+1.0, "klcj,ak,ci,bl->abij", "ijak", False), (+1.0, "abid,dj->abij", "abic", False),
+             (-1.0, "kbid,ak,dj->abij", "iajb", False), (+1.0, "abcd,ci,dj->abij", "abcd", True),
+             (-1.0, "kbcd,ak,ci,dj->abij", "iabc", True), (-1.0, "alid,bl,dj->abij", "aijb", False),
+             (+1.0, "klid,ak,bl,dj->abij", "ijka", False), (-1.0, "alcd,ci,bl,dj->abij", "aibc", True),
+             (+1.0, "klcd,ak,ci,bl,dj->abij", "ijab", True)],
+    "klij": [(+1.0, "klaj,ai->klij", "ijak", False), (+1.0, "klib,bj->klij", "ijka", False),
+             (+1.0, "klab,ai,bj->klij", "ijab", False)],
+    "ijab": [],
+    "ijka": [(+1.0, "ijba,bk->ijka", "ijab", False)],
+    "ijak": [(+1.0, "ijab,bk->ijak", "ijab", False)],
+    "iajb": [(+1.0, "iacb,cj->iajb", "iabc", False), (-1.0, "ikjb,ak->iajb", "ijka", False),
+             (-1.0, "ikcb,cj,ak->iajb", "ijab", False)],
+    "iabj": [(-1.0, "ikbj,ak->iabj", "ijak", False), (+1.0, "iabc,cj->iabj", "iabc", False),
+             (-1.0, "ikbc,ak,cj->iabj", "ijab", False)],
+    "iabc": [(-1.0, "ijbc,aj->iabc", "ijab", False)],
+    "abic": [(-1.0, "jbic,aj->abic", "iajb", False), (+1.0, "abdc,di->abic", "abcd", False),
+             (-1.0, "jbdc,aj,di->abic", "iabc", False), (-1.0, "ajic,bj->abic", "aijb", False),
+             (+1.0, "kjic,ak,bj->abic", "ijka", False), (-1.0, "ajdc,di,bj->abic", "aibc", False),
+             (+1.0, "kjdc,ak,di,bj->abic", "ijab", False)],
+    "iajk": [(-1.0, "iljk,al->iajk", "klij", False), (+1.0, "iajb,bk->iajk", "iajb", False),
+             (-1.0, "iljb,al,bk->iajk", "ijka", False), (+1.0, "iabk,bj->iajk", "iabj", False),
+             (-1.0, "ilbk,bj,al->iajk", "ijak", False), (+1.0, "iabc,bj,ck->iajk", "iabc", False),
+             (-1.0, "ilbc,bj,al,ck->iajk", "ijab", False)],
+    "abcd": [(-1.0, "jbcd,aj->abcd", "iabc", False), (-1.0, "aicd,bi->abcd", "aibc", False),
+             (+1.0, "jicd,aj,bi->abcd", "ijab", False)],
+}
+
+SINGLES_TERMS = [(+1.0, "jb,abij->ai", "fov Tt"), (+1.0, "ajbc,bcij->ai", "aibc Tt"),
+                 (-1.0, "kjbc,ak,bcij->ai", "ijab t Tt"), (-1.0, "jkib,abjk->ai", "ijka Tt"),
+                 (-1.0, "jkcb,ci,abjk->ai", "ijab t Tt")]
+
+
+def _dev_dict(dict_t_V):
+    return {k: (bk.asdev(v) if v is not None else None) for k, v in dict_t_V.items()}
+
+
+def dressed_fock(no, fock, T1, dV):
+    """Device tensors in, dressed Fock (new tensor) out.  ccsd.py:226-288."""
+    src = dict(dV)
+    src.update(t=T1, foo=fock[:no, :no], fvv=fock[no:, no:], fov=fock[:no, no:])
+    out = bk.copy(fock)
+    views = {"ov": out[:no, no:], "vo": out[no:, :no], "oo": out[:no, :no], "vv": out[no:, no:]}
+    for blk, rows in FOCK_TERMS.items():
+        for coef, spec, names in rows:
+            bk.einsum(spec, *[src[n] for n in names.split()], out=views[blk], alpha=coef, beta=1.0)
+    return out
+
+
+def dressed_block(key, T1, dV, skip_tau=False):
+    """One T1-dressed V block from the undressed dictionary.  ccsd.py:322-419."""
+    blk = bk.copy(dV[key])
+    for coef, spec, source, is_tau in V_TERMS[key]:
+        if skip_tau and is_tau:
+            continue
+        nt = spec.split("->")[0].count(",")
+        bk.einsum(spec, dV[source], *([T1] * nt), out=blk, alpha=coef, beta=1.0)
+    return blk
+
+
+def singles_residual(no, fock_dressed, T1, T2, dV):
+    """R_ai from the dressed Fock matrix and the UNDRESSED integrals (ccsd.py:167-168, 423-438)."""
+    Tt = bk.tilde(T2, swap_ij=True)
+    src = dict(dV)
+    src.update(t=T1, Tt=Tt, fov=fock_dressed[:no, no:])
+    R1 = bk.copy(fock_dressed[no:, :no])
+    for coef, spec, names in SINGLES_TERMS:
+        bk.einsum(spec, *[src[n] for n in names.split()], out=R1, alpha=coef, beta=1.0)
+    return R1
+
+
+def tau_ladder(T1, dV):
+    """Returns the ``pp_ladder(T2, R)`` callback described in the module docstring."""
+    def apply(T2, R):
+        ct = bk.contract_terms
+        tau = bk.copy(T2)
+        ct("abij", [(1.0, "ai", T1, "bj", T1)], out=tau, beta=1.0)
+        ct("abij", [(1.0, "abcd", dV["abcd"], "cdij", tau)], out=R, beta=1.0)
+        W1 = ct("kbij", [(1.0, "kbcd", dV["iabc"], "cdij", tau)])
+        ct("abij", [(-1.0, "ak", T1, "kbij", W1)], out=R, beta=1.0)
+        W2 = ct("alij", [(1.0, "alcd", dV["aibc"], "cdij", tau)])
+        W3 = ct("klij", [(1.0, "klcd", dV["ijab"], "cdij", tau)])
+        ct("alij", [(-1.0, "ak", T1, "klij", W3)], out=W2, beta=1.0)
+        ct("abij", [(-1.0, "bl", T1, "alij", W2)], out=R, beta=1.0)
+    return apply
+
+
+class CCSD(ccd.CCD):
+    def __init__(self, no, is_diis=True, delta_e=1.e-8, is_non_canonical=False, is_dcsd=False):
+        self.t_T_ai = None
+        self.t_T_abij = None
+        self.is_dcd = is_dcsd
+        self.is_diis = is_diis
+        self.is_bruekner = False
+        self.is_dr_ccd = False
+        self.no = no
+        self.max_iter = 50
+        self.delta = 1.0
+        self.delta_e = delta_e
+        self.debug_level = 1
+        if self.is_diis:
+            self.mixer = diis.DIIS(dim_space=6)
+
+    def write_logging_info(self):
+        return
+
+    # ---- public building blocks (numpy or CUDA tensors in, same kind out) ----
+    def get_T1_dressed_fock(self, t_fock_pq, t_T_ai, dict_t_V):
+        want_numpy = not isinstance(t_fock_pq, torch.Tensor)
+        out = dressed_fock(self.no, bk.asdev(t_fock_pq), bk.asdev(t_T_ai), _dev_dict(dict_t_V))
+        return bk.tonumpy(out) if want_numpy else out
+
+    def get_T1_dressed_V(self, t_T_ai, dict_t_V, dict_t_V_dressed=None):
+        """All (or the requested) dressed blocks; blocks the reference leaves
+        undressed stay ``None`` (``dict.fromkeys``, ccsd.py:316-317)."""
+        want_numpy = not isinstance(t_T_ai, torch.Tensor)
+        if dict_t_V_dressed is None or len(dict_t_V_dressed) == 0:
+            dict_t_V_dressed = {}.fromkeys(dict_t_V, None)
+        dV, T1 = _dev_dict(dict_t_V), bk.asdev(t_T_ai)
+        for key in V_TERMS:
+            if key in dict_t_V_dressed:
+                blk = dressed_block(key, T1, dV)
+                dict_t_V_dressed[key] = bk.tonumpy(blk) if want_numpy else blk
+        return dict_t_V_dressed
+
+    def get_singles_residual(self, t_fock_pq, t_T_ai, t_T_abij, dict_t_V):
+        want_numpy = not isinstance(t_T_abij, torch.Tensor)
+        R1 = singles_residual(self.no, bk.asdev(t_fock_pq), bk.asdev(t_T_ai),
+                              bk.asdev(t_T_abij).contiguous(), _dev_dict(dict_t_V))
+        return bk.tonumpy(R1) if want_numpy else R1
+
+    def get_doubles_residual(self, t_fock_pq, t_T_abij, dict_t_V_dressed):
+        d = dict_t_V_dressed
+        return self.get_residual(t_fock_pq, t_T_abij, d["klij"], d["ijab"], d["abij"], d["iajb"],
+                                 d["iabj"], d["abcd"])
+
+    def get_energy(self, t_fock_ia, t_T_ai, t_T_abij, t_V_ijab):
+        """[one-body, direct, exchange], ccsd.py:458-466."""
+        T1, T2 = bk.asdev(t_T_ai).contiguous(), bk.asdev(t_T_abij).contiguous()
+        scal = bk.zeros(8)
+        bk.energy_doubles(T2, bk.asdev(t_V_ijab), scal, T1=T1)
+        bk.contract_terms("", [(2.0, "ia", bk.asdev(t_fock_ia), "ai", T1)], out=scal[4])
+        s = scal.cpu().numpy()
+        return [float(s[4]), float(s[0]), float(s[1])]
+
+    # ------------------------------------------------------------------
+    def solve(self, t_fock_pq, t_V_pqrs, level_shift=0., amps=None, sp=0, **kwargs):
+        algo_name = "ccsd.solve"
+        t_start = time.time()
+        no = self.no
+        delta = self.delta
+        max_iter = kwargs.get("max_iter", self.max_iter)
+        delta_e = kwargs.get("delta_e", self.delta_e)
+        blocks_given = isinstance(t_V_pqrs, dict)
+        want_numpy = not (blocks_given or isinstance(t_V_pqrs, torch.Tensor))
+
+        fock_host = bk.tonumpy(t_fock_pq)
+        nv = fock_host.shape[0] - no
+        eps_i = bk.asdev(fock_host.diagonal()[:no].copy())
+        eps_a = bk.asdev(fock_host.diagonal()[no:].copy())
+        fock = bk.asdev(fock_host)
+        if blocks_given:       # extension: pre-partitioned blocks (V_pqrs too big to exist)
+            dV = _dev_dict(t_V_pqrs)
+            dtype_name = "float64"
+        else:
+            V = bk.asdev(t_V_pqrs)
+            dV = part_2_body_int(no, V)
+            dtype_name = str(V.dtype).replace("torch.", "")
+
+        print_logging_info(algo_name)
+        print_logging_info("Using dcsd: ", self.is_dcd, level=1)
+        print_logging_info("Solving doubles amplitude equation", level=1)
+        print_logging_info("Using data type %s" % dtype_name, level=1)
+        print_logging_info("Using DIIS mixer: ", self.is_diis, level=1)
+        print_logging_info("Iteration = 0", level=1)
+
+        e_mp2, T2 = mp2.solve_device(eps_i, eps_a, dV["ijab"], dV["abij"], level_shift)
+        T1 = bk.zeros(nv, no)
+        amps_host = None
+        if amps is not None:
+            if isinstance(amps[0], torch.Tensor):
+                T1, T2 = bk.asdev(amps[0]), bk.asdev(amps[1])
+            else:
+                amps_host = amps
+                T1, T2 = bk.asdev(amps[0]).contiguous(), bk.asdev(amps[1]).contiguous()
+
+        scal = bk.zeros(8)
+        dE = abs(e_mp2)
+        iteration = 0
+        e_last = e_mp2
+        e_ccsd = e_1b = e_dir = e_ex = 0.0
+        f_ia = fock[:no, no:]
+        while abs(dE) > delta_e and iteration <= max_iter:
+            iteration += 1
+            ft = dressed_fock(no, fock, T1, dV)
+            R1 = singles_residual(no, ft, T1, T2, dV)
+            R2 = ccd.doubles_residual(
+                no, ft, T2, dressed_block("klij", T1, dV), dV["ijab"],
+                dressed_block("abij", T1, dV, skip_tau=True), dressed_block("iajb", T1, dV),
+                dressed_block("iabj", T1, dV), None, is_dcd=self.is_dcd,
+                pp_ladder=tau_ladder(T1, dV))
+            dT1 = bk.update_singles(eps_i, eps_a, level_shift, delta, R1, T1)
+            dT2 = bk.update_doubles(eps_i, eps_a, level_shift, delta, R2, T2, scal[3:4])
+            del R1, R2
+            if amps_host is not None and (iteration == 1 or not self.is_diis):
+                amps_host[0][...] = bk.tonumpy(T1)
+                amps_host[1][...] = bk.tonumpy(T2)
+            if self.is_diis:
+                T1, T2 = self.mixer.mix([dT1, dT2], [T1, T2])
+            bk.energy_doubles(T2, dV["ijab"], scal, T1=T1)
+            bk.contract_terms("", [(2.0, "ia", f_ia, "ai", T1)], out=scal[4])
+            s = scal.cpu().numpy()
+            e_dir, e_ex, e_1b = float(s[0]), float(s[1]), float(s[4])
+            e_ccsd = e_1b + e_dir + e_ex
+            dE = e_ccsd - e_last
+            e_last = e_ccsd
+            t2_norm, res_norm = float(np.sqrt(s[2])), float(np.sqrt(s[3]))
+            if iteration <= max_iter:
+                print_logging_info("Iteration = ", iteration, level=1)
+                print_logging_info("Correlation Energy = {:.14f}".format(e_ccsd), level=2)
+                print_logging_info("dE = {:.12e}".format(dE), level=2)
+                print_logging_info("L1 Norm of T2 = {:.14f}".format(t2_norm), level=2)
+                print_logging_info("Norm Residual = {:.14f}".format(res_norm), level=2)
+            else:
+                print_logging_info("A converged solution is not found!", level=1)
+
+        print_logging_info("Fock contribution = {:.12f}".format(e_1b), level=1)
+        print_logging_info("Direct contribution = {:.12f}".format(e_dir), level=1)
+        print_logging_info("Exchange contribution = {:.12f}".format(e_ex), level=1)
+        print_logging_info("CCSD correlation energy = {:.12f}".format(e_ccsd), level=1)
+        print_logging_info("{:.3f} seconds spent on ccsd".format(time.time() - t_start), level=1)
+        self.iterations = iteration
+        if want_numpy:
+            T1, T2, eps_i, eps_a = (bk.tonumpy(x) for x in (T1, T2, eps_i, eps_a))
+        self.t_T_ai = T1
+        self.t_T_abij = T2
+        return {"ccsd e": e_ccsd, "t1": T1, "t2": T2, "hole e": eps_i, "particle e": eps_a, "dE": dE}

@@ -1,0 +1,338 @@
+"""TEST INFRASTRUCTURE: a numpy emulation of the C ABI in include/pymes_b200.h.
+
+It exists so that the *host logic* of pymes_b200 (einsum parsing, descriptor
+building, dressing term tables, DIIS bookkeeping, solver drivers) can be checked
+against the oracle in the GPU-less build container.  It is installed only by the
+``cpu_abi`` fixture in tests/conftest.py (monkeypatching ``_lib.load`` and the
+device helpers); the product package never imports it, has no CPU path of its
+own, and raises if the CUDA library is missing.  The semantics implemented here
+are exactly the ones documented in the header, descriptor field by field.
+"""
+import ctypes as C
+import itertools
+
+import numpy as np
+import torch
+
+
+def _window(ptr, n):
+    """float64 view of n host doubles starting at raw address ptr."""
+    return np.ctypeslib.as_array((C.c_double * n).from_address(ptr))
+
+
+def _val(p):
+    if p is None:
+        return None
+    return p.value if hasattr(p, "value") else int(p)
+
+
+def _offsets(exts, strides):
+    """Offsets of a composite index, first listed index fastest."""
+    mult = [np.arange(e, dtype=np.int64) * s for e, s in zip(exts, strides)]
+    out = np.zeros(1, dtype=np.int64)
+    for m in mult[::-1]:
+        out = (out[:, None] + m[None, :]).reshape(-1)
+    return out
+
+
+def _gather(ptr, offs):
+    lo, hi = int(offs.min()), int(offs.max())
+    win = _window(ptr + 8 * lo, hi - lo + 1)
+    return win[offs - lo], win, lo
+
+
+class FakeLib:
+    """Drop-in for the ctypes library object."""
+
+    def __init__(self):
+        self.launches = 0
+
+    # ---- info -------------------------------------------------------
+    def pmb_version(self):
+        return 100
+
+    def pmb_launch_count(self):
+        return self.launches
+
+    def pmb_launch_count_reset(self):
+        self.launches = 0
+
+    def pmb_error_string(self, code):
+        return b"emulated error %d" % code
+
+    def pmb_reduce_workspace(self):
+        return 8 * 64
+
+    def pmb_contract_workspace(self, dref):
+        return 0
+
+    def pmb_contract_set_tuning(self, a, b):
+        return None
+
+    # ---- contraction ------------------------------------------------
+    def pmb_contract(self, dref, ws, ws_bytes, stream):
+        d = dref._obj
+        self.launches += 1
+        m_ext = [d.m_ext[i] for i in range(d.nm)]
+        n_ext = [d.n_ext[i] for i in range(d.nn)]
+        M = int(np.prod(m_ext)) if m_ext else 1
+        N = int(np.prod(n_ext)) if n_ext else 1
+        acc = np.zeros((M, N))
+        for ti in range(d.nterms):
+            t = d.terms[ti]
+            k_ext = [t.k_ext[i] for i in range(t.nk)]
+            am = _offsets(m_ext, [t.a_mstr[i] for i in range(d.nm)])
+            ak = _offsets(k_ext, [t.a_kstr[i] for i in range(t.nk)])
+            bk_ = _offsets(k_ext, [t.b_kstr[i] for i in range(t.nk)])
+            bn = _offsets(n_ext, [t.b_nstr[i] for i in range(d.nn)])
+            A, _, _ = _gather(t.A, (am[:, None] + ak[None, :]).reshape(-1))
+            B, _, _ = _gather(t.B, (bk_[:, None] + bn[None, :]).reshape(-1))
+            acc += t.alpha * (A.reshape(M, -1) @ B.reshape(-1, N))
+        cm = _offsets(m_ext, [d.c_mstr[i] for i in range(d.nm)])
+        cn = _offsets(n_ext, [d.c_nstr[i] for i in range(d.nn)])
+        offs = (cm[:, None] + cn[None, :]).reshape(-1)
+        old, win, lo = _gather(d.C, offs)
+        new = acc.reshape(-1) + (d.beta * old if d.beta != 0.0 else 0.0)
+        win[offs - lo] = new
+        return 0
+
+    # ---- elementwise ------------------------------------------------
+    def pmb_axpby4(self, ext, alpha, inp, in_str, beta, out, out_str, stream):
+        self.launches += 1
+        e = [ext[i] for i in range(4)]
+        oi = _offsets(e[::-1], [in_str[i] for i in range(4)][::-1])
+        oo = _offsets(e[::-1], [out_str[i] for i in range(4)][::-1])
+        src, _, _ = _gather(_val(inp), oi)
+        old, win, lo = _gather(_val(out), oo)
+        win[oo - lo] = alpha * src + (beta * old if beta != 0.0 else 0.0)
+        return 0
+
+    @staticmethod
+    def _denoms(no, nv, ei, ea, shift):
+        ei, ea = _window(_val(ei), no), _window(_val(ea), nv)
+        return (ei[None, None, :, None] + ei[None, None, None, :] - ea[:, None, None, None]
+                - ea[None, :, None, None] + shift), ei, ea
+
+    def pmb_mp2_amplitudes(self, no, nv, ei, ea, shift, V, v_str, T2, stream):
+        self.launches += 1
+        D, _, _ = self._denoms(no, nv, ei, ea, shift)
+        offs = _offsets([no, no, nv, nv], [v_str[3], v_str[2], v_str[1], v_str[0]])
+        v, _, _ = _gather(_val(V), offs)
+        _window(_val(T2), nv * nv * no * no)[:] = (v.reshape(nv, nv, no, no) / D).reshape(-1)
+        return 0
+
+    def pmb_update_doubles(self, no, nv, ei, ea, shift, delta, R, dT, T2, scal, ws, wsb, stream):
+        self.launches += 2
+        n = nv * nv * no * no
+        D, _, _ = self._denoms(no, nv, ei, ea, shift)
+        d = _window(_val(R), n) * (1.0 / D).reshape(-1)
+        _window(_val(dT), n)[:] = d
+        _window(_val(T2), n)[:] += delta * d
+        _window(_val(scal), 1)[0] = np.sum(d * d)
+        return 0
+
+    def pmb_update_singles(self, no, nv, ei, ea, shift, delta, R1, dT1, T1, stream):
+        self.launches += 1
+        ei_, ea_ = _window(_val(ei), no), _window(_val(ea), nv)
+        D = ei_[None, :] - ea_[:, None] + shift
+        d = _window(_val(R1), nv * no) * (1.0 / D).reshape(-1)
+        _window(_val(dT1), nv * no)[:] = d
+        _window(_val(T1), nv * no)[:] += delta * d
+        return 0
+
+    def pmb_energy_doubles(self, no, nv, T2, T1, V, v_str, mp2_form, scal, ws, wsb, stream):
+        self.launches += 3
+        n = nv * nv * no * no
+        t = _window(_val(T2), n).reshape(nv, nv, no, no)
+        tau = t
+        if _val(T1):
+            t1 = _window(_val(T1), nv * no).reshape(nv, no)
+            tau = t + np.einsum("ai,bj->abij", t1, t1)
+        offs = _offsets([nv, nv, no, no], [v_str[3], v_str[2], v_str[1], v_str[0]])
+        v, _, _ = _gather(_val(V), offs)
+        v = v.reshape(no, no, nv, nv)
+        s = _window(_val(scal), 3)
+        s[0] = 2.0 * np.einsum("abij,ijab->", tau, v)
+        s[1] = -np.einsum("abij,jiab->" if mp2_form else "abij,ijba->", tau, v)
+        s[2] = np.sum(t * t)
+        return 0
+
+    def pmb_tilde(self, no, nv, T2, Tt, swap_ij, stream):
+        self.launches += 1
+        n = nv * nv * no * no
+        t = _window(_val(T2), n).reshape(nv, nv, no, no)
+        perm = (0, 1, 3, 2) if swap_ij else (1, 0, 2, 3)
+        _window(_val(Tt), n)[:] = (2.0 * t - t.transpose(perm)).reshape(-1)
+        return 0
+
+    def pmb_sym_baji(self, no, nv, Ex, R, accumulate, stream):
+        self.launches += 1
+        n = nv * nv * no * no
+        e = _window(_val(Ex), n).reshape(nv, nv, no, no)
+        v = (e + e.transpose(1, 0, 3, 2)).reshape(-1)
+        r = _window(_val(R), n)
+        r[:] = r + v if accumulate else v
+        return 0
+
+    def pmb_dots(self, nvec, X, Y, n, out, ws, wsb, stream):
+        self.launches += 2
+        y = _window(_val(Y), n)
+        o = _window(_val(out), nvec)
+        for k in range(nvec):
+            o[k] = np.dot(_window(X[k], n), y)
+        return 0
+
+    def pmb_lincomb(self, nvec, c, X, n, beta, out, stream):
+        self.launches += 1
+        o = _window(_val(out), n)
+        acc = beta * o if beta != 0.0 else np.zeros(n)
+        for k in range(nvec):
+            acc = acc + c[k] * _window(X[k], n)
+        o[:] = acc
+        return 0
+
+    # ---- UEG --------------------------------------------------------
+    @staticmethod
+    def _ueg(u):
+        u = u._obj
+        nP = u.n_orb
+        kvec = np.ctypeslib.as_array((C.c_int32 * (3 * nP)).from_address(u.kvec)).reshape(nP, 3)
+        kp = _window(u.kp, 3 * nP).reshape(nP, 3)
+        n = 2 * u.imax + 1
+        imap = np.ctypeslib.as_array((C.c_int32 * n ** 3).from_address(u.index_map))
+        tab = _window(u.u_table, u.u_table_len) if u.u_table else None
+        return u, nP, kvec.astype(np.int64), kp, imap, tab
+
+    @staticmethod
+    def _u(tab, v):
+        n2 = np.sum(np.asarray(v) ** 2, axis=-1)
+        return np.where(n2 < len(tab), tab[np.minimum(n2, len(tab) - 1)], 0.0)
+
+    def pmb_ueg_umat(self, u, box_len, cutoff, nq, qvec, out, stream):
+        self.launches += 1
+        u, nP, kvec, kp, imap, tab = self._ueg(u)
+        q = np.ctypeslib.as_array((C.c_int32 * (3 * nq)).from_address(_val(qvec))).reshape(nq, 3)
+        g = np.arange(-cutoff, cutoff + 1)
+        kprime = np.array(list(itertools.product(g, g, g)), dtype=np.int64)
+        k1 = 2 * np.pi * kprime / box_len
+        o = _window(_val(out), nq)
+        for n in range(nq):
+            qf = 2 * np.pi * q[n].astype(float) / box_len
+            k2 = qf - k1
+            o[n] = np.sum(np.einsum("ni,ni->n", k1, k2) * self._u(tab, kprime)
+                          * self._u(tab, q[n].astype(np.int64) - kprime)) / u.omega
+        return 0
+
+    def pmb_ueg_pair_tables(self, u, mode, umat_pr, W0, W1, stream):
+        self.launches += 1
+        u, nP, kvec, kp, imap, tab = self._ueg(u)
+        um = _window(_val(umat_pr), nP * nP).reshape(nP, nP) if _val(umat_pr) else np.zeros((nP, nP))
+        w0 = np.zeros((nP, nP))
+        w1 = np.zeros((nP, nP))
+        no = u.n_occ
+        for p in range(nP):
+            for r in range(nP):
+                d = kp[r] - kp[p]
+                di = kvec[r] - kvec[p]
+                d2 = d.dot(d)
+                nz = abs(d2) > 0
+                ud = float(self._u(tab, di)) if tab is not None else 0.0
+
+                def ex3(o):
+                    v = kp[o] - kp[:no]
+                    return np.sum(v.dot(d) * ud * self._u(tab, kvec[o] - kvec[:no])) / u.omega
+
+                def pk(o):
+                    b = kp[o] - kp[:no]
+                    a = b - d
+                    bi = kvec[o] - kvec[:no]
+                    return np.sum(np.einsum("ni,ni->n", a, b) * self._u(tab, bi - di)
+                                  * self._u(tab, bi)) / u.omega
+                if mode == 0:
+                    w0[p, r] = 4 * np.pi / d2 / u.omega if nz else 0.0
+                elif mode == 1:
+                    w0[p, r] = (-u.n_ele * d2 * ud ** 2 / u.omega) / u.omega if nz else 0.0
+                elif mode == 2:
+                    if nz:
+                        w0[p, r] = (4 * np.pi / d2 + um[p, r] + d2 * ud) / u.omega
+                        w1[p, r] = -ud / u.omega
+                    else:
+                        w0[p, r] = um[p, r] / u.omega
+                elif mode == 3:
+                    w0[p, r] = ((4 * np.pi / d2 + um[p, r] + d2 * ud) if nz else um[p, r]) / u.omega
+                elif mode == 4:
+                    if nz:
+                        w0[p, r] = 4 * np.pi / d2 / u.omega
+                        w1[p, r] = -ud / u.omega
+                elif mode == 5:
+                    if nz:
+                        w0[p, r] = (-u.n_ele * d2 * ud ** 2 / u.omega + 2 * ex3(r) - 2 * ex3(p)
+                                    + 2 * pk(r)) / u.omega
+                    else:
+                        w0[p, r] = 2 * pk(r) / u.omega
+                elif mode == 6:
+                    w0[p, r] = 2 * ex3(r) / u.omega if nz else 0.0
+                elif mode == 7:
+                    w0[p, r] = -2 * ex3(p) / u.omega if nz else 0.0
+                elif mode == 8:
+                    w0[p, r] = 2 * pk(r) / u.omega
+        _window(_val(W0), nP * nP)[:] = w0.reshape(-1)
+        if _val(W1):
+            _window(_val(W1), nP * nP)[:] = w1.reshape(-1)
+        return 0
+
+    def pmb_ueg_build_block(self, u, W0a, W1a, W0s, lo, ext, out, stream):
+        self.launches += 1
+        u, nP, kvec, kp, imap, tab = self._ueg(u)
+        get = lambda p: _window(_val(p), nP * nP).reshape(nP, nP) if _val(p) else None
+        W0a, W1a, W0s = get(W0a), get(W1a), get(W0s)
+        lo = [lo[i] for i in range(4)]
+        ext = [ext[i] for i in range(4)]
+        blk = np.zeros(ext)
+        n = 2 * u.imax + 1
+        for p in range(lo[0], lo[0] + ext[0]):
+            for q in range(lo[1], lo[1] + ext[1]):
+                for r in range(lo[2], lo[2] + ext[2]):
+                    v = kvec[q] - (kvec[r] - kvec[p]) + u.imax
+                    loc = n * n * v[0] + n * v[1] + v[2]
+                    if not 0 <= loc < n ** 3:
+                        continue
+                    s = imap[loc]
+                    if s < 0 or s >= nP or not lo[3] <= s < lo[3] + ext[3]:
+                        continue
+                    w = 0.0
+                    if W0a is not None:
+                        w = W0a[p, r]
+                    if W1a is not None and W1a[p, r] != 0.0:
+                        w += W1a[p, r] * (kp[r] - kp[s]).dot(kp[r] - kp[p])
+                    if W0s is not None:
+                        w += 0.5 * (W0s[p, r] + W0s[q, s])
+                    blk[p - lo[0], q - lo[1], r - lo[2], s - lo[3]] = w
+        _window(_val(out), blk.size)[:] = blk.reshape(-1)
+        return 0
+
+
+def install(monkeypatch):
+    """Route pymes_b200 through the emulator with host tensors (tests only)."""
+    from pymes_b200 import _lib, backend as bk
+    fake = FakeLib()
+    cpu = torch.device("cpu")
+    monkeypatch.setattr(_lib, "load", lambda: fake)
+
+    def check(rc, what=""):
+        if rc != 0:
+            raise RuntimeError("%s failed (%d)" % (what, rc))
+    monkeypatch.setattr(_lib, "check", check)
+    monkeypatch.setattr(bk, "require_cuda", lambda: None)
+    monkeypatch.setattr(bk, "device", lambda: cpu)
+    monkeypatch.setattr(bk, "_stream", lambda: None)
+    monkeypatch.setattr(bk, "_device_key", lambda: "cpu-emulator")
+
+    def asdev(x):
+        if isinstance(x, torch.Tensor):
+            return x.to(torch.float64)
+        a = np.asarray(x, dtype=np.float64)
+        return torch.from_numpy(np.ascontiguousarray(a))
+    monkeypatch.setattr(bk, "asdev", asdev)
+    bk._scratch.pop("cpu-emulator", None)
+    return fake
