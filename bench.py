@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the coupled-cluster amplitude-equation hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W          (N=1: plain python; N>1: torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+One "step" = one CCSD iteration with DIIS (dressing -> singles + doubles residual ->
+amplitude update -> DIIS -> energy) on the transcorrelated 3D UEG with 54 electrons
+(BASELINE.json configs[1]).  The ~500-orbital basis of that config needs 305-454 GB for
+V_abcd alone, so the basis grows with the number of GPUs such that each GPU's (ab) row block
+of V_abcd stays ~60-80 GB ("weak" scaling): 341 / 389 / 469 / 515 plane waves at 1 / 2 / 4 / 8
+GPUs.  Integrals are generated on the device from the k-vector table (synthetic data in
+the sense that nothing is read from disk; it is the physical TC-UEG Hamiltonian).
+
+Printed line: see the contract in the task statement; `value` is FP64 TFLOP/s computed from
+the ALGORITHMIC flop count of the reference's doubles residual
+F_CCD = 2o^2v^4 + 20o^3v^3 + 4o^4v^2 + 4o^2v^3 + 4o^3v^2 (T1-dressing flops are
+executed but not counted) divided by the measured time of a whole iteration.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_ELE, RS, K_CUTOFF = 54, 1.0, 2.0
+# plane-wave cutoff (units of (2pi/L)^2 / 2 ... ueg.py:128) -> nP for 54 electrons
+CUTOFF_FOR_GPUS = {1: 18.0, 2: 20.0, 4: 24.0, 8: 25.0}        # 341, 389, 469, 515 orbitals
+SM_COUNT, DMMA_FMA_PER_CLK_PER_SM = 148, 64
+
+
+def flops_ccd(o, v, is_dcd=False):
+    o, v = float(o), float(v)
+    if is_dcd:
+        return 2*o**2*v**4 + 10*o**3*v**3 + 2*o**4*v**2 + 4*o**2*v**3 + 4*o**3*v**2
+    return 2*o**2*v**4 + 20*o**3*v**3 + 4*o**4*v**2 + 4*o**2*v**3 + 4*o**3*v**2
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------
+# clocks / throttle reasons during the timed region
+# ----------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz, self.ok = None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:          # noqa: BLE001
+            log("clock sampler unavailable:", e)
+
+    def run(self):
+        while self.ok and not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:           # noqa: BLE001
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------
+# CPU arm: the oracle's restatement of the reference, in the reference's einsum modes
+# ----------------------------------------------------------------------------
+def cpu_sample(steps, warmup, budget_s=150.0):
+    """Time `steps` CCSD sweeps of the reference algorithm (oracle port) on a bounded sample of
+    the workload: the same TC-UEG 54e Hamiltonian in a smaller plane-wave basis."""
+    import numpy as np
+    from oracle import cc_oracle as oc, ueg_oracle as uo
+    cores = len(os.sched_getaffinity(0))
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    no = N_ELE // 2
+    pick = None
+    for cutoff, nP in ((7.0, 81), (6.0, 65), (5.0, 57), (4.0, 33)):
+        est = flops_ccd(no, nP - no) / 1.5e9 * (steps + warmup)      # ~1.5 GF/s as surveyed
+        pick = (cutoff, nP)
+        if est <= budget_s:
+            break
+    cutoff, nP = pick
+    m = uo.UEG(N_ELE, RS).init_single_basis(cutoff)
+    assert m.n_orb == nP
+    m.k_cutoff, m.gamma = K_CUTOFF, None
+    fock, V = m.tc_hamiltonian(no)
+    oc.set_ccd_einsum_mode("as_written")          # ccd.py uses bare np.einsum
+    dV = oc.partition(no, V)
+    eps_i, eps_a = fock.diagonal()[:no].copy(), fock.diagonal()[no:].copy()
+    _, T2 = oc.mp2(eps_i, eps_a, dV["ijab"], dV["abij"])
+    T1 = np.zeros((nP - no, no))
+    d1, d2 = oc.denominators(eps_i, eps_a)
+    mixer = oc.DIIS(6)
+    e = 0.0
+    for _ in range(warmup):
+        T1, T2, e, _dt = oc.ccsd_sweep(no, fock, dV, T1, T2, d1, d2, mixer)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        T1, T2, e, _dt = oc.ccsd_sweep(no, fock, dV, T1, T2, d1, d2, mixer)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    oc.set_ccd_einsum_mode("optimized")
+    F = flops_ccd(no, nP - no)
+    return {"value": F / dt / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+            "sample": "TC-UEG 54e rs=%.1f, %d plane waves (o=27, v=%d): %d CCSD+DIIS sweeps of the numpy "
+                      "oracle in the reference's einsum modes (ccd.py rows single-threaded c_einsum, "
+                      "ccsd.py rows optimize=True/BLAS), %.2f s per sweep" % (RS, nP, nP - no, steps, dt),
+            "seconds_per_step": dt, "n_orb": nP, "energy": float(sum(e))}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = args.steps, args.warmup
+    base = cpu_sample(steps, min(warmup, 1))
+    no = N_ELE // 2
+    line = {"impl": "reference", "metric": "ccsd_iteration_fp64_tflops", "value": base["value"],
+            "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(warmup, 1),
+            "ms_per_step": base["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus, no),
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, no):
+    cutoff = CUTOFF_FOR_GPUS[n_gpus]
+    return {"workload": "TC-UEG 54e rs=%.1f CCSD+DIIS iteration, plane-wave cutoff %g" % (RS, cutoff),
+            "method": "CCSD", "correlator": "trunc k_c=%g" % K_CUTOFF, "n_occ": no,
+            "l2_policy": "inputs_exceed_l2 (V_abcd row block >> 126 MB)",
+            "parallelism": "ab-block x%d" % n_gpus}
+
+
+# ----------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------
+def build_hamiltonian(m, no, a_range=None):
+    """Fock matrix (host) and the 16 partition blocks (device) of the TC-UEG Hamiltonian,
+    assembled as in pymes/test/test_ueg/test_symmetrised_2body_integral.py:84-160."""
+    import numpy as np
+    from pymes_b200.integral.partition import KEYS
+    nP = m.n_orb
+    parts = [("only_2b", m.trunc), ("effect_2b", m.trunc)]
+    # Fock from the pure 2-body part: f = h + 2 V_piqi - V_piiq  (hf.py:14-18)
+    W0, W1 = m.pair_tables("only_2b", m.trunc)
+    Vd = m.build_block((0, 0, 0, 0), (nP, no, nP, no), W0a=W0, W1a=W1).cpu().numpy()
+    Vx = m.build_block((0, 0, 0, 0), (nP, no, no, nP), W0a=W0, W1a=W1).cpu().numpy()
+    fock = np.diag(m.kinetic()).astype(np.float64)
+    fock += 2.0 * np.einsum("piqi->pq", Vd)
+    fock -= np.einsum("piiq->pq", Vx)
+    fock += np.diag(m.double_contractions_in_3_body())
+    del Vd, Vx
+    dV = m.eval_2b_blocks(no, list(KEYS), parts)
+    return fock, dV
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pymes_b200 import backend as bk, log as plog
+    from pymes_b200.model import ueg
+    from pymes_b200.solver import ccsd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    plog.set_quiet(True)
+    no = N_ELE // 2
+    cutoff = args.cutoff if args.cutoff else CUTOFF_FOR_GPUS[args.gpus]
+
+    t0 = time.time()
+    m = ueg.UEG(N_ELE, no, no, RS)
+    m.init_single_basis(cutoff)
+    m.k_cutoff, m.gamma = K_CUTOFF, None
+    nP, nv = m.n_orb, m.n_orb - no
+    if world > 1:
+        from pymes_b200 import parallel
+        comm = parallel.Comm(dist.group.WORLD)
+        cc = parallel.ShardedCCSD(no, comm)
+        fock, dV = parallel.build_sharded_hamiltonian(m, no, comm, build_hamiltonian)
+    else:
+        cc = ccsd.CCSD(no)
+        fock, dV = build_hamiltonian(m, no)
+    torch.cuda.synchronize()
+    t_build = time.time() - t0
+    if rank == 0:
+        log("TC-UEG 54e: nP=%d (o=%d, v=%d), integrals built in %.1f s, %.1f GB allocated"
+            % (nP, no, nv, t_build, torch.cuda.memory_allocated() / 1e9))
+    e_mp2 = cc.setup(fock, dV)
+    if rank == 0:
+        log("E_MP2 = %.10f" % e_mp2)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        e = cc.sweep()
+        if rank == 0:
+            log("warmup %d: E = %.10f" % (w, e[0] + e[1] + e[2]))
+
+    sampler = ClockSampler(local)
+    bk.enable_timing(True)
+    launches0 = bk.launch_count()
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for k in range(args.steps):
+        e = cc.sweep()
+    ev1.record()
+    barrier()
+    clocks = sampler.result()
+    launches = bk.launch_count() - launches0
+    ms = ev0.elapsed_time(ev1) / args.steps
+    regions = bk.timing_report()
+    bk.enable_timing(False)
+    e_final = e[0] + e[1] + e[2]
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    F = flops_ccd(no, nv)
+    value = F / (ms * 1e-3) / 1e12
+
+    # dominant kernel: the particle-particle ladder contraction (this rank's row block)
+    pp_ms = regions.get("pp_ladder", [])
+    rows = getattr(cc, "local_rows", nv) if world > 1 else nv
+    pp_flops = 2.0 * rows * nv * nv * nv * no * no
+    pp_avg = sum(pp_ms) / len(pp_ms) if pp_ms else None
+    peak = SM_COUNT * DMMA_FMA_PER_CLK_PER_SM * 2 * (clocks.get("sm_max_mhz") or 1965) * 1e6 / 1e12
+    roof = {"bound": "tensor", "kernel": "contract_kernel (pp ladder V_abcd.tau, DMMA.8x8x4)",
+            "achieved": (pp_flops / (pp_avg * 1e-3) / 1e12) if pp_avg else None,
+            "peak": peak, "unit": "TFLOP/s",
+            "peak_source": "FP64 tensor (DMMA) issue peak: 148 SM x 64 FMA/clk x 2 x sm_max_mhz; "
+                           "MEASURED_PEAKS.json has no FP64 entry (its bf16 figure does not apply)",
+            "traffic": None, "launches_timed": len(pp_ms), "ms_per_launch": pp_avg,
+            "flops_per_launch": pp_flops}
+    roof["frac"] = roof["achieved"] / peak if roof["achieved"] else None
+    if clocks.get("sm_mhz"):
+        roof["frac_at_observed_clock"] = (roof["achieved"] / (peak * clocks["sm_mhz"] / (clocks["sm_max_mhz"] or 1965))
+                                          if roof["achieved"] else None)
+    prof = os.path.join(ROOT, "profiles", "pp_ladder_traffic.json")
+    if os.path.exists(prof):
+        try:
+            roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:               # noqa: BLE001
+            pass
+
+    # end to end: amplitudes in pinned host memory every step, new amplitudes + energies back
+    t1h = torch.empty((nv, no), dtype=torch.float64).pin_memory()
+    rows_l = cc._st["T2"].shape[0]
+    t2h = torch.empty(tuple(cc._st["T2"].shape), dtype=torch.float64).pin_memory()
+    t1h.copy_(cc._st["T1"])
+    t2h.copy_(cc._st["T2"])
+    cc.sweep_host(t1h, t2h)
+    barrier()
+    tw = time.perf_counter()
+    for k in range(args.steps):
+        cc.sweep_host(t1h, t2h)
+    barrier()
+    e2e_ms = (time.perf_counter() - tw) / args.steps * 1e3
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    io_bytes = (t1h.numel() + t2h.numel()) * 8
+    e2e = {"value": F / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes + 8 * 8,
+           "api": "CCSD.sweep_host(T1, T2): amplitudes from pinned host memory in, one iteration, "
+                  "amplitudes and energies back; the static operator (Fock, V blocks) stays in HBM"}
+
+    line = {"metric": "ccsd_iteration_fp64_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(args.gpus, no), n_orb=nP, n_virt=nv,
+                           flops_per_step=F, energy=e_final, build_seconds=t_build),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof}
+    if rank == 0:
+        if args.gpus == 1 and not args.no_cpu:
+            cores = len(os.sched_getaffinity(0))
+            log("timing the CPU oracle on %d host cores ..." % cores)
+            line["cpu_baseline"] = cpu_sample(2, 0, budget_s=40.0)
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cutoff", type=float, default=0.0, help="override the plane-wave cutoff (debug)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.gpus not in CUTOFF_FOR_GPUS:
+        raise SystemExit("--gpus must be one of %s" % sorted(CUTOFF_FOR_GPUS))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

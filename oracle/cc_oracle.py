@@ -27,6 +27,22 @@ def _es(sub, *ops):
     return np.einsum(sub.replace(" ", ""), *ops, optimize=True)
 
 
+# ``pymes/solver/ccd.py`` calls bare ``np.einsum`` (no ``optimize``: numpy's single-threaded
+# c_einsum loop), while ccsd.py / eom_ccsd.py use ``optimize=True`` (ccsd.py:11).  The values
+# agree to round-off; the *timing* does not, so the CPU-baseline legs of bench.py switch the
+# ccd.py rows to "as_written" to time what the reference really executes.
+_MODE = {"ccd": "optimized"}
+
+
+def set_ccd_einsum_mode(mode):
+    assert mode in ("optimized", "as_written")
+    _MODE["ccd"] = mode
+
+
+def _es_ccd(sub, *ops):
+    return np.einsum(sub.replace(" ", ""), *ops, optimize=(_MODE["ccd"] == "optimized"))
+
+
 # --------------------------------------------------------------------------
 # integral partition -- reference pymes/integral/partition.py:4-39
 # --------------------------------------------------------------------------
@@ -90,22 +106,22 @@ def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj,
 
     I = V_klij.copy()                                           # ccd.py:178-180
     if ccd:
-        I = I + _es("klcd,cdij->klij", V_ijab, T2)
-    R = V_abij + _es("klij,abkl->abij", I, T2)                  # ccd.py:185-186
-    R = R + _es("abcd,cdij->abij", V_abcd, T2)                  # ccd.py:187
+        I = I + _es_ccd("klcd,cdij->klij", V_ijab, T2)
+    R = V_abij + _es_ccd("klij,abkl->abij", I, T2)                  # ccd.py:185-186
+    R = R + _es_ccd("abcd,cdij->abij", V_abcd, T2)                  # ccd.py:187
     if ccd:                                                     # ccd.py:189-191
-        R = R + _es("alcj,cbil->abij", _es("klcd,adkj->alcj", V_ijab, T2), T2)
-    R = R + _es("acik,cbkj->abij", Tt,
-                _es("klcd,dblj->cbkj", V_ijab, Tt))             # ccd.py:202-204
+        R = R + _es_ccd("alcj,cbil->abij", _es_ccd("klcd,adkj->alcj", V_ijab, T2), T2)
+    R = R + _es_ccd("acik,cbkj->abij", Tt,
+                _es_ccd("klcd,dblj->cbkj", V_ijab, Tt))             # ccd.py:202-204
 
     if is_bruekner:                                             # ccd.py:209-211
         Xac, Xki = fab.copy(), fij.copy()
     else:                                                       # ccd.py:213-216
-        Xac = fab - 0.5 * _es("adkl,lkdc->ac", Tt, V_ijab)
-        Xki = fij + 0.5 * _es("cdil,lkdc->ki", Tt, V_ijab)
+        Xac = fab - 0.5 * _es_ccd("adkl,lkdc->ac", Tt, V_ijab)
+        Xki = fij + 0.5 * _es_ccd("cdil,lkdc->ki", Tt, V_ijab)
     if ccd:                                                     # ccd.py:218-221
-        Xac = Xac - 0.5 * _es("adkl,lkdc->ac", Tt, V_ijab)
-        Xki = Xki + 0.5 * _es("cdil,lkdc->ki", Tt, V_ijab)
+        Xac = Xac - 0.5 * _es_ccd("adkl,lkdc->ac", Tt, V_ijab)
+        Xki = Xki + 0.5 * _es_ccd("cdil,lkdc->ki", Tt, V_ijab)
 
     ops = {"Xac": Xac, "Xki": Xki, "T": T2, "Tt": Tt, "iajb": V_iajb,
            "iabj": V_iabj}
@@ -119,19 +135,19 @@ def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj,
         (+1.0, "alci,bclj->abij", "Xp", "T", True),             # ccd.py:240
     ]
     if ccd:
-        ops["Xp"] = _es("klcd,daki->alci", V_ijab, T2)          # ccd.py:238
+        ops["Xp"] = _es_ccd("klcd,daki->alci", V_ijab, T2)          # ccd.py:238
     Ex = np.zeros_like(R)
     for coef, sub, a, b, ccd_only in ex_rows:
         if ccd_only and not ccd:
             continue
-        Ex += coef * _es(sub, ops[a], ops[b])
+        Ex += coef * _es_ccd(sub, ops[a], ops[b])
     return R + Ex + Ex.transpose(1, 0, 3, 2)                    # ccd.py:249-252
 
 
 def ccd_energy(T2, V_ijab):
     """(direct, exchange) -- reference ccd.py:256-262."""
-    return (2.0 * _es("abij,ijab->", T2, V_ijab),
-            -1.0 * _es("abij,ijba->", T2, V_ijab))
+    return (2.0 * _es_ccd("abij,ijab->", T2, V_ijab),
+            -1.0 * _es_ccd("abij,ijba->", T2, V_ijab))
 
 
 def ccsd_energy(f_ia, T1, T2, V_ijab):
@@ -341,6 +357,21 @@ def ccd_solve(no, fock, V, level_shift=0.0, is_dcd=False, is_diis=True,
     return {"e": e, "t2": T2, "dE": dE, "iterations": it, "e_mp2": e_mp2}
 
 
+def ccsd_sweep(no, fock, dV, T1, T2, d1, d2, mixer=None, is_dcsd=False):
+    """One iteration of the CCSD loop body, reference ccsd.py:159-194."""
+    ft = dressed_fock(no, fock, T1, dV)
+    dVt = dressed_V(T1, dV)
+    R1 = singles_residual(no, ft, T1, T2, dV)                   # ccsd.py:167-168
+    R2 = doubles_residual(no, ft, T2, dVt["klij"], dVt["ijab"], dVt["abij"],
+                          dVt["iajb"], dVt["iabj"], dVt["abcd"], is_dcsd)
+    dT1, dT2 = R1 / d1, R2 / d2
+    T1 = T1 + dT1
+    T2 = T2 + dT2
+    if mixer is not None:
+        T1, T2 = mixer.mix([dT1, dT2], [T1, T2])
+    return T1, T2, ccsd_energy(fock[:no, no:], T1, T2, dV["ijab"]), dT2
+
+
 def ccsd_solve(no, fock, V, level_shift=0.0, is_dcsd=False, is_diis=True,
                delta_e=1e-8, max_iter=50, amps=None, trace=None):
     nv = fock.shape[0] - no
@@ -355,17 +386,7 @@ def ccsd_solve(no, fock, V, level_shift=0.0, is_dcsd=False, is_diis=True,
     dE, e_last, e, it = abs(e_mp2), e_mp2, 0.0, 0
     while abs(dE) > delta_e and it <= max_iter:
         it += 1
-        ft = dressed_fock(no, fock, T1, dV)
-        dVt = dressed_V(T1, dV)
-        R1 = singles_residual(no, ft, T1, T2, dV)               # ccsd.py:167-168
-        R2 = doubles_residual(no, ft, T2, dVt["klij"], dVt["ijab"], dVt["abij"],
-                              dVt["iajb"], dVt["iabj"], dVt["abcd"], is_dcsd)
-        dT1, dT2 = R1 / d1, R2 / d2
-        T1 = T1 + dT1
-        T2 = T2 + dT2
-        if mixer is not None:
-            T1, T2 = mixer.mix([dT1, dT2], [T1, T2])
-        e1, ed, ex = ccsd_energy(fock[:no, no:], T1, T2, dV["ijab"])
+        T1, T2, (e1, ed, ex), dT2 = ccsd_sweep(no, fock, dV, T1, T2, d1, d2, mixer, is_dcsd)
         e = e1 + ed + ex
         dE, e_last = e - e_last, e
         if trace is not None:

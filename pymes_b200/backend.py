@@ -101,6 +101,44 @@ def launch_count():
 
 
 # --------------------------------------------------------------------------
+# optional per-region device timing (CUDA events on the launching stream; used by
+# bench.py for the roofline of the dominant kernel -- no synchronisation is added)
+# --------------------------------------------------------------------------
+_timing = {"on": False, "events": {}}
+
+
+def enable_timing(flag=True):
+    _timing["on"] = bool(flag)
+    _timing["events"] = {}
+
+
+class timed:
+    """``with timed("pp_ladder"): ...`` records start/stop events when timing is enabled."""
+
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if _timing["on"]:
+            self.t0 = torch.cuda.Event(enable_timing=True)
+            self.t1 = torch.cuda.Event(enable_timing=True)
+            self.t0.record(torch.cuda.current_stream())
+        return self
+
+    def __exit__(self, *exc):
+        if _timing["on"]:
+            self.t1.record(torch.cuda.current_stream())
+            _timing["events"].setdefault(self.tag, []).append((self.t0, self.t1))
+        return False
+
+
+def timing_report():
+    """{tag: [milliseconds per recorded region]} (synchronises the device)."""
+    torch.cuda.synchronize()
+    return {tag: [a.elapsed_time(b) for a, b in ev] for tag, ev in _timing["events"].items()}
+
+
+# --------------------------------------------------------------------------
 # contraction front end
 # --------------------------------------------------------------------------
 def _parse(spec):

@@ -125,6 +125,23 @@ class UEG:
         vals = np.asarray(correlator(n2 * (2 * np.pi / self.L) ** 2), dtype=np.float64)
         return torch.from_numpy(np.ascontiguousarray(vals)).to(bk.device())
 
+    def _umat_device(self, desc, q_int, lattice_cutoff):
+        lib = _lib.load()
+        q_int = np.ascontiguousarray(np.asarray(q_int).reshape(-1, 3).astype(np.int32))
+        qdev = torch.from_numpy(q_int.reshape(-1)).to(bk.device())
+        out = bk.empty(len(q_int))
+        _lib.check(lib.pmb_ueg_umat(C.byref(desc), float(self.L), int(lattice_cutoff), len(q_int),
+                                    bk._ptr(qdev), bk._ptr(out), bk._stream()), "pmb_ueg_umat")
+        return out
+
+    def umat(self, q_int, correlator, lattice_cutoff=30):
+        """u_mat(q) = sum_k' (k'.(q-k')) u(k'^2) u((q-k')^2) / Omega over the [-30,30]^3 lattice
+        (``sumNablaUSquare``, ueg.py:581-596) for integer transfer vectors ``q_int`` [nq,3]."""
+        self.correlator = correlator
+        u_table = self._correlator_table(correlator, lattice_cutoff)
+        desc = self._descriptor(u_table)
+        return self._umat_device(desc, q_int, lattice_cutoff).cpu().numpy()
+
     def pair_tables(self, mode, correlator=None, lattice_cutoff=30):
         """(W0, W1, descriptor keep-alives) for one branch of ueg.py:411-504."""
         lib = _lib.load()
@@ -141,10 +158,7 @@ class UEG:
             k = self.k_int().astype(np.int64)
             q = (k[None, :, :] - k[:, None, :]).reshape(-1, 3)          # q[p*nP+r] = k_r - k_p
             uniq, inverse = np.unique(q, axis=0, return_inverse=True)
-            qdev = torch.from_numpy(uniq.astype(np.int32).reshape(-1)).to(bk.device())
-            umat_q = bk.empty(len(uniq))
-            _lib.check(lib.pmb_ueg_umat(C.byref(desc), float(self.L), int(lattice_cutoff), len(uniq),
-                                        bk._ptr(qdev), bk._ptr(umat_q), bk._stream()), "pmb_ueg_umat")
+            umat_q = self._umat_device(desc, uniq, lattice_cutoff)
             idx = torch.from_numpy(inverse.reshape(-1).astype(np.int64)).to(bk.device())
             umat_pr = umat_q[idx].contiguous()
         W0, W1 = bk.empty(nP * nP), bk.empty(nP * nP)

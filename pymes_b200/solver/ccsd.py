@@ -133,7 +133,8 @@ def tau_ladder(T1, dV):
         ct = bk.contract_terms
         tau = bk.copy(T2)
         ct("abij", [(1.0, "ai", T1, "bj", T1)], out=tau, beta=1.0)
-        ct("abij", [(1.0, "abcd", dV["abcd"], "cdij", tau)], out=R, beta=1.0)
+        with bk.timed("pp_ladder"):
+            ct("abij", [(1.0, "abcd", dV["abcd"], "cdij", tau)], out=R, beta=1.0)
         W1 = ct("kbij", [(1.0, "kbcd", dV["iabc"], "cdij", tau)])
         ct("abij", [(-1.0, "ak", T1, "kbij", W1)], out=R, beta=1.0)
         W2 = ct("alij", [(1.0, "alcd", dV["aibc"], "cdij", tau)])
@@ -202,77 +203,115 @@ class CCSD(ccd.CCD):
         return [float(s[4]), float(s[0]), float(s[1])]
 
     # ------------------------------------------------------------------
-    def solve(self, t_fock_pq, t_V_pqrs, level_shift=0., amps=None, sp=0, **kwargs):
-        algo_name = "ccsd.solve"
-        t_start = time.time()
+    def setup(self, t_fock_pq, t_V_pqrs, level_shift=0., amps=None):
+        """Upload the static operator (Fock, V blocks), MP2 start amplitudes (ccsd.py:118-156).
+        ``t_V_pqrs`` is V_pqrs (numpy / CUDA tensor) or -- extension for systems whose V_pqrs
+        cannot exist as one array -- a dict of the 16 partition blocks as CUDA tensors."""
         no = self.no
-        delta = self.delta
-        max_iter = kwargs.get("max_iter", self.max_iter)
-        delta_e = kwargs.get("delta_e", self.delta_e)
         blocks_given = isinstance(t_V_pqrs, dict)
-        want_numpy = not (blocks_given or isinstance(t_V_pqrs, torch.Tensor))
-
         fock_host = bk.tonumpy(t_fock_pq)
         nv = fock_host.shape[0] - no
-        eps_i = bk.asdev(fock_host.diagonal()[:no].copy())
-        eps_a = bk.asdev(fock_host.diagonal()[no:].copy())
-        fock = bk.asdev(fock_host)
-        if blocks_given:       # extension: pre-partitioned blocks (V_pqrs too big to exist)
-            dV = _dev_dict(t_V_pqrs)
-            dtype_name = "float64"
+        st = self._st = {}
+        st["want_numpy"] = not (blocks_given or isinstance(t_V_pqrs, torch.Tensor))
+        st["eps_i"] = bk.asdev(fock_host.diagonal()[:no].copy())
+        st["eps_a"] = bk.asdev(fock_host.diagonal()[no:].copy())
+        st["fock"] = bk.asdev(fock_host)
+        if blocks_given:
+            st["dV"] = _dev_dict(t_V_pqrs)
+            st["dtype_name"] = "float64"
         else:
             V = bk.asdev(t_V_pqrs)
-            dV = part_2_body_int(no, V)
-            dtype_name = str(V.dtype).replace("torch.", "")
-
-        print_logging_info(algo_name)
-        print_logging_info("Using dcsd: ", self.is_dcd, level=1)
-        print_logging_info("Solving doubles amplitude equation", level=1)
-        print_logging_info("Using data type %s" % dtype_name, level=1)
-        print_logging_info("Using DIIS mixer: ", self.is_diis, level=1)
-        print_logging_info("Iteration = 0", level=1)
-
-        e_mp2, T2 = mp2.solve_device(eps_i, eps_a, dV["ijab"], dV["abij"], level_shift)
+            st["dV"] = part_2_body_int(no, V)
+            st["dtype_name"] = str(V.dtype).replace("torch.", "")
+        st["shift"] = level_shift
+        e_mp2, T2 = mp2.solve_device(st["eps_i"], st["eps_a"], st["dV"]["ijab"], st["dV"]["abij"],
+                                     level_shift)
         T1 = bk.zeros(nv, no)
-        amps_host = None
+        st["amps_host"] = None
         if amps is not None:
             if isinstance(amps[0], torch.Tensor):
                 T1, T2 = bk.asdev(amps[0]), bk.asdev(amps[1])
             else:
-                amps_host = amps
+                st["amps_host"] = amps
                 T1, T2 = bk.asdev(amps[0]).contiguous(), bk.asdev(amps[1]).contiguous()
+        st["T1"], st["T2"] = T1, T2
+        st["scal"] = bk.zeros(8)
+        st["e_mp2"] = e_mp2
+        st["iteration"] = 0
+        return e_mp2
 
-        scal = bk.zeros(8)
+    def sweep(self):
+        """One CCSD/DCSD iteration (loop body ccsd.py:159-197) on the device-resident state:
+        dressing -> singles + doubles residual -> update -> DIIS -> energy.
+        Returns (e_1b, e_dir, e_ex, |T2|, |dT2|)."""
+        st = self._st
+        no, dV, fock = self.no, st["dV"], st["fock"]
+        T1, T2, scal = st["T1"], st["T2"], st["scal"]
+        eps_i, eps_a, shift = st["eps_i"], st["eps_a"], st["shift"]
+        st["iteration"] += 1
+        ft = dressed_fock(no, fock, T1, dV)
+        R1 = singles_residual(no, ft, T1, T2, dV)
+        R2 = ccd.doubles_residual(
+            no, ft, T2, dressed_block("klij", T1, dV), dV["ijab"],
+            dressed_block("abij", T1, dV, skip_tau=True), dressed_block("iajb", T1, dV),
+            dressed_block("iabj", T1, dV), None, is_dcd=self.is_dcd,
+            pp_ladder=tau_ladder(T1, dV))
+        dT1 = bk.update_singles(eps_i, eps_a, shift, self.delta, R1, T1)
+        dT2 = bk.update_doubles(eps_i, eps_a, shift, self.delta, R2, T2, scal[3:4])
+        del R1, R2
+        amps_host = st["amps_host"]
+        if amps_host is not None and (st["iteration"] == 1 or not self.is_diis):
+            amps_host[0][...] = bk.tonumpy(T1)          # the reference mutates `amps` in place
+            amps_host[1][...] = bk.tonumpy(T2)
+        if self.is_diis:
+            T1, T2 = self.mixer.mix([dT1, dT2], [T1, T2])
+        st["T1"], st["T2"] = T1, T2
+        bk.energy_doubles(T2, dV["ijab"], scal, T1=T1)
+        bk.contract_terms("", [(2.0, "ia", fock[:no, no:], "ai", T1)], out=scal[4])
+        s = scal.cpu().numpy()
+        return float(s[4]), float(s[0]), float(s[1]), float(np.sqrt(s[2])), float(np.sqrt(s[3]))
+
+    def sweep_host(self, t1_host, t2_host):
+        """Host-buffer form of :meth:`sweep`: amplitudes come in as host tensors / arrays
+        (pinned memory makes the copy asynchronous), one iteration runs on the device, and the
+        new amplitudes are copied back into the same host buffers.  Returns the energies and
+        norms of :meth:`sweep`.  The static operator (Fock, V blocks) stays device-resident."""
+        st = self._st
+        t1 = t1_host if isinstance(t1_host, torch.Tensor) else torch.from_numpy(t1_host)
+        t2 = t2_host if isinstance(t2_host, torch.Tensor) else torch.from_numpy(t2_host)
+        st["T1"] = t1.to(bk.device(), non_blocking=True)
+        st["T2"] = t2.to(bk.device(), non_blocking=True)
+        out = self.sweep()
+        t1.copy_(st["T1"], non_blocking=True)
+        t2.copy_(st["T2"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out
+
+    def solve(self, t_fock_pq, t_V_pqrs, level_shift=0., amps=None, sp=0, **kwargs):
+        algo_name = "ccsd.solve"
+        t_start = time.time()
+        max_iter = kwargs.get("max_iter", self.max_iter)
+        delta_e = kwargs.get("delta_e", self.delta_e)
+
+        print_logging_info(algo_name)
+        print_logging_info("Using dcsd: ", self.is_dcd, level=1)
+        print_logging_info("Solving doubles amplitude equation", level=1)
+        e_mp2 = self.setup(t_fock_pq, t_V_pqrs, level_shift, amps)
+        st = self._st
+        print_logging_info("Using data type %s" % st["dtype_name"], level=1)
+        print_logging_info("Using DIIS mixer: ", self.is_diis, level=1)
+        print_logging_info("Iteration = 0", level=1)
+
         dE = abs(e_mp2)
         iteration = 0
         e_last = e_mp2
         e_ccsd = e_1b = e_dir = e_ex = 0.0
-        f_ia = fock[:no, no:]
         while abs(dE) > delta_e and iteration <= max_iter:
             iteration += 1
-            ft = dressed_fock(no, fock, T1, dV)
-            R1 = singles_residual(no, ft, T1, T2, dV)
-            R2 = ccd.doubles_residual(
-                no, ft, T2, dressed_block("klij", T1, dV), dV["ijab"],
-                dressed_block("abij", T1, dV, skip_tau=True), dressed_block("iajb", T1, dV),
-                dressed_block("iabj", T1, dV), None, is_dcd=self.is_dcd,
-                pp_ladder=tau_ladder(T1, dV))
-            dT1 = bk.update_singles(eps_i, eps_a, level_shift, delta, R1, T1)
-            dT2 = bk.update_doubles(eps_i, eps_a, level_shift, delta, R2, T2, scal[3:4])
-            del R1, R2
-            if amps_host is not None and (iteration == 1 or not self.is_diis):
-                amps_host[0][...] = bk.tonumpy(T1)
-                amps_host[1][...] = bk.tonumpy(T2)
-            if self.is_diis:
-                T1, T2 = self.mixer.mix([dT1, dT2], [T1, T2])
-            bk.energy_doubles(T2, dV["ijab"], scal, T1=T1)
-            bk.contract_terms("", [(2.0, "ia", f_ia, "ai", T1)], out=scal[4])
-            s = scal.cpu().numpy()
-            e_dir, e_ex, e_1b = float(s[0]), float(s[1]), float(s[4])
+            e_1b, e_dir, e_ex, t2_norm, res_norm = self.sweep()
             e_ccsd = e_1b + e_dir + e_ex
             dE = e_ccsd - e_last
             e_last = e_ccsd
-            t2_norm, res_norm = float(np.sqrt(s[2])), float(np.sqrt(s[3]))
             if iteration <= max_iter:
                 print_logging_info("Iteration = ", iteration, level=1)
                 print_logging_info("Correlation Energy = {:.14f}".format(e_ccsd), level=2)
@@ -288,7 +327,8 @@ class CCSD(ccd.CCD):
         print_logging_info("CCSD correlation energy = {:.12f}".format(e_ccsd), level=1)
         print_logging_info("{:.3f} seconds spent on ccsd".format(time.time() - t_start), level=1)
         self.iterations = iteration
-        if want_numpy:
+        T1, T2, eps_i, eps_a = st["T1"], st["T2"], st["eps_i"], st["eps_a"]
+        if st["want_numpy"]:
             T1, T2, eps_i, eps_a = (bk.tonumpy(x) for x in (T1, T2, eps_i, eps_a))
         self.t_T_ai = T1
         self.t_T_abij = T2

@@ -1,0 +1,349 @@
+"""Parity of the CUDA path (through the C ABI in libpymes_b200.so) with the CPU oracle
+and the reference-generated goldens.  Needs a B200: run with ``-m gpu``.
+
+Tolerances (north_star): correlation energy 1e-10 Eh, amplitudes 1e-9 relative."""
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import golden
+from tests import test_host_logic as host
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _native_library_loaded():
+    """Fail loudly (not skip) if the CUDA extension is not what runs."""
+    assert torch.cuda.is_available(), "the -m gpu tests need a CUDA device"
+    from pymes_b200 import _lib, backend as bk
+    lib = _lib.load()
+    import ctypes as C
+    sm, cc, mem = C.c_int(), C.c_int(), C.c_size_t()
+    _lib.check(lib.pmb_device_info(C.byref(sm), C.byref(cc), C.byref(mem)))
+    assert cc.value >= 100, "libpymes_b200.so is built for sm_100a"
+    before = bk.launch_count()
+    yield
+    assert bk.launch_count() > before, "no kernel of libpymes_b200.so was launched"
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+# --------------------------------------------------------------------------
+# the host-logic checks, now on the real kernels (cpu_abi=None -> CUDA path)
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("spec,shapes", host.test_contract_matches_einsum.pytestmark[0].args[1])
+def test_contract_small(spec, shapes):
+    host.test_contract_matches_einsum(None, spec, shapes)
+
+
+def test_contract_views_multi_term():
+    host.test_contract_on_strided_views_and_multi_term(None)
+
+
+def test_multi_operand_einsum():
+    host.test_multi_operand_einsum(None)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_ccd_residual_energy_mp2(tag):
+    host.test_ccd_residual_energy_mp2(None, tag)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_ccsd_dressing_singles_doubles(tag):
+    host.test_ccsd_dressing_singles_doubles(None, tag)
+
+
+def test_diis_sequence():
+    host.test_diis_matches_reference_sequence(None)
+
+
+@pytest.mark.parametrize("tag", ["LiH_321g", "LiH_tc"])
+def test_molecule_solvers_iteration_parity(tag, capsys):
+    host.test_solvers_follow_reference_iteration_by_iteration(None, tag, capsys)
+
+
+def test_amps_aliasing():
+    host.test_amps_warm_start_aliasing(None)
+
+
+def test_ueg_coulomb_build_and_fock():
+    host.test_ueg_coulomb_integrals_and_ccd(None)
+
+
+def test_ueg_tc_tables():
+    host.test_ueg_tc_tables_small(None)
+
+
+# --------------------------------------------------------------------------
+# contraction engine: every tile configuration, both load mappings, ragged edges,
+# split-K, multi-term accumulation, strided views
+# --------------------------------------------------------------------------
+CASES = [
+    # pp ladder shapes (M=v^2, K=v^2, N=o^2); N=49 is the hostile 14-electron case
+    ("abcd,cdij->abij", [(50, 50, 50, 50), (50, 50, 7, 7)]),
+    ("abcd,cdij->abij", [(23, 23, 23, 23), (23, 23, 13, 13)]),
+    # hh ladder / I build: tiny K or tiny M -> split-K path
+    ("klij,abkl->abij", [(7, 7, 7, 7), (40, 40, 7, 7)]),
+    ("klcd,cdij->klij", [(6, 6, 45, 45), (45, 45, 6, 6)]),
+    # ring-type, interleaved M/K/N groups
+    ("klcd,adkj->alcj", [(9, 9, 31, 31), (31, 31, 9, 9)]),
+    ("alcj,cbil->abij", [(31, 9, 31, 9), (31, 31, 9, 9)]),
+    ("acik,cbkj->abij", [(33, 33, 8, 8), (33, 33, 8, 8)]),
+    ("kbic,ackj->abij", [(8, 33, 8, 33), (33, 33, 8, 8)]),
+    ("acik,kbcj->abij", [(33, 33, 8, 8), (8, 33, 33, 8)]),
+    # Fock-like
+    ("adkl,lkdc->ac", [(37, 37, 6, 6), (6, 6, 37, 37)]),
+    ("cdil,lkdc->ki", [(37, 37, 6, 6), (6, 6, 37, 37)]),
+    ("ac,cbij->abij", [(41, 41), (41, 41, 5, 5)]),
+    ("ki,abkj->abij", [(5, 5), (41, 41, 5, 5)]),
+    # T1-dressing shapes
+    ("kbcd,cdij->kbij", [(5, 29, 29, 29), (29, 29, 5, 5)]),
+    ("ak,kbij->abij", [(29, 5), (5, 29, 5, 5)]),
+    ("ai,bj->abij", [(17, 4), (17, 4)]),
+    ("ia,ai->", [(6, 300), (300, 6)]),
+    # plain big GEMM crossing many tiles in both directions
+    ("mk,kn->mn", [(517, 301), (301, 389)]),
+]
+
+
+@pytest.mark.parametrize("cfg", [-1, 0, 1, 2, 3])
+@pytest.mark.parametrize("spec,shapes", CASES)
+def test_contract_engine(spec, shapes, cfg):
+    from pymes_b200 import _lib, backend as bk
+    rng = np.random.default_rng(hash(spec) % 1000 + len(shapes[0]))
+    A, B = (rng.standard_normal(s) for s in shapes)
+    ref = np.einsum(spec, A, B, optimize=True)
+    _lib.load().pmb_contract_set_tuning(cfg, 0)
+    try:
+        got = bk.contract(spec, A, B, alpha=-0.75)
+        assert _rel(got.cpu().numpy(), -0.75 * ref) < 1e-13
+        out = bk.asdev(rng.standard_normal(ref.shape))
+        keep = out.cpu().numpy().copy()
+        bk.contract(spec, A, B, out=out, alpha=1.25, beta=-0.5)
+        assert _rel(out.cpu().numpy(), -0.5 * keep + 1.25 * ref) < 1e-13
+    finally:
+        _lib.load().pmb_contract_set_tuning(-1, 0)
+
+
+@pytest.mark.parametrize("split", [1, 2, 3, 7, 16])
+def test_contract_split_k(split):
+    from pymes_b200 import _lib, backend as bk
+    rng = np.random.default_rng(split)
+    A = rng.standard_normal((6, 6, 41, 41))
+    B = rng.standard_normal((41, 41, 6, 6))
+    ref = np.einsum("klcd,cdij->klij", A, B, optimize=True)
+    _lib.load().pmb_contract_set_tuning(-1, split)
+    try:
+        out = bk.asdev(np.ones_like(ref))
+        bk.contract("klcd,cdij->klij", A, B, out=out, beta=2.0)
+        assert _rel(out.cpu().numpy(), 2.0 + ref) < 1e-13
+    finally:
+        _lib.load().pmb_contract_set_tuning(-1, 0)
+
+
+def test_contract_views_of_V_pqrs_no_symmetry():
+    """Operands are strided views of one V_pqrs with NO permutational symmetry."""
+    from pymes_b200 import backend as bk
+    from pymes_b200.integral.partition import part_2_body_int
+    rng = np.random.default_rng(11)
+    no, nv = 5, 21
+    n = no + nv
+    V = rng.standard_normal((n, n, n, n))
+    T = rng.standard_normal((nv, nv, no, no))
+    dV, dVn = part_2_body_int(no, bk.asdev(V)), part_2_body_int(no, V)
+    Td = bk.asdev(T)
+    for spec, key in (("abcd,cdij->abij", "abcd"), ("klcd,cdij->klij", "ijab"),
+                      ("kaic,cbkj->abij", "iajb"), ("kbcj,acik->abij", "iabj"),
+                      ("kbcd,cdij->kbij", "iabc"), ("alcd,cdij->alij", "aibc")):
+        got = bk.contract(spec, dV[key], Td).cpu().numpy()
+        assert _rel(got, np.einsum(spec, dVn[key], T, optimize=True)) < 1e-13, spec
+
+
+def test_contract_eight_terms_one_launch():
+    from pymes_b200 import backend as bk
+    rng = np.random.default_rng(5)
+    nv, no = 19, 6
+    Ts = [rng.standard_normal((nv, nv, no, no)) for _ in range(8)]
+    Xs = [rng.standard_normal((nv, nv, no, no)) for _ in range(8)]
+    before = bk.launch_count()
+    got = bk.contract_terms("abij", [(0.1 * (k + 1), "acik", bk.asdev(Ts[k]), "cbkj", bk.asdev(Xs[k]))
+                                     for k in range(8)])
+    assert bk.launch_count() - before == 1
+    ref = sum(0.1 * (k + 1) * np.einsum("acik,cbkj->abij", Ts[k], Xs[k]) for k in range(8))
+    assert _rel(got.cpu().numpy(), ref) < 1e-13
+
+
+def test_contract_bad_arguments():
+    from pymes_b200 import _lib
+    import ctypes as C
+    lib = _lib.load()
+    d = _lib.Contract()
+    d.nterms = 0
+    assert lib.pmb_contract(C.byref(d), None, 0, None) == -1
+    with pytest.raises(RuntimeError, match="bad argument"):
+        _lib.check(-1, "x")
+
+
+# --------------------------------------------------------------------------
+# elementwise kernels against plain numpy
+# --------------------------------------------------------------------------
+def test_elementwise_kernels():
+    from pymes_b200 import backend as bk
+    rng = np.random.default_rng(3)
+    no, nv = 6, 17
+    ei, ea = np.sort(rng.uniform(-2, -1, no)), np.sort(rng.uniform(1, 3, nv))
+    T = rng.standard_normal((nv, nv, no, no))
+    R = rng.standard_normal((nv, nv, no, no))
+    V = rng.standard_normal((no, no, nv, nv))
+    T1 = rng.standard_normal((nv, no))
+    D = (ei[None, None, :, None] + ei[None, None, None, :] - ea[:, None, None, None]
+         - ea[None, :, None, None] + 0.25)
+    Td, scal = bk.asdev(T.copy()), bk.zeros(8)
+    dT = bk.update_doubles(bk.asdev(ei), bk.asdev(ea), 0.25, 1.0, bk.asdev(R), Td, scal[3:4])
+    assert _rel(dT.cpu().numpy(), R / D) < 1e-14
+    assert _rel(Td.cpu().numpy(), T + R / D) < 1e-14
+    assert abs(scal[3].item() - np.sum((R / D) ** 2)) < 1e-10 * np.sum((R / D) ** 2)
+    bk.energy_doubles(bk.asdev(T), bk.asdev(V), scal, T1=bk.asdev(T1))
+    tau = T + np.einsum("ai,bj->abij", T1, T1)
+    s = scal.cpu().numpy()
+    assert abs(s[0] - 2 * np.einsum("abij,ijab->", tau, V)) < 1e-10
+    assert abs(s[1] + np.einsum("abij,ijba->", tau, V)) < 1e-10
+    assert abs(s[2] - np.sum(T * T)) < 1e-10
+    assert _rel(bk.tilde(bk.asdev(T)).cpu().numpy(), 2 * T - T.transpose(1, 0, 2, 3)) == 0
+    assert _rel(bk.tilde(bk.asdev(T), swap_ij=True).cpu().numpy(), 2 * T - T.transpose(0, 1, 3, 2)) == 0
+    Rd = bk.asdev(R.copy())
+    bk.sym_baji(bk.asdev(T), Rd, accumulate=True)
+    assert _rel(Rd.cpu().numpy(), R + T + T.transpose(1, 0, 3, 2)) < 1e-15
+    xs = [rng.standard_normal(1000003) for _ in range(7)]
+    y = rng.standard_normal(1000003)
+    got = bk.dots([bk.asdev(x) for x in xs], bk.asdev(y)).cpu().numpy()
+    np.testing.assert_allclose(got, [x @ y for x in xs], rtol=1e-11, atol=1e-9)
+    c = rng.standard_normal(7)
+    got = bk.lincomb(c, [bk.asdev(x) for x in xs]).cpu().numpy()
+    np.testing.assert_allclose(got, sum(ci * x for ci, x in zip(c, xs)), rtol=1e-13, atol=1e-13)
+    src = bk.asdev(V)
+    got = bk.axpby(2.0, src.permute(2, 3, 0, 1)).cpu().numpy()
+    assert _rel(got, 2 * V.transpose(2, 3, 0, 1)) == 0
+
+
+# --------------------------------------------------------------------------
+# solvers against goldens that only make sense at GPU speed
+# --------------------------------------------------------------------------
+def test_hf_augccpvdz_ccsd_diis_full_subspace():
+    """HF / aug-cc-pVDZ (o=5, v=27): DIIS subspace overflows -> bug-compatible bookkeeping."""
+    from pymes_b200.solver import ccsd
+    g = golden("mol_HF_augccpvdz")
+    no = int(g["n_elec"]) // 2
+    for name, flag in (("ccsd", False), ("dcsd", True)):
+        cc = ccsd.CCSD(no, is_dcsd=flag)
+        r = cc.solve(g["fock"], g["V"], delta_e=1e-8, max_iter=50)
+        assert cc.iterations == len(g[name + "_trace"])
+        assert abs(r["ccsd e"] - g[name + "_e"]) < 1e-10
+        assert _rel(r["t2"], g[name + "_t2"]) < 1e-9
+        assert _rel(r["t1"], g[name + "_t1"]) < 1e-9
+
+
+def test_ueg_14e_ccd_dcd_reference_goldens():
+    """UEG 14e / 57 PW (config 1): rs=1.0 to convergence and the rs=0.5, shift -1 constants of
+    pymes/test/test_ueg/test_ccd_dcd.py:208-209."""
+    from pymes_b200.model import ueg
+    from pymes_b200.mean_field import hf
+    from pymes_b200.solver import ccd, dcd
+    g = golden("ueg_coulomb")
+    for rs, tag, shift in ((1.0, "rs1", 0.0), (0.5, "rs05", -1.0)):
+        m = ueg.UEG(14, 7, 7, rs)
+        m.init_single_basis(5.0)
+        V = m.eval_2b_integrals(device=True)
+        assert V.is_cuda
+        fock = hf.construct_hf_matrix(7, np.diag(m.kinetic()), V)
+        np.testing.assert_allclose(fock.cpu().numpy() if isinstance(fock, torch.Tensor) else fock,
+                                   g[tag + "_fock"], rtol=1e-12, atol=1e-13)
+        cc = ccd.CCD(7)
+        r = cc.solve(g[tag + "_fock"], V, level_shift=shift)
+        assert cc.iterations == len(g[tag + "_ccd_trace"])
+        assert abs(r["ccd e"] - g[tag + "_ccd_e"]) < 1e-10
+        dd = dcd.DCD(7)
+        r = dd.solve(g[tag + "_fock"], V, level_shift=shift)
+        assert cc.iterations == len(g[tag + "_ccd_trace"])
+        assert abs(r["ccd e"] - g[tag + "_dcd_e"]) < 1e-10
+    assert abs(g["rs05_ccd_e"] - (-0.5120153512190824)) < 1e-6       # test_ccd_dcd.py:208
+    assert abs(g["rs05_dcd_e"] - (-0.515296499349519)) < 1e-6        # test_ccd_dcd.py:209
+
+
+def test_ueg_tc_full_build_and_ccd():
+    """TC-UEG 14e rs=0.5 (test_symmetrised_2body_integral.py:205-220): u_mat, both TC integral
+    kinds, TC-CCD energy -0.256670836708 (1e-8 there, 1e-10 against the regenerated golden)."""
+    from pymes_b200.model import ueg
+    from pymes_b200.solver import ccd
+    from pymes_b200 import backend as bk
+    g = golden("ueg_tc")
+    m = ueg.UEG(14, 7, 7, 0.5)
+    m.init_single_basis(5.0)
+    m.k_cutoff = float(g["k_cutoff"])
+    m.gamma = None
+    nP = m.n_orb
+    V2 = m.eval_2b_integrals(correlator=m.trunc, is_only_2b=True, device=True)
+    assert _rel(V2.cpu().numpy(), host._dense(g["V2_idx"], g["V2_val"], nP)) < 1e-11
+    Veff = m.eval_2b_integrals(correlator=m.trunc, is_effect_2b=True, device=True)
+    assert _rel(Veff.cpu().numpy(), host._dense(g["Veff_idx"], g["Veff_val"], nP)) < 1e-11
+    V = bk.lincomb([1.0, 1.0], [V2, Veff])
+    r = ccd.CCD(7).solve(g["fock"], V)
+    assert abs(r["ccd e"] - g["ccd_e"]) < 1e-10
+    assert abs(r["ccd e"] - (-0.256670836708)) < 1e-8
+    # blocks built directly == slices of the dense tensor
+    blocks = m.eval_2b_blocks(7, ["abcd", "iajb", "klij"], [("only_2b", m.trunc), ("effect_2b", m.trunc)])
+    Vn = V.cpu().numpy()
+    assert _rel(blocks["abcd"].cpu().numpy(), Vn[7:, 7:, 7:, 7:]) < 1e-13
+    assert _rel(blocks["iajb"].cpu().numpy(), Vn[:7, 7:, :7, 7:]) < 1e-13
+
+
+def test_umat_golden():
+    from pymes_b200.model import ueg
+    g = golden("ueg_tc")
+    m = ueg.UEG(14, 7, 7, 0.5)
+    m.init_single_basis(5.0)
+    m.k_cutoff = float(g["k_cutoff"])
+    m.gamma = None
+    got = m.umat(g["umat_q"], m.trunc)
+    np.testing.assert_allclose(got, g["umat"], rtol=1e-11)
+
+
+# --------------------------------------------------------------------------
+# size-independent properties at a size the oracle cannot reach quickly
+# --------------------------------------------------------------------------
+def test_pp_ladder_linearity_and_blas_crosscheck_large():
+    """o=27, v=96: linearity in T and agreement with numpy's BLAS matmul on the same data."""
+    from pymes_b200 import backend as bk
+    no, nv = 27, 96
+    g = torch.Generator(device="cuda").manual_seed(0)
+    V = torch.randn(nv, nv, nv, nv, dtype=torch.float64, device="cuda", generator=g)
+    T1 = torch.randn(nv, nv, no, no, dtype=torch.float64, device="cuda", generator=g)
+    T2 = torch.randn(nv, nv, no, no, dtype=torch.float64, device="cuda", generator=g)
+    R1 = bk.contract("abcd,cdij->abij", V, T1)
+    R2 = bk.contract("abcd,cdij->abij", V, T2)
+    R12 = bk.contract("abcd,cdij->abij", V, bk.lincomb([1.0, -2.5], [T1, T2]))
+    lin = (R12 - (R1 - 2.5 * R2)).abs().max().item() / R12.abs().max().item()
+    assert lin < 1e-13
+    ref = V.cpu().numpy().reshape(nv * nv, nv * nv) @ T1.cpu().numpy().reshape(nv * nv, no * no)
+    assert _rel(R1.cpu().numpy().reshape(nv * nv, no * no), ref) < 1e-13
+
+
+def test_residual_no_symmetry_shortcut_medium():
+    """Random blocks with no symmetry at o=6, v=30 against the oracle."""
+    from pymes_b200.solver import ccd
+    from oracle import cc_oracle as oc
+    rng = np.random.default_rng(99)
+    no, nv = 6, 30
+    f = rng.standard_normal((no + nv, no + nv))
+    T = 0.1 * rng.standard_normal((nv, nv, no, no))
+    blk = dict(klij=(no,) * 4, ijab=(no, no, nv, nv), abij=(nv, nv, no, no), iajb=(no, nv, no, nv),
+               iabj=(no, nv, nv, no), abcd=(nv,) * 4)
+    args = [rng.standard_normal(blk[k]) for k in ("klij", "ijab", "abij", "iajb", "iabj", "abcd")]
+    for flag in (False, True):
+        got = ccd.CCD(no, is_dcd=flag).get_residual(f, T, *args)
+        ref = oc.doubles_residual(no, f, T, *args, is_dcd=flag)
+        assert _rel(got, ref) < 1e-12
