@@ -252,6 +252,9 @@ def contract_terms(out_sub, terms, out=None, beta=0.0):
     One kernel launch accumulates every term in registers.
     """
     lib = _lib.load()
+    if out is not None and out.device != device():
+        raise RuntimeError("pymes_b200: output tensor lives on %s, the kernels write to %s "
+                           "(there is no CPU fallback)" % (out.device, device()))
     d, out, _operands = describe_contraction(out_sub, terms, out, beta)
     need = lib.pmb_contract_workspace(C.byref(d))
     ws = scratch().splitk_ws(need) if need else None

@@ -23,7 +23,9 @@ def _native_library_loaded():
     _lib.check(lib.pmb_device_info(C.byref(sm), C.byref(cc), C.byref(mem)))
     assert cc.value >= 100, "libpymes_b200.so is built for sm_100a"
     before = bk.launch_count()
+    host.DEVICE = "cuda"
     yield
+    host.DEVICE = "cpu"
     assert bk.launch_count() > before, "no kernel of libpymes_b200.so was launched"
 
 

@@ -13,9 +13,17 @@ from tests.conftest import golden
 TOL = dict(rtol=1e-10, atol=1e-11)
 
 
+DEVICE = "cpu"      # tests/test_gpu_parity.py re-runs these bodies with DEVICE = "cuda"
+
+
 def _t(x):
     x = np.asarray(x, dtype=np.float64)
-    return torch.from_numpy(np.ascontiguousarray(x)) if x.ndim else torch.tensor(float(x), dtype=torch.float64)
+    t = torch.from_numpy(np.ascontiguousarray(x)) if x.ndim else torch.tensor(float(x), dtype=torch.float64)
+    return t.to(DEVICE)
+
+
+def _n(t):
+    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
 
 
 def test_library_exports_every_declared_symbol():
@@ -61,11 +69,11 @@ def test_contract_matches_einsum(cpu_abi, spec, shapes):
     A, B = (rng.standard_normal(s) for s in shapes)
     ref = np.einsum(spec, A, B)
     got = bk.contract(spec, A, B, alpha=0.7)
-    np.testing.assert_allclose(got.numpy(), 0.7 * ref, **TOL)
+    np.testing.assert_allclose(_n(got), 0.7 * ref, **TOL)
     out = _t(rng.standard_normal(ref.shape))
-    keep = out.numpy().copy()
+    keep = _n(out).copy()
     bk.contract(spec, A, B, out=out, alpha=-1.5, beta=0.25)
-    np.testing.assert_allclose(out.numpy(), 0.25 * keep - 1.5 * ref, **TOL)
+    np.testing.assert_allclose(_n(out), 0.25 * keep - 1.5 * ref, **TOL)
 
 
 def test_contract_on_strided_views_and_multi_term(cpu_abi):
@@ -78,17 +86,17 @@ def test_contract_on_strided_views_and_multi_term(cpu_abi):
     dV = part_2_body_int(no, _t(V))
     dVn = part_2_body_int(no, V)
     got = bk.contract("abcd,cdij->abij", dV["abcd"], _t(T))
-    np.testing.assert_allclose(got.numpy(), np.einsum("abcd,cdij->abij", dVn["abcd"], T), **TOL)
+    np.testing.assert_allclose(_n(got), np.einsum("abcd,cdij->abij", dVn["abcd"], T), **TOL)
     I = rng.standard_normal((no,) * 4)
     R = _t(dVn["abij"].copy())
     bk.contract_terms("abij", [(1.0, "abkl", _t(T), "klij", _t(I)),
                                (2.0, "cdij", _t(T), "abcd", dV["abcd"])], out=R, beta=1.0)
     ref = dVn["abij"] + np.einsum("abkl,klij->abij", T, I) + 2 * np.einsum("abcd,cdij->abij", dVn["abcd"], T)
-    np.testing.assert_allclose(R.numpy(), ref, **TOL)
+    np.testing.assert_allclose(_n(R), ref, **TOL)
     # output into a strided view
     F = _t(np.zeros((no + nv, no + nv)))
     bk.contract("bj,jabi->ia", _t(rng.standard_normal((nv, no))), dV["iabj"], out=F[:no, no:])
-    assert np.abs(F.numpy()[no:, :]).max() == 0 and np.abs(F.numpy()[:no, no:]).max() > 0
+    assert np.abs(_n(F)[no:, :]).max() == 0 and np.abs(_n(F)[:no, no:]).max() > 0
 
 
 def test_multi_operand_einsum(cpu_abi):
@@ -100,7 +108,7 @@ def test_multi_operand_einsum(cpu_abi):
     for spec, ops in (("bj,jkbc,ci,ak->ai", (t, V, t, t)),
                       ("klcd,ak,ci,bl,dj->abij", (V, t, t, t, t)),
                       ("baij->abij", (rng.standard_normal((nv, nv, no, no)),))):
-        np.testing.assert_allclose(bk.einsum(spec, *ops).numpy(), np.einsum(spec, *ops, optimize=True), **TOL)
+        np.testing.assert_allclose(_n(bk.einsum(spec, *ops)), np.einsum(spec, *ops, optimize=True), **TOL)
     with pytest.raises(ValueError):
         bk.einsum("ab,ab->ab", t, t)
 
@@ -151,7 +159,7 @@ def test_ccsd_dressing_singles_doubles(cpu_abi, tag):
                               ccsd.dressed_block("abij", T1, dVd, skip_tau=True),
                               ccsd.dressed_block("iajb", T1, dVd), ccsd.dressed_block("iabj", T1, dVd),
                               None, pp_ladder=ccsd.tau_ladder(T1, dVd))
-    np.testing.assert_allclose(R2.numpy(), g["R2"], **TOL)
+    np.testing.assert_allclose(_n(R2), g["R2"], **TOL)
     # requesting a subset of keys
     sub = cc.get_T1_dressed_V(g["T1"], dV, {"klij": None, "iabc": None})
     assert set(sub) == {"klij", "iabc"}
@@ -165,8 +173,8 @@ def test_diis_matches_reference_sequence(cpu_abi):
     for n in range(int(g["n_calls"])):
         out = mixer.mix([_t(g[f"e1_{n}"]), _t(g[f"e2_{n}"])], [_t(g[f"a1_{n}"]), _t(g[f"a2_{n}"])])
         np.testing.assert_allclose(mixer.L, g[f"L_{n}"], rtol=1e-12, atol=1e-14)
-        np.testing.assert_allclose(out[0].numpy(), g[f"o1_{n}"], rtol=1e-9, atol=1e-11)
-        np.testing.assert_allclose(out[1].numpy(), g[f"o2_{n}"], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(_n(out[0]), g[f"o1_{n}"], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(_n(out[1]), g[f"o2_{n}"], rtol=1e-9, atol=1e-11)
 
 
 @pytest.mark.parametrize("tag", ["LiH_321g", "LiH_tc"])
@@ -254,7 +262,7 @@ def test_ueg_coulomb_integrals_and_ccd(cpu_abi):
     fock = hf.construct_hf_matrix(7, np.diag(m.kinetic()), V)
     np.testing.assert_allclose(fock, g["rs1_fock"], rtol=1e-12, atol=1e-13)
     blocks = m.eval_2b_blocks(7, ["abij", "iajb"], [("coulomb", None)])
-    np.testing.assert_array_equal(blocks["iajb"].numpy(), V[:7, 7:, :7, 7:])
+    np.testing.assert_array_equal(_n(blocks["iajb"]), V[:7, 7:, :7, 7:])
 
 
 @pytest.mark.slow
@@ -285,6 +293,6 @@ def test_ueg_tc_tables_small(cpu_abi):
     # eval_2b_integrals(is_effect_2b=True) returns the (pq)(rs)<->(qp)(sr) symmetrised tensor
     blk = m.build_block((0, 0, 0, 0), (3, nP, 3, nP), W0s=W0)
     ref = _dense(g["Veff_idx"], g["Veff_val"], nP)[:3, :, :3, :]
-    np.testing.assert_allclose(blk.numpy(), ref, rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(_n(blk), ref, rtol=1e-10, atol=1e-14)
     np.testing.assert_allclose(m.double_contractions_in_3_body(), g["one_body"], rtol=1e-11)
     np.testing.assert_allclose(m.triple_contractions_in_3_body(), g["zero_body"], rtol=1e-11)
