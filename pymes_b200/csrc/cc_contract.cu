@@ -75,25 +75,38 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
         : "d"(a), "d"(b));
 }
 
-// Load one [BK][BX] operand tile from global memory into registers.
+// 8-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the
+// destination, which is how ragged tile edges are handled without branches.
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// Issue the asynchronous gather of one [BK][BX] operand tile into shared memory.
 //   x-fast: consecutive threads walk x (the operand is unit-stride along m/n)
 //   k-fast: every 4 lanes read 4 consecutive k (one 32 B sector), 8 x per warp
+// s_x: per-row element offsets of this term (0 for rows outside the tensor),
+// s_k: per-k element offsets of this k-tile (0 beyond K).
 template <int BX, int NT>
-__device__ __forceinline__ void gload(double (&r)[BX * BK / NT], const double *__restrict__ G,
-                                      const long long *s_x, const long long *s_k, int xrem,
-                                      int krem, bool kfast, double alpha, int tid) {
+__device__ __forceinline__ void gather_tile(double *S, const double *__restrict__ G,
+                                            const long long *s_x, const long long *s_k, int xrem,
+                                            int krem, bool kfast, int tid) {
     constexpr int PER = BX * BK / NT;
+    constexpr int LD = BX + SPAD;
     if (!kfast) {
         const int x = tid % BX;
         const int kb = tid / BX;
         const bool xok = x < xrem;
-        const long long gx = s_x[x];
+        const double *gx = G + s_x[x];
 #pragma unroll
         for (int it = 0; it < PER; ++it) {
             const int kk = it * (NT / BX) + kb;
-            double v = 0.0;
-            if (xok && kk < krem) v = alpha * __ldg(G + gx + s_k[kk]);
-            r[it] = v;
+            cp_async8(S + kk * LD + x, gx + s_k[kk], (xok && kk < krem) ? 8 : 0);
         }
     } else {
         const int lane = tid & 31, warp = tid >> 5;
@@ -102,57 +115,33 @@ __device__ __forceinline__ void gload(double (&r)[BX * BK / NT], const double *_
         static_assert(NW % KQ == 0, "warps must tile the k quads");
         const int kk = (warp % KQ) * 4 + (lane & 3);
         const bool kok = kk < krem;
-        const long long gk = s_k[kk];
+        const double *gk = G + s_k[kk];
 #pragma unroll
         for (int it = 0; it < PER; ++it) {
             const int x = ((it * NW + warp) / KQ) * 8 + (lane >> 2);
-            double v = 0.0;
-            if (kok && x < xrem) v = alpha * __ldg(G + s_x[x] + gk);
-            r[it] = v;
+            cp_async8(S + kk * LD + x, gk + s_x[x], (kok && x < xrem) ? 8 : 0);
         }
     }
 }
 
-template <int BX, int NT>
-__device__ __forceinline__ void sstore(const double (&r)[BX * BK / NT], double *S, bool kfast,
-                                       int tid) {
-    constexpr int PER = BX * BK / NT;
-    constexpr int LD = BX + SPAD;
-    if (!kfast) {
-        const int x = tid % BX;
-        const int kb = tid / BX;
-#pragma unroll
-        for (int it = 0; it < PER; ++it) S[(it * (NT / BX) + kb) * LD + x] = r[it];
-    } else {
-        const int lane = tid & 31, warp = tid >> 5;
-        constexpr int KQ = BK / 4;
-        constexpr int NW = NT / 32;
-        const int kk = (warp % KQ) * 4 + (lane & 3);
-#pragma unroll
-        for (int it = 0; it < PER; ++it) {
-            const int x = ((it * NW + warp) / KQ) * 8 + (lane >> 2);
-            S[kk * LD + x] = r[it];
-        }
-    }
-}
-
-template <int BM, int BN, int WARPS_M, int WARPS_N, int MINB>
+template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, int MINB>
 __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
     contract_kernel(const __grid_constant__ Params p) {
     constexpr int NT = WARPS_M * WARPS_N * 32;
     constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
     constexpr int MT = WM / 8, NTL = WN / 8;
     constexpr int LDA = BM + SPAD, LDB = BN + SPAD;
+    constexpr int KSLOTS = STAGES + 1;
     static_assert(NT % BM == 0 && NT % BN == 0, "x-fast mapping needs NT % BX == 0");
     static_assert((BM * BK) % NT == 0 && (BN * BK) % NT == 0, "tile/threads");
+    static_assert(NT >= 2 * BK, "k-offset producers");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *As = reinterpret_cast<double *>(smem_raw);   // [2][BK][LDA]
-    double *Bs = As + 2 * BK * LDA;                       // [2][BK][LDB]
-    long long *s_am = reinterpret_cast<long long *>(Bs + 2 * BK * LDB);  // [BM]
-    long long *s_bn = s_am + BM;                          // [BN]
-    long long *s_ka = s_bn + BN;                          // [2][BK]
-    long long *s_kb = s_ka + 2 * BK;                      // [2][BK]
+    double *As = reinterpret_cast<double *>(smem_raw);    // [STAGES][BK][LDA]
+    double *Bs = As + STAGES * BK * LDA;                   // [STAGES][BK][LDB]
+    long long *s_k = reinterpret_cast<long long *>(Bs + STAGES * BK * LDB);  // [KSLOTS][2][BK]
+    long long *s_am = s_k + KSLOTS * 2 * BK;               // [nterms][BM]
+    long long *s_bn = s_am + p.nterms * BM;                // [nterms][BN]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -163,77 +152,87 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
     const int kt_lo = blockIdx.y * p.ktiles_per_split;
     const int kt_hi = min(kt_lo + p.ktiles_per_split, p.total_ktiles);
 
+    // term that owns global k-tile g (terms are laid out back to back along k)
+    auto term_of = [&](int g) {
+        int ti = 0;
+        while (ti + 1 < p.nterms && g >= p.t[ti + 1].kt_begin) ++ti;
+        return ti;
+    };
+    // element offsets of the BK contracted indices of k-tile g, both operands
+    auto koffs = [&](int g) {
+        if (tid < 2 * BK && g < kt_hi) {
+            const TermDev &t = p.t[term_of(g)];
+            const int kk = tid & (BK - 1);
+            const int k = (g - t.kt_begin) * BK + kk;
+            const bool isb = tid >= BK;
+            long long off = 0;
+            if (k < t.K) off = decomp(k, t.nk, t.k_ext, isb ? t.b_kstr : t.a_kstr);
+            s_k[(g % KSLOTS) * 2 * BK + tid] = off;
+        }
+    };
+    auto issue = [&](int g) {
+        if (g < kt_hi) {
+            const int ti = term_of(g);
+            const TermDev &t = p.t[ti];
+            const int krem = t.K - (g - t.kt_begin) * BK;
+            const int st = (g - kt_lo) % STAGES;
+            const long long *ko = s_k + (g % KSLOTS) * 2 * BK;
+            gather_tile<BM, NT>(As + st * BK * LDA, t.A, s_am + ti * BM, ko, mrem, krem, t.a_kfast != 0, tid);
+            gather_tile<BN, NT>(Bs + st * BK * LDB, t.B, s_bn + ti * BN, ko + BK, nrem, krem, t.b_kfast != 0, tid);
+        }
+        cp_async_commit();
+    };
+
+    for (int ti = 0; ti < p.nterms; ++ti) {
+        const TermDev &t = p.t[ti];
+        for (int i = tid; i < BM; i += NT)
+            s_am[ti * BM + i] = (i < mrem) ? decomp(m0 + i, p.nm, p.m_ext, t.a_mstr) : 0;
+        for (int i = tid; i < BN; i += NT)
+            s_bn[ti * BN + i] = (i < nrem) ? decomp(n0 + i, p.nn, p.n_ext, t.b_nstr) : 0;
+    }
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) koffs(kt_lo + s);
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issue(kt_lo + s);
+
     double acc[MT][NTL][2];
 #pragma unroll
     for (int i = 0; i < MT; ++i)
 #pragma unroll
         for (int j = 0; j < NTL; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    for (int ti = 0; ti < p.nterms; ++ti) {
-        const TermDev &t = p.t[ti];
-        const int lo = max(kt_lo, t.kt_begin) - t.kt_begin;
-        const int hi = min(kt_hi, t.kt_begin + t.nkt) - t.kt_begin;
-        if (lo >= hi) continue;  // uniform over the CTA
-        const bool akf = t.a_kfast != 0, bkf = t.b_kfast != 0;
-
-        auto koffs = [&](int kt, int buf) {
-            if (tid < 2 * BK) {
-                const int kk = tid & (BK - 1);
-                const int k = kt * BK + kk;
-                const bool isb = tid >= BK;
-                long long off = 0;
-                if (k < t.K) off = decomp(k, t.nk, t.k_ext, isb ? t.b_kstr : t.a_kstr);
-                (isb ? s_kb : s_ka)[buf * BK + kk] = off;
-            }
-        };
-
-        __syncthreads();  // previous term no longer reads the offset arrays
-        for (int i = tid; i < BM; i += NT)
-            s_am[i] = (i < mrem) ? decomp(m0 + i, p.nm, p.m_ext, t.a_mstr) : 0;
-        for (int i = tid; i < BN; i += NT)
-            s_bn[i] = (i < nrem) ? decomp(n0 + i, p.nn, p.n_ext, t.b_nstr) : 0;
-        koffs(lo, 0);
-        __syncthreads();
-
-        double ra[BM * BK / NT], rb[BN * BK / NT];
-        gload<BM, NT>(ra, t.A, s_am, s_ka, mrem, t.K - lo * BK, akf, t.alpha, tid);
-        gload<BN, NT>(rb, t.B, s_bn, s_kb, nrem, t.K - lo * BK, bkf, 1.0, tid);
-        sstore<BM, NT>(ra, As, akf, tid);
-        sstore<BN, NT>(rb, Bs, bkf, tid);
-        if (lo + 1 < hi) koffs(lo + 1, 1);
-        __syncthreads();
-
-        for (int kt = lo; kt < hi; ++kt) {
-            const int cur = (kt - lo) & 1;
-            const bool more = kt + 1 < hi;
-            if (more) {
-                const int krem = t.K - (kt + 1) * BK;
-                gload<BM, NT>(ra, t.A, s_am, s_ka + (cur ^ 1) * BK, mrem, krem, akf, t.alpha, tid);
-                gload<BN, NT>(rb, t.B, s_bn, s_kb + (cur ^ 1) * BK, nrem, krem, bkf, 1.0, tid);
-            }
-            const double *a = As + cur * BK * LDA + warp_m * WM + (lane >> 2);
-            const double *b = Bs + cur * BK * LDB + warp_n * WN + (lane >> 2);
+    int cur_term = term_of(kt_lo);
+    double alpha = p.t[cur_term].alpha;
+    int term_end = p.t[cur_term].kt_begin + p.t[cur_term].nkt;
+    for (int g = kt_lo; g < kt_hi; ++g) {
+        cp_async_wait<STAGES - 2>();   // tile g has landed (this thread's copies)
+        __syncthreads();               // ... everyone's; stage (g-1) is free again
+        issue(g + STAGES - 1);
+        koffs(g + STAGES);
+        if (g >= term_end) {
+            cur_term = term_of(g);
+            alpha = p.t[cur_term].alpha;
+            term_end = p.t[cur_term].kt_begin + p.t[cur_term].nkt;
+        }
+        const int st = (g - kt_lo) % STAGES;
+        const double *a = As + st * BK * LDA + warp_m * WM + (lane >> 2);
+        const double *b = Bs + st * BK * LDB + warp_n * WN + (lane >> 2);
 #pragma unroll
-            for (int ks = 0; ks < BK / 4; ++ks) {
-                const int row = ks * 4 + (lane & 3);
-                double af[MT], bf[NTL];
+        for (int ks = 0; ks < BK / 4; ++ks) {
+            const int row = ks * 4 + (lane & 3);
+            double af[MT], bf[NTL];
 #pragma unroll
-                for (int i = 0; i < MT; ++i) af[i] = a[row * LDA + i * 8];
+            for (int i = 0; i < MT; ++i) af[i] = a[row * LDA + i * 8] * alpha;
 #pragma unroll
-                for (int j = 0; j < NTL; ++j) bf[j] = b[row * LDB + j * 8];
+            for (int j = 0; j < NTL; ++j) bf[j] = b[row * LDB + j * 8];
 #pragma unroll
-                for (int i = 0; i < MT; ++i)
+            for (int i = 0; i < MT; ++i)
 #pragma unroll
-                    for (int j = 0; j < NTL; ++j) dmma(acc[i][j], af[i], bf[j]);
-            }
-            if (more) {
-                sstore<BM, NT>(ra, As + (cur ^ 1) * BK * LDA, akf, tid);
-                sstore<BN, NT>(rb, Bs + (cur ^ 1) * BK * LDB, bkf, tid);
-                if (kt + 2 < hi) koffs(kt + 2, cur);
-            }
-            __syncthreads();
+                for (int j = 0; j < NTL; ++j) dmma(acc[i][j], af[i], bf[j]);
         }
     }
+    cp_async_wait<0>();
 
     // ---- epilogue -------------------------------------------------------
     // DMMA C fragment: row = lane/4, cols = 2*(lane%4) + {0,1}
@@ -281,7 +280,7 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
     }
 }
 
-// C[m,n] = beta*C + sum_s ws[s][m][n]  (split-K second stage, fixed order)
+// C[m,n] = beta*C[m,n] + sum_s ws[s][m][n]  (split-K second stage, fixed order)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constant__ Params p) {
     const size_t MN = (size_t)p.M * (size_t)p.N;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < MN;
@@ -309,18 +308,20 @@ constexpr int kNumCfg = 4;
 static int g_force_cfg = -1;
 static int g_force_split = 0;
 
-template <int BM, int BN>
-constexpr size_t smem_bytes() {
-    return sizeof(double) * 2 * BK * (BM + SPAD + BN + SPAD) + sizeof(long long) * (BM + BN + 4 * BK);
+template <int BM, int BN, int STAGES>
+constexpr size_t smem_bytes(int nterms) {
+    return sizeof(double) * STAGES * BK * (BM + SPAD + BN + SPAD) +
+           sizeof(long long) * ((size_t)nterms * (BM + BN) + (STAGES + 1) * 2 * BK);
 }
 
-template <int BM, int BN, int WMW, int WNW, int MINB>
+template <int BM, int BN, int WMW, int WNW, int STAGES, int MINB>
 static int launch_cfg(const Params &p, dim3 grid, cudaStream_t s) {
-    auto kern = contract_kernel<BM, BN, WMW, WNW, MINB>;
-    constexpr size_t sm = smem_bytes<BM, BN>();
+    auto kern = contract_kernel<BM, BN, WMW, WNW, STAGES, MINB>;
+    const size_t sm = smem_bytes<BM, BN, STAGES>(p.nterms);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem_bytes<BM, BN, STAGES>(PMB_MAX_TERMS));
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
@@ -462,10 +463,10 @@ extern "C" int pmb_contract(const pmb_contract_t *d, void *ws, size_t ws_bytes, 
     }
     dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)p.nsplit, 1);
     switch (cfg) {
-        case 0: rc = launch_cfg<128, 128, 4, 2, 1>(p, grid, s); break;
-        case 1: rc = launch_cfg<128, 64, 4, 2, 1>(p, grid, s); break;
-        case 2: rc = launch_cfg<64, 64, 2, 2, 3>(p, grid, s); break;
-        default: rc = launch_cfg<64, 32, 2, 2, 3>(p, grid, s); break;
+        case 0: rc = launch_cfg<128, 128, 4, 2, 4, 1>(p, grid, s); break;
+        case 1: rc = launch_cfg<128, 64, 4, 2, 4, 1>(p, grid, s); break;
+        case 2: rc = launch_cfg<64, 64, 2, 2, 3, 3>(p, grid, s); break;
+        default: rc = launch_cfg<64, 32, 2, 2, 3, 3>(p, grid, s); break;
     }
     if (rc != 0) return rc;
     if (p.nsplit > 1) {
