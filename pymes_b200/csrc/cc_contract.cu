@@ -27,6 +27,12 @@ namespace pmb {
 
 constexpr int BK = 16;
 constexpr int SPAD = 4;
+static_assert(BK == 16, "the main loop is written for four DMMA k sub-steps per tile");
+
+template <int V>
+struct IntC {
+    static constexpr int value = V;
+};
 
 struct TermDev {
     const double *A;
@@ -92,19 +98,23 @@ __device__ __forceinline__ void cp_async_wait() {
 //   k-fast: every 4 lanes read 4 consecutive k (one 32 B sector), 8 x per warp
 // s_x: per-row element offsets of this term (0 for rows outside the tensor),
 // s_k: per-k element offsets of this k-tile (0 beyond K).
-template <int BX, int NT>
+// The copies of one tile are issued in NPARTS slices (PART = 0..NPARTS-1) so that the
+// main loop can interleave them with its DMMA sub-steps.
+template <int BX, int NT, int PART, int NPARTS>
 __device__ __forceinline__ void gather_tile(double *S, const double *__restrict__ G,
                                             const long long *s_x, const long long *s_k, int xrem,
                                             int krem, bool kfast, int tid) {
     constexpr int PER = BX * BK / NT;
     constexpr int LD = BX + SPAD;
+    static_assert(PER % NPARTS == 0, "tile copies must split evenly");
+    constexpr int IT0 = PART * (PER / NPARTS), IT1 = IT0 + PER / NPARTS;
     if (!kfast) {
         const int x = tid % BX;
         const int kb = tid / BX;
         const bool xok = x < xrem;
         const double *gx = G + s_x[x];
 #pragma unroll
-        for (int it = 0; it < PER; ++it) {
+        for (int it = IT0; it < IT1; ++it) {
             const int kk = it * (NT / BX) + kb;
             cp_async8(S + kk * LD + x, gx + s_k[kk], (xok && kk < krem) ? 8 : 0);
         }
@@ -117,14 +127,14 @@ __device__ __forceinline__ void gather_tile(double *S, const double *__restrict_
         const bool kok = kk < krem;
         const double *gk = G + s_k[kk];
 #pragma unroll
-        for (int it = 0; it < PER; ++it) {
+        for (int it = IT0; it < IT1; ++it) {
             const int x = ((it * NW + warp) / KQ) * 8 + (lane >> 2);
             cp_async8(S + kk * LD + x, gk + s_x[x], (kok && x < xrem) ? 8 : 0);
         }
     }
 }
 
-template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, int MINB>
+template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, int MINB, bool INTERLEAVE>
 __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
     contract_kernel(const __grid_constant__ Params p) {
     constexpr int NT = WARPS_M * WARPS_N * 32;
@@ -170,15 +180,46 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
             s_k[(g % KSLOTS) * 2 * BK + tid] = off;
         }
     };
-    auto issue = [&](int g) {
-        if (g < kt_hi) {
+    constexpr int NPARTS = BK / 4;   // one slice of the next tile's copies per DMMA sub-step
+    struct TileRef {                 // everything the copies of one k-tile need, resolved once
+        const double *A, *B;
+        const long long *am, *bn, *ko;
+        double *as, *bs;
+        int krem;
+        bool akf, bkf, valid;
+    };
+    auto tile_ref = [&](int g) {
+        TileRef r;
+        r.valid = g < kt_hi;
+        if (r.valid) {
             const int ti = term_of(g);
             const TermDev &t = p.t[ti];
-            const int krem = t.K - (g - t.kt_begin) * BK;
             const int st = (g - kt_lo) % STAGES;
-            const long long *ko = s_k + (g % KSLOTS) * 2 * BK;
-            gather_tile<BM, NT>(As + st * BK * LDA, t.A, s_am + ti * BM, ko, mrem, krem, t.a_kfast != 0, tid);
-            gather_tile<BN, NT>(Bs + st * BK * LDB, t.B, s_bn + ti * BN, ko + BK, nrem, krem, t.b_kfast != 0, tid);
+            r.A = t.A;
+            r.B = t.B;
+            r.am = s_am + ti * BM;
+            r.bn = s_bn + ti * BN;
+            r.ko = s_k + (g % KSLOTS) * 2 * BK;
+            r.as = As + st * BK * LDA;
+            r.bs = Bs + st * BK * LDB;
+            r.krem = t.K - (g - t.kt_begin) * BK;
+            r.akf = t.a_kfast != 0;
+            r.bkf = t.b_kfast != 0;
+        }
+        return r;
+    };
+    auto issue_part = [&](const TileRef &r, auto part) {
+        constexpr int PART = decltype(part)::value;
+        if (r.valid) {
+            gather_tile<BM, NT, PART, NPARTS>(r.as, r.A, r.am, r.ko, mrem, r.krem, r.akf, tid);
+            gather_tile<BN, NT, PART, NPARTS>(r.bs, r.B, r.bn, r.ko + BK, nrem, r.krem, r.bkf, tid);
+        }
+    };
+    auto issue = [&](int g) {
+        const TileRef r = tile_ref(g);
+        if (r.valid) {
+            gather_tile<BM, NT, 0, 1>(r.as, r.A, r.am, r.ko, mrem, r.krem, r.akf, tid);
+            gather_tile<BN, NT, 0, 1>(r.bs, r.B, r.bn, r.ko + BK, nrem, r.krem, r.bkf, tid);
         }
         cp_async_commit();
     };
@@ -208,7 +249,10 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
     for (int g = kt_lo; g < kt_hi; ++g) {
         cp_async_wait<STAGES - 2>();   // tile g has landed (this thread's copies)
         __syncthreads();               // ... everyone's; stage (g-1) is free again
-        issue(g + STAGES - 1);
+        TileRef nxt;
+        nxt.valid = false;
+        if (INTERLEAVE) nxt = tile_ref(g + STAGES - 1);
+        else issue(g + STAGES - 1);
         koffs(g + STAGES);
         if (g >= term_end) {
             cur_term = term_of(g);
@@ -218,19 +262,25 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
         const int st = (g - kt_lo) % STAGES;
         const double *a = As + st * BK * LDA + warp_m * WM + (lane >> 2);
         const double *b = Bs + st * BK * LDB + warp_n * WN + (lane >> 2);
-#pragma unroll
-        for (int ks = 0; ks < BK / 4; ++ks) {
+        auto substep = [&](auto part) {
+            constexpr int ks = decltype(part)::value;
             const int row = ks * 4 + (lane & 3);
             double af[MT], bf[NTL];
 #pragma unroll
             for (int i = 0; i < MT; ++i) af[i] = a[row * LDA + i * 8] * alpha;
 #pragma unroll
             for (int j = 0; j < NTL; ++j) bf[j] = b[row * LDB + j * 8];
+            if (INTERLEAVE) issue_part(nxt, part);   // overlaps the fragment-load latency
 #pragma unroll
             for (int i = 0; i < MT; ++i)
 #pragma unroll
                 for (int j = 0; j < NTL; ++j) dmma(acc[i][j], af[i], bf[j]);
-        }
+        };
+        substep(IntC<0>{});
+        substep(IntC<1>{});
+        substep(IntC<2>{});
+        substep(IntC<3>{});
+        if (INTERLEAVE) cp_async_commit();
     }
     cp_async_wait<0>();
 
@@ -302,8 +352,10 @@ struct TileCfg {
     double eff;
 };
 static const TileCfg kCfg[] = {
-    {128, 128, 256, 1.00}, {128, 64, 256, 0.95}, {64, 64, 128, 0.70}, {64, 32, 128, 0.55}};
-constexpr int kNumCfg = 4;
+    // eff = measured pp-ladder rate relative to the best config (profiles/r1_tile_sweep.md)
+    {128, 128, 256, 1.00}, {128, 64, 256, 0.90}, {64, 64, 128, 1.00}, {64, 32, 128, 0.80},
+    {128, 64, 128, 0.90}};
+constexpr int kNumCfg = 5;
 
 static int g_force_cfg = -1;
 static int g_force_split = 0;
@@ -314,9 +366,9 @@ constexpr size_t smem_bytes(int nterms) {
            sizeof(long long) * ((size_t)nterms * (BM + BN) + (STAGES + 1) * 2 * BK);
 }
 
-template <int BM, int BN, int WMW, int WNW, int STAGES, int MINB>
-static int launch_cfg(const Params &p, dim3 grid, cudaStream_t s) {
-    auto kern = contract_kernel<BM, BN, WMW, WNW, STAGES, MINB>;
+template <int BM, int BN, int WMW, int WNW, int STAGES, int MINB, bool IL>
+static int launch_one(const Params &p, dim3 grid, cudaStream_t s) {
+    auto kern = contract_kernel<BM, BN, WMW, WNW, STAGES, MINB, IL>;
     const size_t sm = smem_bytes<BM, BN, STAGES>(p.nterms);
     static bool attr_done = false;
     if (!attr_done) {
@@ -328,6 +380,12 @@ static int launch_cfg(const Params &p, dim3 grid, cudaStream_t s) {
     kern<<<grid, WMW * WNW * 32, sm, s>>>(p);
     count_launch();
     return cuda_status();
+}
+
+template <int BM, int BN, int WMW, int WNW, int STAGES, int MINB>
+static int launch_cfg(const Params &p, dim3 grid, cudaStream_t s, bool interleave) {
+    return interleave ? launch_one<BM, BN, WMW, WNW, STAGES, MINB, true>(p, grid, s)
+                      : launch_one<BM, BN, WMW, WNW, STAGES, MINB, false>(p, grid, s);
 }
 
 static bool prod_fits(const int64_t *ext, int n, int64_t *out) {
@@ -342,7 +400,7 @@ static bool prod_fits(const int64_t *ext, int n, int64_t *out) {
 }
 
 static int choose_cfg(int64_t M, int64_t N) {
-    if (g_force_cfg >= 0 && g_force_cfg < kNumCfg) return g_force_cfg;
+    if (g_force_cfg >= 0 && (g_force_cfg & 7) < kNumCfg) return g_force_cfg & 7;
     int best = 0;
     double best_cost = 1e300;
     for (int c = 0; c < kNumCfg; ++c) {
@@ -462,11 +520,16 @@ extern "C" int pmb_contract(const pmb_contract_t *d, void *ws, size_t ws_bytes, 
         p.ws = (double *)ws;
     }
     dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)p.nsplit, 1);
+    // copies of the next tile interleaved with the DMMA sub-steps: pays off when one CTA
+    // owns the SM (cfg 0), costs registers/occupancy otherwise.  Tuning bit 8 flips it.
+    bool il = (cfg == 0);
+    if (g_force_cfg >= 0 && (g_force_cfg & 8)) il = !il;
     switch (cfg) {
-        case 0: rc = launch_cfg<128, 128, 4, 2, 4, 1>(p, grid, s); break;
-        case 1: rc = launch_cfg<128, 64, 4, 2, 4, 1>(p, grid, s); break;
-        case 2: rc = launch_cfg<64, 64, 2, 2, 3, 3>(p, grid, s); break;
-        default: rc = launch_cfg<64, 32, 2, 2, 3, 3>(p, grid, s); break;
+        case 0: rc = launch_cfg<128, 128, 4, 2, 4, 1>(p, grid, s, il); break;
+        case 1: rc = launch_cfg<128, 64, 4, 2, 4, 1>(p, grid, s, il); break;
+        case 2: rc = launch_cfg<64, 64, 2, 2, 3, 3>(p, grid, s, il); break;
+        case 4: rc = launch_cfg<128, 64, 2, 2, 3, 2>(p, grid, s, il); break;
+        default: rc = launch_cfg<64, 32, 2, 2, 3, 3>(p, grid, s, il); break;
     }
     if (rc != 0) return rc;
     if (p.nsplit > 1) {

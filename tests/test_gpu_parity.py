@@ -112,7 +112,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("cfg", [-1, 0, 1, 2, 3])
+@pytest.mark.parametrize("cfg", [-1, 0, 1, 2, 3, 4])
 @pytest.mark.parametrize("spec,shapes", CASES)
 def test_contract_engine(spec, shapes, cfg):
     from pymes_b200 import _lib, backend as bk
