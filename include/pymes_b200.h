@@ -162,6 +162,25 @@ int pmb_lincomb(int nvec, const double *c_host, const double *const *X,
 
 size_t pmb_reduce_workspace(void);
 
+/* Batched strided multiply-reduce (no tensor cores; HBM/L2-bound):             */
+/*   out[I] = beta * out[I] + alpha * sum_R A[I,R] * B[I,R]                      */
+/* I = up to 4 output indices (an operand that lacks one has stride 0 there),   */
+/* R = up to 4 summed indices present in both operands; first listed index is   */
+/* the fastest.  Covers the einsums of the reference that are NOT matrix        */
+/* products because an index is shared by both operands AND the output:        */
+/* the H-bar diagonals eom_ccsd.py:169-266 ("kica,caki->ai", "kiab,abkj->abij", */
+/* "ijcd,cdij->ij", ...).  nr = 0 gives an elementwise product.                 */
+typedef struct {
+    const double *A;
+    const double *B;
+    double *out;
+    int32_t ni, nr;
+    int64_t i_ext[PMB_MAX_DIMS], o_istr[PMB_MAX_DIMS], a_istr[PMB_MAX_DIMS], b_istr[PMB_MAX_DIMS];
+    int64_t r_ext[PMB_MAX_DIMS], a_rstr[PMB_MAX_DIMS], b_rstr[PMB_MAX_DIMS];
+    double alpha, beta;
+} pmb_bdot_t;
+int pmb_bdot(const pmb_bdot_t *d, pmb_stream_t stream);
+
 /* ------------------------------------------------------------------------ */
 /* UEG momentum-conserving two-electron integrals  pymes/model/ueg.py:265-596 */
 /*                                                                          */

@@ -397,6 +397,162 @@ def ccsd_solve(no, fock, V, level_shift=0.0, is_dcsd=False, is_diis=True,
             "e_mp2": e_mp2}
 
 
+# --------------------------------------------------------------------------
+# EOM-EE-CCSD sigma, diagonals and Davidson -- reference pymes/solver/eom_ccsd.py
+# Term tables: (coefficient, einsum string, operand names); fov/foo/fvv = Fock blocks,
+# T = ground-state T2, u1/u2 = trial vector, other names = integral-dictionary keys.
+# --------------------------------------------------------------------------
+SIGMA1_TERMS = [                                                       # eom_ccsd.py:288-308
+    (+2., "jb,baji->ai", "fov u2"), (-1., "ji,aj->ai", "foo u1"),
+    (-1., "jb,abji->ai", "fov u2"), (+1., "ab,bi->ai", "fvv u1"),
+    (+2., "jabi,bj->ai", "iabj u1"), (-1., "jaib,bj->ai", "iajb u1"),
+    (-2., "jkib,abjk->ai", "ijka u2"), (+2., "jabc,bcji->ai", "iabc u2"),
+    (+1., "jkib,bajk->ai", "ijka u2"), (-1., "jacb,bcji->ai", "iabc u2"),
+    (+4., "jkbc,baji,ck->ai", "ijab T u1"), (-2., "jkbc,bajk,ci->ai", "ijab T u1"),
+    (-2., "jkbc,bcji,ak->ai", "ijab T u1"), (-2., "jkbc,abji,ck->ai", "ijab T u1"),
+    (-2., "jkcb,baji,ck->ai", "ijab T u1"), (+1., "jkbc,abjk,ci->ai", "ijab T u1"),
+    (+1., "jkcb,bcji,ak->ai", "ijab T u1"), (+1., "jkcb,abji,ck->ai", "ijab T u1"),
+]
+
+SIGMA2_P_TERMS = [                                                     # eom_ccsd.py:332-373
+    (-2., "klid,abkj,dl->abij", "ijka T u1"), (-2., "klci,cbkj,al->abij", "ijak T u1"),
+    (+2., "kacd,cbkj,di->abij", "iabc T u1"), (+2., "ladc,cbij,dl->abij", "iabc T u1"),
+    (-1., "kd,abkj,di->abij", "fov T u1"), (-1., "lc,cbij,al->abij", "fov T u1"),
+    (+1., "klid,abkl,dj->abij", "ijka T u1"), (+1., "klic,cbkj,al->abij", "ijka T u1"),
+    (+1., "klid,adkj,bl->abij", "ijka T u1"), (-1., "kbij,ak->abij", "iajk u1"),
+    (+1., "kldi,bdkj,al->abij", "ijak T u1"), (-1., "kacd,bckj,di->abij", "iabc T u1"),
+    (+1., "kldi,abkj,dl->abij", "ijak T u1"), (-1., "kadc,cbkj,di->abij", "iabc T u1"),
+    (-1., "kadc,bcki,dj->abij", "iabc T u1"), (-1., "lacd,cdji,bl->abij", "iabc T u1"),
+    (-1., "lacd,cbij,dl->abij", "iabc T u1"), (+1., "abic,cj->abij", "abic u1"),
+    (+4., "klcd,caki,dblj->abij", "ijab T u2"), (-2., "klcd,cakl,dbij->abij", "ijab T u2"),
+    (-2., "klcd,cdki,ablj->abij", "ijab T u2"), (-2., "klcd,caki,bdlj->abij", "ijab T u2"),
+    (+2., "kaci,cbkj->abij", "iabj u2"), (-2., "klcd,acki,dblj->abij", "ijab T u2"),
+    (-2., "kldc,caki,dblj->abij", "ijab T u2"), (-2., "kldc,abkj,dcil->abij", "ijab T u2"),
+    (-2., "lkcd,cbij,adlk->abij", "ijab T u2"), (-1., "ki,abkj->abij", "foo u2"),
+    (+1., "ac,cbij->abij", "fvv u2"), (-1., "kaic,cbkj->abij", "iajb u2"),
+    (-1., "kbic,ackj->abij", "iajb u2"), (+1., "klcd,ackl,dbij->abij", "ijab T u2"),
+    (+1., "kldc,cdki,ablj->abij", "ijab T u2"), (+1., "klcd,acki,bdlj->abij", "ijab T u2"),
+    (-1., "kaci,bckj->abij", "iabj u2"), (+1., "kldc,acki,dblj->abij", "ijab T u2"),
+    (+1., "kldc,abkj,dcli->abij", "ijab T u2"), (+1., "kldc,caki,dbjl->abij", "ijab T u2"),
+    (+1., "kldc,ackj,dbil->abij", "ijab T u2"), (+1., "lkcd,cbij,dalk->abij", "ijab T u2"),
+]
+
+SIGMA2_NP_TERMS = [                                                    # eom_ccsd.py:380-383
+    (+1., "klij,abkl->abij", "klij u2"), (+1., "kldc,abkl,dcij->abij", "ijab T u2"),
+    (+1., "lkcd,cdij,ablk->abij", "ijab T u2"), (+1., "abcd,cdij->abij", "abcd u2"),
+]
+
+
+def _eom_ops(no, fock, dV, u1, u2, T2):
+    ops = dict(dV)
+    ops.update(foo=fock[:no, :no], fov=fock[:no, no:], fvv=fock[no:, no:], T=T2, u1=u1, u2=u2)
+    return ops
+
+
+def eom_sigma_singles(no, fock, dV, u1, u2, T2):
+    """eom_ccsd.py:268-310."""
+    ops = _eom_ops(no, fock, dV, u1, u2, T2)
+    out = np.zeros(u1.shape, dtype=np.result_type(u1, u2))
+    for coef, spec, names in SIGMA1_TERMS:
+        out += coef * _es(spec, *[ops[n] for n in names.split()])
+    return out
+
+
+def eom_sigma_doubles(no, fock, dV, u1, u2, T2):
+    """eom_ccsd.py:312-385 (explicit + baji permutation at line 377)."""
+    ops = _eom_ops(no, fock, dV, u1, u2, T2)
+    out = np.zeros(u2.shape, dtype=np.result_type(u1, u2))
+    for coef, spec, names in SIGMA2_P_TERMS:
+        out += coef * _es(spec, *[ops[n] for n in names.split()])
+    out = out + out.transpose(1, 0, 3, 2)
+    for coef, spec, names in SIGMA2_NP_TERMS:
+        out += coef * _es(spec, *[ops[n] for n in names.split()])
+    return out
+
+
+def eom_diag_singles(no, fock, dV, T2):
+    """eom_ccsd.py:169-198."""
+    V, d = dV["ijab"], None
+    d = -fock[:no, :no].diagonal()[None, :] + fock[no:, no:].diagonal()[:, None]
+    d = d + 2. * _es("iaai->ai", dV["iabj"]) - _es("iaia->ai", dV["iajb"])
+    d = d + 4. * _es("jiba,baji->ai", V, T2)
+    d = d - 2. * _es("jkba,abjk->a", V, T2)[:, None] - 2. * _es("jicb,bcji->i", V, T2)[None, :]
+    d = d - 2. * _es("jiba,abji->ai", V, T2) - 2. * _es("jiab,baji->ai", V, T2)
+    d = d + _es("jkab,abjk->a", V, T2)[:, None] + _es("jicb,bcji->i", V, T2)[None, :]
+    return d + _es("jiab,abji->ai", V, T2)
+
+
+def eom_diag_doubles(no, fock, dV, T2):
+    """eom_ccsd.py:200-266 (including the [a,i] placement of the "ibib->bi" term, line 231)."""
+    V, nv = dV["ijab"], T2.shape[0]
+    ai = lambda x: x[:, None, :, None]
+    d = np.zeros((nv, nv, no, no))
+    d += ai(4. * _es("kica,caki->ai", V, T2))
+    d += -2. * _es("klca,cakl->a", V, T2)[:, None, None, None]
+    d += -2. * _es("kicd,cdki->i", V, T2)[None, None, :, None]
+    d += ai(-2. * _es("kica,caki->ai", V, T2))
+    d += ai(2. * _es("iaai->ai", dV["iabj"]))
+    d += ai(-2. * _es("kica,acki->ai", V, T2))
+    d += ai(-2. * _es("kiac,caki->ai", V, T2))
+    d += -2. * _es("kjab,abkj->abj", V, T2)[:, :, None, :]
+    d += -2. * _es("ijcb,cbij->ij", V, T2)[None, None, :, :]
+    d += -fock[:no, :no].diagonal()[None, None, :, None] + fock[no:, no:].diagonal()[:, None, None, None]
+    d += ai(-1. * _es("iaia->ai", dV["iajb"]))
+    d += ai(-1. * _es("ibib->bi", dV["iajb"]))
+    d += _es("klca,ackl->a", V, T2)[:, None, None, None]
+    d += _es("kidc,cdki->i", V, T2)[None, None, :, None]
+    d += ai(_es("kicb,acki->ai", V, T2))
+    d += ai(-1. * _es("iaai->ai", dV["iabj"]))
+    d += ai(_es("kiac,acki->ai", V, T2))
+    d += _es("kiab,abkj->abij", V, T2)
+    d += _es("kjac,caki->aij", V, T2)[:, None, :, :]
+    d += _es("kjac,ackj->aj", V, T2)[:, None, None, :]
+    d += _es("ijca,cbij->abij", V, T2)
+    d = d + d.transpose(1, 0, 3, 2)
+    d += _es("ijij->ij", dV["klij"])[None, None, :, :]
+    d += _es("klab,abkl->ab", V, T2)[:, :, None, None]
+    d += _es("ijcd,cdij->ij", V, T2)[None, None, :, :]
+    d += _es("abab->ab", dV["abcd"])[:, :, None, None]
+    return d
+
+
+def eom_davidson(no, fock, dV, T2, n_excit=3, max_iter=500, e_epsilon=1e-8):
+    """Block Davidson of eom_ccsd.py:46-167: unit guesses on the smallest eps_a - eps_i, dense QR
+    of the whole subspace every sweep, sigma for every vector, plain (non-conjugated) projections,
+    scalar preconditioner e_n - D_guess + 1e-5, collapse at 4 n_excit vectors."""
+    nv = T2.shape[0]
+    eps = fock.diagonal()
+    D_ai = -(eps[:no][None, :] - eps[no:][:, None]).ravel()
+    guess = np.argsort(D_ai)[:n_excit]
+    n1 = nv * no
+    U = np.zeros((n1 + T2.size, n_excit))
+    U[guess, np.arange(n_excit)] = 1.0
+    e_excit = np.zeros(n_excit)
+    diff = np.inf
+    for it in range(max_iter):
+        U, _ = np.linalg.qr(U)                                  # eom_ccsd.py:512-541
+        m = U.shape[1]
+        W = np.empty_like(U)
+        for l in range(m):
+            u1, u2 = U[:n1, l].reshape(nv, no), U[n1:, l].reshape(T2.shape)
+            W[:n1, l] = eom_sigma_singles(no, fock, dV, u1, u2, T2).ravel()
+            W[n1:, l] = eom_sigma_doubles(no, fock, dV, u1, u2, T2).ravel()
+        B = U.T @ W                                             # eom_ccsd.py:103-109
+        ev, v = np.linalg.eig(B)
+        low = ev.argsort()[:n_excit]
+        e, v = np.real(ev[low]), np.real(v[:, low])
+        if m >= 4 * n_excit:                                    # eom_ccsd.py:122-133
+            U = U @ v
+        else:                                                   # eom_ccsd.py:134-147
+            Y = (W @ v - (U @ v) * e[None, :]) / (e - D_ai[guess] + 1e-5)[None, :]
+            U = np.concatenate([U, Y], axis=1)
+            diff = np.linalg.norm(e_excit - e)
+            e_excit = e
+        if diff < e_epsilon:
+            break
+    return e_excit, it + 1
+
+
 def flops_doubles_residual(no, nv, is_dcd=False):
     """Algorithmic flop count of one residual (SURVEY 8d / BASELINE.md 3)."""
     o, v = float(no), float(nv)

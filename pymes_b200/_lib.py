@@ -28,6 +28,13 @@ class Contract(C.Structure):
                 ("C", C.c_void_p), ("beta", C.c_double), ("terms", Term * MAX_TERMS)]
 
 
+class Bdot(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("B", C.c_void_p), ("out", C.c_void_p), ("ni", C.c_int32), ("nr", C.c_int32),
+                ("i_ext", I64x4), ("o_istr", I64x4), ("a_istr", I64x4), ("b_istr", I64x4),
+                ("r_ext", I64x4), ("a_rstr", I64x4), ("b_rstr", I64x4),
+                ("alpha", C.c_double), ("beta", C.c_double)]
+
+
 class Ueg(C.Structure):
     _fields_ = [("n_orb", C.c_int32), ("imax", C.c_int32), ("n_occ", C.c_int32), ("n_ele", C.c_int32),
                 ("omega", C.c_double), ("u_table", C.c_void_p), ("u_table_len", C.c_int32),
@@ -60,6 +67,7 @@ _SIGS = {
     "pmb_lincomb": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_void_p), C.c_int64, C.c_double,
                               C.c_void_p, C.c_void_p]),
     "pmb_reduce_workspace": (C.c_size_t, []),
+    "pmb_bdot": (C.c_int, [C.POINTER(Bdot), C.c_void_p]),
     "pmb_ueg_umat": (C.c_int, [C.POINTER(Ueg), C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_void_p]),
     "pmb_ueg_pair_tables": (C.c_int, [C.POINTER(Ueg), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -400,6 +400,76 @@ def lincomb(coefs, xs, out=None, beta=0.0):
     return out
 
 
+def bdot(spec, A, B, out=None, alpha=1.0, beta=0.0):
+    """out[I] = beta*out + alpha * sum_R A[I,R]*B[I,R] for einsum strings in which some index is
+    shared by both operands AND the output (e.g. "kica,caki->ai"), which no GEMM expresses.
+    Indices of one operand only must appear in the output.  HBM-bound ``pmb_bdot``."""
+    lib = _lib.load()
+    sa, sb, so = _parse(spec)
+    A, B = asdev(A), asdev(B)
+    ext = {}
+    for sub, t in ((sa, A), (sb, B)):
+        if len(set(sub)) != len(sub) or t.dim() != len(sub):
+            raise ValueError("bad subscripts %s" % sub)
+        for ch, n in zip(sub, t.shape):
+            if ext.setdefault(ch, int(n)) != int(n):
+                raise ValueError("extent mismatch for %s" % ch)
+    red = [ch for ch in sa if ch in sb and ch not in so]
+    if (set(sa) | set(sb)) - set(red) != set(so) or len(set(so)) != len(so):
+        raise ValueError("every non-summed index must appear in the output: %s" % spec)
+    if len(so) > 4 or len(red) > 4:
+        raise ValueError("at most 4 output and 4 summed indices")
+    shape = tuple(ext[ch] for ch in so)
+    if out is None:
+        if beta != 0.0:
+            raise ValueError("beta != 0 needs an output tensor")
+        out = empty(*shape)
+    elif tuple(out.shape) != shape:
+        raise ValueError("output shape mismatch")
+    astr, bstr, ostr = dict(zip(sa, A.stride())), dict(zip(sb, B.stride())), dict(zip(so, out.stride()))
+    iord = sorted(so, key=lambda ch: (ostr[ch], ch))            # fastest output index first
+    rord = sorted(red, key=lambda ch: (astr[ch], ch))
+    d = _lib.Bdot()
+    d.A, d.B, d.out = A.data_ptr(), B.data_ptr(), out.data_ptr()
+    d.ni, d.nr, d.alpha, d.beta = len(iord), len(rord), float(alpha), float(beta)
+    _fill(d.i_ext, [ext[ch] for ch in iord])
+    _fill(d.o_istr, [ostr[ch] for ch in iord])
+    _fill(d.a_istr, [astr.get(ch, 0) for ch in iord])
+    _fill(d.b_istr, [bstr.get(ch, 0) for ch in iord])
+    _fill(d.r_ext, [ext[ch] for ch in rord])
+    _fill(d.a_rstr, [astr[ch] for ch in rord])
+    _fill(d.b_rstr, [bstr[ch] for ch in rord])
+    _lib.check(lib.pmb_bdot(C.byref(d), _stream()), "pmb_bdot")
+    return out
+
+
+def diag_view(t, sub, out_sub):
+    """Strided VIEW of a tensor with repeated subscripts, e.g. diag_view(V, "iaai", "ai")[a,i] =
+    V[i,a,a,i] (the einsum("iaai->ai") of eom_ccsd.py:182); no data is moved."""
+    strides, sizes = {}, {}
+    for ch, st, n in zip(sub, t.stride(), t.shape):
+        strides[ch] = strides.get(ch, 0) + st
+        if sizes.setdefault(ch, n) != n:
+            raise ValueError("repeated index %s with different extents" % ch)
+    if set(out_sub) != set(sub):
+        raise ValueError("diag_view keeps every index: %s -> %s" % (sub, out_sub))
+    return torch.as_strided(t, [sizes[ch] for ch in out_sub], [strides[ch] for ch in out_sub],
+                            t.storage_offset())
+
+
+def add_broadcast(alpha, src, src_sub, out, out_sub):
+    """out[out_sub] += alpha * src[src_sub] with src broadcast over the indices it lacks
+    (numpy's ``x[:, None, :, None]`` adds of eom_ccsd.py:206-262)."""
+    lib = _lib.load()
+    src = asdev(src)
+    sstr = dict(zip(src_sub, src.stride()))
+    ext = _lib.I64x4(*_pad4(out.shape, 1))
+    si = _lib.I64x4(*_pad4([sstr.get(ch, 0) for ch in out_sub], 0))
+    so = _lib.I64x4(*_pad4(out.stride(), 0))
+    _lib.check(lib.pmb_axpby4(ext, float(alpha), _ptr(src), si, 1.0, _ptr(out), so, _stream()), "pmb_axpby4")
+    return out
+
+
 # --------------------------------------------------------------------------
 # N-operand einsum (pairwise evaluation on the DMMA engine)
 # --------------------------------------------------------------------------

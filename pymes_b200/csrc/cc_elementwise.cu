@@ -226,6 +226,76 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// out[I] = beta*out[I] + alpha * sum_R A[I,R]*B[I,R]; one warp per output element when the
+// reduction is long (lanes stride over R, fixed-order shuffle tree), one thread otherwise.
+struct BdotDev {
+    const double *A, *B;
+    double *out;
+    int ni, nr;
+    long long I, R;
+    long long i_ext[4], o_istr[4], a_istr[4], b_istr[4], r_ext[4], a_rstr[4], b_rstr[4];
+    double alpha, beta;
+};
+
+__device__ __forceinline__ void bdot_offsets(const BdotDev &d, long long idx, long long &oo, long long &ao,
+                                             long long &bo) {
+    oo = ao = bo = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < d.ni) {
+            const long long e = d.i_ext[k], q = idx / e, r = idx - q * e;
+            oo += r * d.o_istr[k];
+            ao += r * d.a_istr[k];
+            bo += r * d.b_istr[k];
+            idx = q;
+        }
+    }
+}
+
+__device__ __forceinline__ double bdot_term(const BdotDev &d, long long ridx, long long ao, long long bo) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < d.nr) {
+            const long long e = d.r_ext[k], q = ridx / e, r = ridx - q * e;
+            ao += r * d.a_rstr[k];
+            bo += r * d.b_rstr[k];
+            ridx = q;
+        }
+    }
+    return d.A[ao] * d.B[bo];
+}
+
+__global__ void __launch_bounds__(256) bdot_thread_kernel(const __grid_constant__ BdotDev d) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < d.I;
+         idx += (long long)gridDim.x * blockDim.x) {
+        long long oo, ao, bo;
+        bdot_offsets(d, idx, oo, ao, bo);
+        double s = 0.0;
+        for (long long r = 0; r < d.R; ++r) s += bdot_term(d, r, ao, bo);
+        s *= d.alpha;
+        if (d.beta != 0.0) s += d.beta * d.out[oo];
+        d.out[oo] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) bdot_warp_kernel(const __grid_constant__ BdotDev d) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < d.I; idx += warps) {
+        long long oo, ao, bo;
+        bdot_offsets(d, idx, oo, ao, bo);
+        double s = 0.0;
+        for (long long r = lane; r < d.R; r += 32) s += bdot_term(d, r, ao, bo);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            s *= d.alpha;
+            if (d.beta != 0.0) s += d.beta * d.out[oo];
+            d.out[oo] = s;
+        }
+    }
+}
+
 static Str4 make_str(const int64_t ext[4], const int64_t in_str[4], const int64_t out_str[4]) {
     Str4 g;
     for (int d = 0; d < 4; ++d) {
@@ -367,6 +437,42 @@ extern "C" int pmb_lincomb(int nvec, const double *c_host, const double *const *
     }
     lincomb_kernel<<<grid_for((size_t)n, 256, 16 * kSmCount), 256, 0, (cudaStream_t)stream>>>(
         L, nvec, (size_t)n, beta, out);
+    count_launch();
+    return cuda_status();
+}
+
+extern "C" int pmb_bdot(const pmb_bdot_t *d, pmb_stream_t stream) {
+    if (!d || !d->A || !d->B || !d->out || d->ni < 0 || d->ni > 4 || d->nr < 0 || d->nr > 4) return PMB_E_BADARG;
+    BdotDev k;
+    k.A = d->A;
+    k.B = d->B;
+    k.out = d->out;
+    k.ni = d->ni;
+    k.nr = d->nr;
+    k.alpha = d->alpha;
+    k.beta = d->beta;
+    k.I = k.R = 1;
+    for (int i = 0; i < 4; ++i) {
+        const bool ui = i < d->ni, ur = i < d->nr;
+        if ((ui && d->i_ext[i] <= 0) || (ur && d->r_ext[i] <= 0)) return PMB_E_BADARG;
+        k.i_ext[i] = ui ? d->i_ext[i] : 1;
+        k.o_istr[i] = ui ? d->o_istr[i] : 0;
+        k.a_istr[i] = ui ? d->a_istr[i] : 0;
+        k.b_istr[i] = ui ? d->b_istr[i] : 0;
+        k.r_ext[i] = ur ? d->r_ext[i] : 1;
+        k.a_rstr[i] = ur ? d->a_rstr[i] : 0;
+        k.b_rstr[i] = ur ? d->b_rstr[i] : 0;
+        k.I *= k.i_ext[i];
+        k.R *= k.r_ext[i];
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (k.R >= 64) {
+        long long blocks = (k.I + 7) / 8;
+        if (blocks > 32LL * kSmCount) blocks = 32LL * kSmCount;
+        bdot_warp_kernel<<<(unsigned)blocks, 256, 0, s>>>(k);
+    } else {
+        bdot_thread_kernel<<<grid_for((size_t)k.I, 256, 16 * kSmCount), 256, 0, s>>>(k);
+    }
     count_launch();
     return cuda_status();
 }

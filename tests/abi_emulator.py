@@ -96,6 +96,23 @@ class FakeLib:
         win[offs - lo] = new
         return 0
 
+    def pmb_bdot(self, dref, stream):
+        d = dref._obj
+        self.launches += 1
+        i_ext = [d.i_ext[i] for i in range(d.ni)]
+        r_ext = [d.r_ext[i] for i in range(d.nr)]
+        oi = _offsets(i_ext, [d.o_istr[i] for i in range(d.ni)])
+        ai = _offsets(i_ext, [d.a_istr[i] for i in range(d.ni)])
+        bi = _offsets(i_ext, [d.b_istr[i] for i in range(d.ni)])
+        ar = _offsets(r_ext, [d.a_rstr[i] for i in range(d.nr)])
+        br = _offsets(r_ext, [d.b_rstr[i] for i in range(d.nr)])
+        A, _, _ = _gather(d.A, (ai[:, None] + ar[None, :]).reshape(-1))
+        B, _, _ = _gather(d.B, (bi[:, None] + br[None, :]).reshape(-1))
+        val = d.alpha * (A * B).reshape(len(oi), -1).sum(axis=1)
+        old, win, lo = _gather(d.out, oi)
+        win[oi - lo] = val + (d.beta * old if d.beta != 0.0 else 0.0)
+        return 0
+
     # ---- elementwise ------------------------------------------------
     def pmb_axpby4(self, ext, alpha, inp, in_str, beta, out, out_str, stream):
         self.launches += 1

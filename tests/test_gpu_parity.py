@@ -80,6 +80,16 @@ def test_ueg_tc_tables():
     host.test_ueg_tc_tables_small(None)
 
 
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_eom_sigma_diag_and_batching(tag):
+    host.test_eom_sigma_diag_and_batching(None, tag)
+
+
+@pytest.mark.parametrize("tag", ["H2_321g", "LiH_321g"])
+def test_eom_davidson_roots(tag):
+    host.test_eom_davidson_roots(None, tag)
+
+
 # --------------------------------------------------------------------------
 # contraction engine: every tile configuration, both load mappings, ragged edges,
 # split-K, multi-term accumulation, strided views
@@ -370,3 +380,35 @@ def test_residual_no_symmetry_shortcut_medium():
         got = ccd.CCD(no, is_dcd=flag).get_residual(f, T, *args)
         ref = oc.doubles_residual(no, f, T, *args, is_dcd=flag)
         assert _rel(got, ref) < 1e-12
+
+
+def test_bdot_and_views():
+    from pymes_b200 import backend as bk
+    rng = np.random.default_rng(0)
+    V, T = rng.standard_normal((6, 6, 19, 19)), rng.standard_normal((19, 19, 6, 6))
+    for spec in ["kica,caki->ai", "kjab,abkj->abj", "ijcd,cdij->ij", "kiab,abkj->abij", "klca,cakl->a",
+                 "ijca,cbij->abij", "klab,abkl->ab"]:
+        assert _rel(bk.bdot(spec, V, T).cpu().numpy(), np.einsum(spec, V, T)) < 1e-13, spec
+    Vx = bk.asdev(rng.standard_normal((6, 19, 19, 6)))
+    assert _rel(bk.diag_view(Vx, "iaai", "ai").cpu().numpy(), np.einsum("iaai->ai", Vx.cpu().numpy())) == 0
+
+
+def test_eom_sigma_medium_random_vs_oracle():
+    """o=5, v=14 random non-symmetric operands, 4 right-hand sides in one batch."""
+    from pymes_b200.solver import eom_ccsd
+    from oracle import cc_oracle as oc
+    rng = np.random.default_rng(21)
+    no, nv = 5, 14
+    n = no + nv
+    V = rng.standard_normal((n, n, n, n))
+    dV = oc.partition(no, V)
+    f = rng.standard_normal((n, n))
+    T2 = 0.2 * rng.standard_normal((nv, nv, no, no))
+    U1, U2 = rng.standard_normal((4, nv, no)), rng.standard_normal((4, nv, nv, no, no))
+    eom = eom_ccsd.EOM_CCSD(no)
+    S1, S2 = eom.sigma_batched(f, dV, U1, U2, T2)
+    for r in range(4):
+        assert _rel(S1[r].cpu().numpy(), oc.eom_sigma_singles(no, f, dV, U1[r], U2[r], T2)) < 1e-12
+        assert _rel(S2[r].cpu().numpy(), oc.eom_sigma_doubles(no, f, dV, U1[r], U2[r], T2)) < 1e-12
+    assert _rel(eom.get_diag_doubles(f, dV, T2), oc.eom_diag_doubles(no, f, dV, T2)) < 1e-12
+    assert _rel(eom.get_diag_singles(f, dV, T2), oc.eom_diag_singles(no, f, dV, T2)) < 1e-12

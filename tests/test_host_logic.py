@@ -296,3 +296,58 @@ def test_ueg_tc_tables_small(cpu_abi):
     np.testing.assert_allclose(_n(blk), ref, rtol=1e-10, atol=1e-14)
     np.testing.assert_allclose(m.double_contractions_in_3_body(), g["one_body"], rtol=1e-11)
     np.testing.assert_allclose(m.triple_contractions_in_3_body(), g["zero_body"], rtol=1e-11)
+
+
+# --------------------------------------------------------------------------
+# EOM-CCSD: compiled sigma program, batching, diagonals, Davidson
+# --------------------------------------------------------------------------
+def _dressed(g):
+    return {k[8:]: g[k] for k in g.keys() if k.startswith("dressed_")}
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_eom_sigma_diag_and_batching(cpu_abi, tag):
+    from pymes_b200.solver import eom_ccsd
+    from oracle import cc_oracle as oc
+    g = golden("dressing_random_" + tag)
+    no = int(g["no"])
+    dVt, ft, T2 = _dressed(g), g["fock_dressed"], g["T2"]
+    eom = eom_ccsd.EOM_CCSD(no, n_excit=2)
+    np.testing.assert_allclose(eom.update_singles(ft, dVt, g["u1"], g["u2"], T2), g["sigma1"], **TOL)
+    np.testing.assert_allclose(eom.update_doubles(ft, dVt, g["u1"], g["u2"], T2), g["sigma2"], **TOL)
+    np.testing.assert_allclose(eom.get_diag_singles(ft, dVt, T2), g["diag1"], **TOL)
+    np.testing.assert_allclose(eom.get_diag_doubles(ft, dVt, T2), g["diag2"], **TOL)
+    # a batch of right-hand sides in one pass == the oracle vector by vector
+    rng = np.random.default_rng(4)
+    U1 = rng.standard_normal((3,) + g["u1"].shape)
+    U2 = rng.standard_normal((3,) + g["u2"].shape)
+    S1, S2 = eom.sigma_batched(ft, dVt, _t(U1), _t(U2), T2)
+    for r in range(3):
+        np.testing.assert_allclose(_n(S1[r]), oc.eom_sigma_singles(no, ft, dVt, U1[r], U2[r], T2), **TOL)
+        np.testing.assert_allclose(_n(S2[r]), oc.eom_sigma_doubles(no, ft, dVt, U1[r], U2[r], T2), **TOL)
+    # fewer contractions than the 62 einsum terms of the reference
+    plan = eom._plan
+    n_groups = sum(len(p["direct"]) + len(p["twostep"]) for p in plan.programs.values())
+    assert n_groups <= 30
+
+
+@pytest.mark.parametrize("tag", ["H2_321g", "LiH_321g"])
+def test_eom_davidson_roots(cpu_abi, tag):
+    """LiH roots are the constants of pymes/test/test_eom_ccsd/test_eom_ccsd.py:9."""
+    from pymes_b200.solver import eom_ccsd, ccsd
+    from pymes_b200.integral.partition import part_2_body_int
+    g = golden("mol_" + tag)
+    no = int(g["n_elec"]) // 2
+    cc = ccsd.CCSD(no)
+    dV = part_2_body_int(no, g["V"])
+    ft = cc.get_T1_dressed_fock(g["fock"], g["ccsd_t1"], dV)
+    dVt = cc.get_T1_dressed_V(g["ccsd_t1"], dV)
+    eom = eom_ccsd.EOM_CCSD(no, n_excit=len(g["eom_e"]))
+    eom.max_iter = 1000
+    e = eom.solve(ft, dVt, g["ccsd_t2"])
+    np.testing.assert_allclose(e, g["eom_e"], rtol=0, atol=1e-8)
+    if tag == "LiH_321g":
+        assert np.allclose(e, [0.1180867117168979, 0.154376205595602])
+    q1, q2 = eom.QR([g["ccsd_t1"], 2 * g["ccsd_t1"] + 1.0], [g["ccsd_t2"], g["ccsd_t2"] ** 2])
+    gram = [[np.vdot(q1[a], q1[b]) + np.vdot(q2[a], q2[b]) for b in range(2)] for a in range(2)]
+    np.testing.assert_allclose(gram, np.eye(2), atol=1e-13)
