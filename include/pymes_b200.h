@@ -114,16 +114,21 @@ int pmb_axpby4(const int64_t ext[4], double alpha, const double *in,
                const int64_t in_str[4], double beta, double *out,
                const int64_t out_str[4], pmb_stream_t stream);
 
+/* Row blocks: the three functions below work on the rows a in [a_lo, a_lo+na)  */
+/* of an [a,b,i,j] tensor (the (ab)-block a rank owns in a sharded run); the   */
+/* amplitude-shaped arguments are the LOCAL contiguous [na,nv,no,no] blocks.   */
+/* a_lo = 0, na = nv is the whole tensor.                                     */
+
 /* T2[a,b,i,j] = V_abij[a,b,i,j] / (e_i + e_j - e_a - e_b + shift)            */
-/* pymes/solver/mp2.py:16-18                                                 */
-int pmb_mp2_amplitudes(int no, int nv, const double *eps_i, const double *eps_a,
-                       double shift, const double *V_abij,
+/* pymes/solver/mp2.py:16-18.  V_abij points at row a_lo (strided view).      */
+int pmb_mp2_amplitudes(int no, int nv, int a_lo, int na, const double *eps_i,
+                       const double *eps_a, double shift, const double *V_abij,
                        const int64_t v_str[4], double *T2, pmb_stream_t stream);
 
 /* dT = R * (1 / (e_i + e_j - e_a - e_b + shift)); T += delta * dT;          */
 /* scal[0] += sum dT^2.   ccd.py:123-124,138 ; ccsd.py:152-156,177-179,197   */
-int pmb_update_doubles(int no, int nv, const double *eps_i, const double *eps_a,
-                       double shift, double delta, const double *R, double *dT,
+int pmb_update_doubles(int no, int nv, int a_lo, int na, const double *eps_i,
+                       const double *eps_a, double shift, double delta, const double *R, double *dT,
                        double *T2, double *scal, void *ws, size_t ws_bytes,
                        pmb_stream_t stream);
 /* same for singles: dT1 = R1 / (e_i - e_a + shift); T1 += delta * dT1       */
@@ -135,7 +140,8 @@ int pmb_update_singles(int no, int nv, const double *eps_i, const double *eps_a,
 /* scal[2] = sum T2^2,   tau = T2 + T1 (x) T1 (T1 may be NULL).               */
 /* ccd.py:256-262,137 ; ccsd.py:458-466,196 ; mp2.py:19-20 (exchange written  */
 /* there as V[j,i,a,b]: set mp2_form = 1).                                   */
-int pmb_energy_doubles(int no, int nv, const double *T2, const double *T1,
+/* V_ijab and T1 are the FULL tensors; T2 is the local row block.              */
+int pmb_energy_doubles(int no, int nv, int a_lo, int na, const double *T2, const double *T1,
                        const double *V_ijab, const int64_t v_str[4],
                        int mp2_form, double *scal, void *ws, size_t ws_bytes,
                        pmb_stream_t stream);

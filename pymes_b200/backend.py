@@ -301,25 +301,29 @@ def copy(src):
     return axpby(1.0, src)
 
 
-def mp2_amplitudes(eps_i, eps_a, shift, V_abij):
+def mp2_amplitudes(eps_i, eps_a, shift, V_abij, rows=None):
+    """T2 = V_abij / D.  ``rows=(a_lo, na)``: V_abij is the local row block [na,nv,no,no]."""
     lib = _lib.load()
     no, nv = eps_i.numel(), eps_a.numel()
-    T2 = empty(nv, nv, no, no)
-    _lib.check(lib.pmb_mp2_amplitudes(no, nv, _ptr(eps_i), _ptr(eps_a), float(shift), _ptr(V_abij),
+    a_lo, na = rows if rows is not None else (0, nv)
+    T2 = empty(na, nv, no, no)
+    _lib.check(lib.pmb_mp2_amplitudes(no, nv, a_lo, na, _ptr(eps_i), _ptr(eps_a), float(shift), _ptr(V_abij),
                                       _lib.I64x4(*V_abij.stride()), _ptr(T2), _stream()),
                "pmb_mp2_amplitudes")
     return T2
 
 
-def update_doubles(eps_i, eps_a, shift, delta, R, T2, scal):
-    """dT = R/D, T2 += delta*dT (in place); scal[0] = |dT|^2.  Returns dT."""
+def update_doubles(eps_i, eps_a, shift, delta, R, T2, scal, rows=None):
+    """dT = R/D, T2 += delta*dT (in place); scal[0] = |dT|^2.  Returns dT.
+    ``rows=(a_lo, na)``: R and T2 are local row blocks [na,nv,no,no]."""
     lib = _lib.load()
     no, nv = eps_i.numel(), eps_a.numel()
+    a_lo, na = rows if rows is not None else (0, nv)
     dT = torch.empty_like(T2)
     ws = scratch().reduce_ws()
-    _lib.check(lib.pmb_update_doubles(no, nv, _ptr(eps_i), _ptr(eps_a), float(shift), float(delta), _ptr(R),
-                                      _ptr(dT), _ptr(T2), _ptr(scal), _ptr(ws), ws.numel() * 8, _stream()),
-               "pmb_update_doubles")
+    _lib.check(lib.pmb_update_doubles(no, nv, a_lo, na, _ptr(eps_i), _ptr(eps_a), float(shift), float(delta),
+                                      _ptr(R), _ptr(dT), _ptr(T2), _ptr(scal), _ptr(ws), ws.numel() * 8,
+                                      _stream()), "pmb_update_doubles")
     return dT
 
 
@@ -332,14 +336,16 @@ def update_singles(eps_i, eps_a, shift, delta, R1, T1):
     return dT1
 
 
-def energy_doubles(T2, V_ijab, scal, T1=None, mp2_form=False):
-    """scal[0:3] = (E_direct, E_exchange, |T2|^2) on the device."""
+def energy_doubles(T2, V_ijab, scal, T1=None, mp2_form=False, rows=None):
+    """scal[0:3] = (E_direct, E_exchange, |T2|^2) on the device (partial sums over the local
+    row block when ``rows=(a_lo, na)``; V_ijab and T1 are always the full tensors)."""
     lib = _lib.load()
-    nv, no = T2.shape[0], T2.shape[2]
+    nv, no = T2.shape[1], T2.shape[2]
+    a_lo, na = rows if rows is not None else (0, nv)
     ws = scratch().reduce_ws()
-    _lib.check(lib.pmb_energy_doubles(no, nv, _ptr(T2), _ptr(T1) if T1 is not None else None, _ptr(V_ijab),
-                                      _lib.I64x4(*V_ijab.stride()), int(mp2_form), _ptr(scal), _ptr(ws),
-                                      ws.numel() * 8, _stream()), "pmb_energy_doubles")
+    _lib.check(lib.pmb_energy_doubles(no, nv, a_lo, na, _ptr(T2), _ptr(T1) if T1 is not None else None,
+                                      _ptr(V_ijab), _lib.I64x4(*V_ijab.stride()), int(mp2_form), _ptr(scal),
+                                      _ptr(ws), ws.numel() * 8, _stream()), "pmb_energy_doubles")
     return scal
 
 

@@ -69,9 +69,9 @@ __global__ void __launch_bounds__(256) axpby4_kernel(Str4 g, double alpha, const
 
 // T2 = V_abij / (e_i + e_j - e_a - e_b + shift)
 __global__ void __launch_bounds__(256)
-    mp2_kernel(int no, int nv, const double *__restrict__ ei, const double *__restrict__ ea, double shift,
-               const double *__restrict__ V, Str4 g, double *__restrict__ T2) {
-    const size_t n = (size_t)nv * nv * no * no;
+    mp2_kernel(int no, int nv, int a_lo, int na, const double *__restrict__ ei, const double *__restrict__ ea,
+               double shift, const double *__restrict__ V, Str4 g, double *__restrict__ T2) {
+    const size_t n = (size_t)na * nv * no * no;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
          idx += (size_t)gridDim.x * blockDim.x) {
         size_t r = idx;
@@ -81,17 +81,18 @@ __global__ void __launch_bounds__(256)
         r /= no;
         const int b = r % nv;
         const int a = (int)(r / nv);
-        const double d = ei[i] + ei[j] - ea[a] - ea[b] + shift;
+        const double d = ei[i] + ei[j] - ea[a_lo + a] - ea[b] + shift;
         T2[idx] = V[a * g.si[0] + b * g.si[1] + i * g.si[2] + j * g.si[3]] / d;
     }
 }
 
 // dT = R * (1/D); T += delta*dT; partial sum of dT^2
 __global__ void __launch_bounds__(kReduceThreads)
-    update_doubles_kernel(int no, int nv, const double *__restrict__ ei, const double *__restrict__ ea,
-                          double shift, double delta, const double *__restrict__ R, double *__restrict__ dT,
-                          double *__restrict__ T2, double *ws) {
-    const size_t n = (size_t)nv * nv * no * no;
+    update_doubles_kernel(int no, int nv, int a_lo, int na, const double *__restrict__ ei,
+                          const double *__restrict__ ea, double shift, double delta,
+                          const double *__restrict__ R, double *__restrict__ dT, double *__restrict__ T2,
+                          double *ws) {
+    const size_t n = (size_t)na * nv * no * no;
     double s[1] = {0.0};
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
          idx += (size_t)gridDim.x * blockDim.x) {
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kReduceThreads)
         r /= no;
         const int b = r % nv;
         const int a = (int)(r / nv);
-        const double dinv = 1.0 / (ei[i] + ei[j] - ea[a] - ea[b] + shift);
+        const double dinv = 1.0 / (ei[i] + ei[j] - ea[a_lo + a] - ea[b] + shift);
         const double d = R[idx] * dinv;
         dT[idx] = d;
         T2[idx] += delta * d;
@@ -127,9 +128,10 @@ __global__ void __launch_bounds__(256)
 // energy: one CTA handles a set of (a,b) pairs; for each pair the o x o block
 // of T2 is contiguous, V[i,j,a,b] and V[i,j,b,a] are gathered.
 __global__ void __launch_bounds__(kReduceThreads)
-    energy_kernel(int no, int nv, const double *__restrict__ T2, const double *__restrict__ T1,
-                  const double *__restrict__ V, Str4 g, int mp2_form, double *ws) {
-    const size_t n = (size_t)nv * nv * no * no;
+    energy_kernel(int no, int nv, int a_lo, int na, const double *__restrict__ T2,
+                  const double *__restrict__ T1, const double *__restrict__ V, Str4 g, int mp2_form,
+                  double *ws) {
+    const size_t n = (size_t)na * nv * no * no;
     double s[3] = {0.0, 0.0, 0.0};
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
          idx += (size_t)gridDim.x * blockDim.x) {
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(kReduceThreads)
         const int i = r % no;
         r /= no;
         const int b = r % nv;
-        const int a = (int)(r / nv);
+        const int a = a_lo + (int)(r / nv);
         const double t = T2[idx];
         double tau = t;
         if (T1) tau += T1[a * no + i] * T1[b * no + j];
@@ -328,26 +330,30 @@ extern "C" int pmb_axpby4(const int64_t ext[4], double alpha, const double *in, 
     return cuda_status();
 }
 
-extern "C" int pmb_mp2_amplitudes(int no, int nv, const double *eps_i, const double *eps_a, double shift,
-                                  const double *V_abij, const int64_t v_str[4], double *T2,
+static bool bad_rows(int nv, int a_lo, int na) { return a_lo < 0 || na <= 0 || a_lo + na > nv; }
+
+extern "C" int pmb_mp2_amplitudes(int no, int nv, int a_lo, int na, const double *eps_i, const double *eps_a,
+                                  double shift, const double *V_abij, const int64_t v_str[4], double *T2,
                                   pmb_stream_t stream) {
-    if (no <= 0 || nv <= 0 || !eps_i || !eps_a || !V_abij || !v_str || !T2) return PMB_E_BADARG;
-    const size_t n = (size_t)nv * nv * no * no;
+    if (no <= 0 || nv <= 0 || bad_rows(nv, a_lo, na) || !eps_i || !eps_a || !V_abij || !v_str || !T2)
+        return PMB_E_BADARG;
+    const size_t n = (size_t)na * nv * no * no;
     mp2_kernel<<<grid_for(n, 256, 16 * kSmCount), 256, 0, (cudaStream_t)stream>>>(
-        no, nv, eps_i, eps_a, shift, V_abij, make_str(nullptr, v_str, nullptr), T2);
+        no, nv, a_lo, na, eps_i, eps_a, shift, V_abij, make_str(nullptr, v_str, nullptr), T2);
     count_launch();
     return cuda_status();
 }
 
-extern "C" int pmb_update_doubles(int no, int nv, const double *eps_i, const double *eps_a, double shift,
-                                  double delta, const double *R, double *dT, double *T2, double *scal,
-                                  void *ws, size_t ws_bytes, pmb_stream_t stream) {
-    if (no <= 0 || nv <= 0 || !eps_i || !eps_a || !R || !dT || !T2 || !scal) return PMB_E_BADARG;
+extern "C" int pmb_update_doubles(int no, int nv, int a_lo, int na, const double *eps_i, const double *eps_a,
+                                  double shift, double delta, const double *R, double *dT, double *T2,
+                                  double *scal, void *ws, size_t ws_bytes, pmb_stream_t stream) {
+    if (no <= 0 || nv <= 0 || bad_rows(nv, a_lo, na) || !eps_i || !eps_a || !R || !dT || !T2 || !scal)
+        return PMB_E_BADARG;
     if (!ws || ws_bytes < pmb_reduce_workspace()) return PMB_E_WORKSPACE;
-    const size_t n = (size_t)nv * nv * no * no;
+    const size_t n = (size_t)na * nv * no * no;
     const int blocks = grid_for(n, kReduceThreads, kReduceBlocks);
     update_doubles_kernel<<<blocks, kReduceThreads, 0, (cudaStream_t)stream>>>(
-        no, nv, eps_i, eps_a, shift, delta, R, dT, T2, (double *)ws);
+        no, nv, a_lo, na, eps_i, eps_a, shift, delta, R, dT, T2, (double *)ws);
     count_launch();
     int rc = cuda_status();
     if (rc) return rc;
@@ -364,15 +370,15 @@ extern "C" int pmb_update_singles(int no, int nv, const double *eps_i, const dou
     return cuda_status();
 }
 
-extern "C" int pmb_energy_doubles(int no, int nv, const double *T2, const double *T1, const double *V_ijab,
-                                  const int64_t v_str[4], int mp2_form, double *scal, void *ws,
-                                  size_t ws_bytes, pmb_stream_t stream) {
-    if (no <= 0 || nv <= 0 || !T2 || !V_ijab || !v_str || !scal) return PMB_E_BADARG;
+extern "C" int pmb_energy_doubles(int no, int nv, int a_lo, int na, const double *T2, const double *T1,
+                                  const double *V_ijab, const int64_t v_str[4], int mp2_form, double *scal,
+                                  void *ws, size_t ws_bytes, pmb_stream_t stream) {
+    if (no <= 0 || nv <= 0 || bad_rows(nv, a_lo, na) || !T2 || !V_ijab || !v_str || !scal) return PMB_E_BADARG;
     if (!ws || ws_bytes < pmb_reduce_workspace()) return PMB_E_WORKSPACE;
-    const size_t n = (size_t)nv * nv * no * no;
+    const size_t n = (size_t)na * nv * no * no;
     const int blocks = grid_for(n, kReduceThreads, kReduceBlocks);
     energy_kernel<<<blocks, kReduceThreads, 0, (cudaStream_t)stream>>>(
-        no, nv, T2, T1, V_ijab, make_str(nullptr, v_str, nullptr), mp2_form, (double *)ws);
+        no, nv, a_lo, na, T2, T1, V_ijab, make_str(nullptr, v_str, nullptr), mp2_form, (double *)ws);
     count_launch();
     int rc = cuda_status();
     if (rc) return rc;

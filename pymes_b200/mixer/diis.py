@@ -26,19 +26,24 @@ class DIIS:
         self.amplitude_list = []
         self.allreduce = allreduce      # callable(np.ndarray) -> np.ndarray, or None
 
-    def _overlap_row(self):
-        """Re sum_nt <e_i[nt], e_new[nt]> for every stored i (diis.py:65-78)."""
+    def _overlap_row(self, sharded=None):
+        """Re sum_nt <e_i[nt], e_new[nt]> for every stored i (diis.py:65-78).  Tensors flagged
+        in ``sharded`` hold only this rank's rows: their partial dots are summed over ranks,
+        replicated tensors are counted once."""
         n = len(self.error_list)
-        row = np.zeros(n)
+        row, row_sh = np.zeros(n), np.zeros(n)
         new = self.error_list[-1]
         for nt in range(len(new)):
-            got = bk.dots([self.error_list[i][nt] for i in range(n)], new[nt])
-            row += got.cpu().numpy()
-        if self.allreduce is not None:
-            row = self.allreduce(row)
-        return row
+            got = bk.dots([self.error_list[i][nt] for i in range(n)], new[nt]).cpu().numpy()
+            if sharded is not None and sharded[nt]:
+                row_sh += got
+            else:
+                row += got
+        if self.allreduce is not None and sharded is not None and any(sharded):
+            row_sh = self.allreduce(row_sh)
+        return row + row_sh
 
-    def mix(self, error, amplitude):
+    def mix(self, error, amplitude, sharded=None):
         """error / amplitude: lists of device tensors (e.g. [dT1, dT2], [T1, T2]).
         Returns the extrapolated amplitudes as new tensors."""
         error = [bk.asdev(e).contiguous() for e in error]
@@ -58,7 +63,7 @@ class DIIS:
             L[:-3, :-3] = self.L[1:-2, 1:-2]       # sic: reference bookkeeping
         else:
             L[:-2, :-2] = self.L[:-1, :-1]
-        L[:n, -2] += self._overlap_row()
+        L[:n, -2] += self._overlap_row(sharded)
         L[-2, :] = L[:, -2]
         self.L = L.copy()
 

@@ -225,11 +225,13 @@ class UEG:
         print_logging_info("{:.3f} s spent on ".format(time.time() - t0) + __name__, level=1)
         return out
 
-    def eval_2b_blocks(self, no, keys, parts):
+    def eval_2b_blocks(self, no, keys, parts, ranges=None):
         """Named sub-blocks (partition.py keys, e.g. "abcd") of a SUM of integral kinds,
         built directly on the device: ``parts`` is a list of ``(mode, correlator)``;
         ``effect_2b`` parts enter symmetrised exactly as in
-        test_symmetrised_2body_integral.py:141-145.  Returns ``{key: cuda tensor}``."""
+        test_symmetrised_2body_integral.py:141-145.  ``ranges`` = ``{key: {dim: (lo, n)}}`` restricts
+        a dimension of a block to absolute orbital indices [lo, lo+n) (the row block one rank of
+        a sharded run owns).  Returns ``{key: cuda tensor}``."""
         nP = self.n_orb
         tabs = []
         for mode, corr in parts:
@@ -245,9 +247,11 @@ class UEG:
             W0s = sym[0][1] if len(sym) == 1 else bk.lincomb([1.0] * len(sym), [t[1] for t in sym])
         out = {}
         for key in keys:
-            lo = tuple(0 if ch in OCCUPIED else no for ch in key)
-            ext = tuple(no if ch in OCCUPIED else nP - no for ch in key)
-            out[key] = self.build_block(lo, ext, W0a=W0a, W1a=W1a, W0s=W0s)
+            lo = [0 if ch in OCCUPIED else no for ch in key]
+            ext = [no if ch in OCCUPIED else nP - no for ch in key]
+            for dim, (r_lo, r_n) in (ranges or {}).get(key, {}).items():
+                lo[dim], ext[dim] = int(r_lo), int(r_n)
+            out[key] = self.build_block(tuple(lo), tuple(ext), W0a=W0a, W1a=W1a, W0s=W0s)
         return out
 
     # ------------------------------------------------- 3-body mean-field parts

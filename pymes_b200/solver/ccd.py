@@ -31,16 +31,39 @@ from ..mixer import diis
 from . import mp2
 
 
+class _Whole:
+    """Trivial shard: one rank owns every row (the single-GPU case)."""
+    lo, size = 0, 1
+
+    def __init__(self, nv):
+        self.na = nv
+
+    def rows(self, t, dim=0):
+        return t
+
+    def gather(self, local):
+        return local
+
+
 def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abcd,
-                     is_dcd=False, is_bruekner=False, pp_ladder=None):
+                     is_dcd=False, is_bruekner=False, pp_ladder=None, shard=None):
     """R_abij for device tensors (reference ccd.py:164-254).
 
     ``pp_ladder``: optional callable ``(T2, R) -> None`` adding V_abcd.T2 into R; used by
     CCSD (dressed ladder without forming the dressed V_abcd) and by sharded runs.
+
+    ``shard`` (``pymes_b200.parallel.Shard``): this rank owns the rows a in [lo, lo+na) of
+    every [a,b,i,j] quantity.  T2 and the o^2v^2-sized integral blocks are replicated; V_abij
+    and V_abcd are the LOCAL row blocks; the returned R is the local row block.  The only
+    exchanges are an all-gather of the ring intermediate Xai (built sharded over its row
+    index c) and an all-gather of Ex for the explicit Ex + Ex^{baji} permutation.
     """
     nv = T2.shape[0]
     ccd = not is_dcd
     ct = bk.contract_terms
+    sh = shard if shard is not None else _Whole(nv)
+    T2a = sh.rows(T2, 0)            # T2[a in A, ., ., .]
+    T2b = sh.rows(T2, 1)            # T2[., a in A, ., .]
 
     # I_klij = V_klij (+ V_ijab.T)                                   ccd.py:178-180
     I = bk.copy(V_klij)
@@ -49,7 +72,7 @@ def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abc
 
     # R = V_abij + I.T (hh ladder) + V_abcd.T (pp ladder)             ccd.py:185-187
     R = bk.copy(V_abij)
-    ladder = [(1.0, "abkl", T2, "klij", I)]
+    ladder = [(1.0, "abkl", T2a, "klij", I)]
     if pp_ladder is None:
         ladder.append((1.0, "abcd", V_abcd, "cdij", T2))
     ct("abij", ladder, out=R, beta=1.0)
@@ -57,13 +80,15 @@ def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abc
         pp_ladder(T2, R)
 
     if ccd:                                                          # ccd.py:189-191
-        X1 = ct("alcj", [(1.0, "klcd", V_ijab, "adkj", T2)])
+        X1 = ct("alcj", [(1.0, "klcd", V_ijab, "adkj", T2a)])
         ct("abij", [(1.0, "alcj", X1, "cbil", T2)], out=R, beta=1.0)
         del X1
 
     Tt = bk.tilde(T2)                                                # ccd.py:199
-    Xai = ct("cbkj", [(1.0, "klcd", V_ijab, "dblj", Tt)])            # ccd.py:202
-    ct("abij", [(1.0, "acik", Tt, "cbkj", Xai)], out=R, beta=1.0)    # ccd.py:204
+    Tta = sh.rows(Tt, 0)
+    # Xai[c,b,k,j]: every rank builds its rows c, then all ranks need all of it   ccd.py:202
+    Xai = sh.gather(ct("cbkj", [(1.0, "klcd", sh.rows(V_ijab, 2), "dblj", Tt)]))
+    ct("abij", [(1.0, "acik", Tta, "cbkj", Xai)], out=R, beta=1.0)   # ccd.py:204
     del Xai
 
     # Fock-like intermediates; the reference adds the same product twice for CCD
@@ -78,17 +103,22 @@ def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abc
         ct("ac", [(-0.5, "adkl", Tt, "lkdc", V_ijab)], out=Xac, beta=1.0)
         ct("ki", [(+0.5, "cdil", Tt, "lkdc", V_ijab)], out=Xki, beta=1.0)
 
-    Ex = ct("abij", [(1.0, "ac", Xac, "cbij", T2)])                  # ccd.py:231
-    ct("abij", [(-1.0, "ki", Xki, "abkj", T2)], out=Ex, beta=1.0)    # ccd.py:232
-    ring = [(-1.0, "kaic", V_iajb, "cbkj", T2),                      # ccd.py:233
-            (+1.0, "acik", Tt, "kbcj", V_iabj)]                      # ccd.py:235
+    Ex = ct("abij", [(1.0, "ac", sh.rows(Xac, 0), "cbij", T2)])      # ccd.py:231
+    ct("abij", [(-1.0, "ki", Xki, "abkj", T2a)], out=Ex, beta=1.0)   # ccd.py:232
+    ring = [(-1.0, "kaic", sh.rows(V_iajb, 1), "cbkj", T2),          # ccd.py:233
+            (+1.0, "acik", Tta, "kbcj", V_iabj)]                     # ccd.py:235
     if ccd:                                                          # ccd.py:238-240
-        Xp = ct("alci", [(1.0, "klcd", V_ijab, "daki", T2)])
+        Xp = ct("alci", [(1.0, "klcd", V_ijab, "daki", T2b)])
         ring += [(-1.0, "alci", Xp, "cblj", T2), (+1.0, "alci", Xp, "bclj", T2)]
     ct("abij", ring, out=Ex, beta=1.0)
-    ct("abij", [(-1.0, "kbic", V_iajb, "ackj", T2)], out=Ex, beta=1.0)   # ccd.py:234
+    ct("abij", [(-1.0, "kbic", V_iajb, "ackj", T2a)], out=Ex, beta=1.0)   # ccd.py:234
 
-    bk.sym_baji(Ex, R, accumulate=True)                              # ccd.py:249-252
+    if shard is None:
+        bk.sym_baji(Ex, R, accumulate=True)                          # ccd.py:249-252
+    else:
+        Exf = sh.gather(Ex)          # the (ba) block lives on another rank
+        bk.axpby(1.0, Ex, 1.0, R)
+        bk.axpby(1.0, sh.rows(Exf.permute(1, 0, 3, 2), 0), 1.0, R)
     return R
 
 

@@ -130,19 +130,19 @@ class FakeLib:
         return (ei[None, None, :, None] + ei[None, None, None, :] - ea[:, None, None, None]
                 - ea[None, :, None, None] + shift), ei, ea
 
-    def pmb_mp2_amplitudes(self, no, nv, ei, ea, shift, V, v_str, T2, stream):
+    def pmb_mp2_amplitudes(self, no, nv, a_lo, na, ei, ea, shift, V, v_str, T2, stream):
         self.launches += 1
         D, _, _ = self._denoms(no, nv, ei, ea, shift)
-        offs = _offsets([no, no, nv, nv], [v_str[3], v_str[2], v_str[1], v_str[0]])
+        offs = _offsets([no, no, nv, na], [v_str[3], v_str[2], v_str[1], v_str[0]])
         v, _, _ = _gather(_val(V), offs)
-        _window(_val(T2), nv * nv * no * no)[:] = (v.reshape(nv, nv, no, no) / D).reshape(-1)
+        _window(_val(T2), na * nv * no * no)[:] = (v.reshape(na, nv, no, no) / D[a_lo:a_lo + na]).reshape(-1)
         return 0
 
-    def pmb_update_doubles(self, no, nv, ei, ea, shift, delta, R, dT, T2, scal, ws, wsb, stream):
+    def pmb_update_doubles(self, no, nv, a_lo, na, ei, ea, shift, delta, R, dT, T2, scal, ws, wsb, stream):
         self.launches += 2
-        n = nv * nv * no * no
+        n = na * nv * no * no
         D, _, _ = self._denoms(no, nv, ei, ea, shift)
-        d = _window(_val(R), n) * (1.0 / D).reshape(-1)
+        d = _window(_val(R), n) * (1.0 / D[a_lo:a_lo + na]).reshape(-1)
         _window(_val(dT), n)[:] = d
         _window(_val(T2), n)[:] += delta * d
         _window(_val(scal), 1)[0] = np.sum(d * d)
@@ -157,20 +157,23 @@ class FakeLib:
         _window(_val(T1), nv * no)[:] += delta * d
         return 0
 
-    def pmb_energy_doubles(self, no, nv, T2, T1, V, v_str, mp2_form, scal, ws, wsb, stream):
+    def pmb_energy_doubles(self, no, nv, a_lo, na, T2, T1, V, v_str, mp2_form, scal, ws, wsb, stream):
         self.launches += 3
-        n = nv * nv * no * no
-        t = _window(_val(T2), n).reshape(nv, nv, no, no)
+        n = na * nv * no * no
+        t = _window(_val(T2), n).reshape(na, nv, no, no)
         tau = t
         if _val(T1):
             t1 = _window(_val(T1), nv * no).reshape(nv, no)
-            tau = t + np.einsum("ai,bj->abij", t1, t1)
+            tau = t + np.einsum("ai,bj->abij", t1[a_lo:a_lo + na], t1)
         offs = _offsets([nv, nv, no, no], [v_str[3], v_str[2], v_str[1], v_str[0]])
         v, _, _ = _gather(_val(V), offs)
         v = v.reshape(no, no, nv, nv)
         s = _window(_val(scal), 3)
-        s[0] = 2.0 * np.einsum("abij,ijab->", tau, v)
-        s[1] = -np.einsum("abij,jiab->" if mp2_form else "abij,ijba->", tau, v)
+        s[0] = 2.0 * np.einsum("abij,ijab->", tau, v[:, :, a_lo:a_lo + na, :])
+        if mp2_form:
+            s[1] = -np.einsum("abij,jiab->", tau, v[:, :, a_lo:a_lo + na, :])
+        else:
+            s[1] = -np.einsum("abij,ijba->", tau, v[:, :, :, a_lo:a_lo + na])
         s[2] = np.sum(t * t)
         return 0
 
