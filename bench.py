@@ -151,8 +151,8 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus, no):
-    cutoff = CUTOFF_FOR_GPUS[n_gpus]
+def workload_config(n_gpus, no, cutoff=None):
+    cutoff = cutoff or CUTOFF_FOR_GPUS[n_gpus]
     return {"workload": "TC-UEG 54e rs=%.1f CCSD+DIIS iteration, plane-wave cutoff %g" % (RS, cutoff),
             "method": "CCSD", "correlator": "trunc k_c=%g" % K_CUTOFF, "n_occ": no,
             "l2_policy": "inputs_exceed_l2 (V_abcd row block >> 126 MB)",
@@ -312,7 +312,7 @@ def run_ours(args):
     line = {"metric": "ccsd_iteration_fp64_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args.gpus, no), n_orb=nP, n_virt=nv,
+            "config": dict(workload_config(args.gpus, no, cutoff), n_orb=nP, n_virt=nv,
                            flops_per_step=F, energy=e_final, build_seconds=t_build),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof}
     if rank == 0:

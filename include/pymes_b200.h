@@ -187,6 +187,14 @@ typedef struct {
 } pmb_bdot_t;
 int pmb_bdot(const pmb_bdot_t *d, pmb_stream_t stream);
 
+/* Shifted complex diagonal preconditioner of the FEAST linear solves             */
+/* feast_eom_ccsd.py:341-342:  y = x / (z - diag + shift), x = xr + i xi,        */
+/* z = zr + i zi, diag real; evaluated on the fly (nothing of size n is stored   */
+/* per quadrature node).  yr/yi may alias xr/xi.                                 */
+int pmb_cdiv_shifted(int64_t n, const double *diag, double zr, double zi, double shift,
+                     const double *xr, const double *xi, double *yr, double *yi,
+                     pmb_stream_t stream);
+
 /* ------------------------------------------------------------------------ */
 /* UEG momentum-conserving two-electron integrals  pymes/model/ueg.py:265-596 */
 /*                                                                          */

@@ -68,6 +68,8 @@ _SIGS = {
                               C.c_void_p, C.c_void_p]),
     "pmb_reduce_workspace": (C.c_size_t, []),
     "pmb_bdot": (C.c_int, [C.POINTER(Bdot), C.c_void_p]),
+    "pmb_cdiv_shifted": (C.c_int, [C.c_int64, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pmb_ueg_umat": (C.c_int, [C.POINTER(Ueg), C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_void_p]),
     "pmb_ueg_pair_tables": (C.c_int, [C.POINTER(Ueg), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -449,6 +449,15 @@ def bdot(spec, A, B, out=None, alpha=1.0, beta=0.0):
     return out
 
 
+def cdiv_shifted(diag, z, shift, xr, xi):
+    """(yr, yi) = (xr + i xi) / (z - diag + shift), elementwise, for flat contiguous tensors."""
+    lib = _lib.load()
+    yr, yi = torch.empty_like(xr), torch.empty_like(xi)
+    _lib.check(lib.pmb_cdiv_shifted(diag.numel(), _ptr(diag), float(np.real(z)), float(np.imag(z)), float(shift),
+                                    _ptr(xr), _ptr(xi), _ptr(yr), _ptr(yi), _stream()), "pmb_cdiv_shifted")
+    return yr, yi
+
+
 def diag_view(t, sub, out_sub):
     """Strided VIEW of a tensor with repeated subscripts, e.g. diag_view(V, "iaai", "ai")[a,i] =
     V[i,a,a,i] (the einsum("iaai->ai") of eom_ccsd.py:182); no data is moved."""

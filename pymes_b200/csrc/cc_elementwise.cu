@@ -298,6 +298,20 @@ __global__ void __launch_bounds__(256) bdot_warp_kernel(const __grid_constant__ 
     }
 }
 
+__global__ void __launch_bounds__(256)
+    cdiv_shifted_kernel(size_t n, const double *__restrict__ diag, double zr, double zi, double shift,
+                        const double *xr, const double *xi, double *yr, double *yi) {
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const double dr = zr - diag[idx] + shift;
+        const double inv = 1.0 / (dr * dr + zi * zi);
+        const double mr = dr * inv, mi = -zi * inv;      // 1 / (dr + i zi)
+        const double a = xr[idx], b = xi[idx];
+        yr[idx] = mr * a - mi * b;
+        yi[idx] = mr * b + mi * a;
+    }
+}
+
 static Str4 make_str(const int64_t ext[4], const int64_t in_str[4], const int64_t out_str[4]) {
     Str4 g;
     for (int d = 0; d < 4; ++d) {
@@ -479,6 +493,16 @@ extern "C" int pmb_bdot(const pmb_bdot_t *d, pmb_stream_t stream) {
     } else {
         bdot_thread_kernel<<<grid_for((size_t)k.I, 256, 16 * kSmCount), 256, 0, s>>>(k);
     }
+    count_launch();
+    return cuda_status();
+}
+
+extern "C" int pmb_cdiv_shifted(int64_t n, const double *diag, double zr, double zi, double shift,
+                                const double *xr, const double *xi, double *yr, double *yi,
+                                pmb_stream_t stream) {
+    if (n <= 0 || !diag || !xr || !xi || !yr || !yi) return PMB_E_BADARG;
+    cdiv_shifted_kernel<<<grid_for((size_t)n, 256, 16 * kSmCount), 256, 0, (cudaStream_t)stream>>>(
+        (size_t)n, diag, zr, zi, shift, xr, xi, yr, yi);
     count_launch();
     return cuda_status();
 }

@@ -220,20 +220,35 @@ class SigmaPlan:
                     ct("r" + ysub, term, out=Y, beta=1.0)
             ct("r" + out, [(1.0, "r" + ysub, Y, zsub, Z)], out=out_t, beta=1.0)
 
-    def apply(self, U1, U2):
-        """sigma for a batch: U1 [r,v,o], U2 [r,v,v,o,o] (contiguous device tensors) ->
-        (S1, S2) of the same shapes.  eom_ccsd.py:268-385 for every r at once."""
+    def apply(self, U1, U2, out=None):
+        """sigma for a batch: U1 [r,v,o], U2 [r,v,v,o,o] device tensors (any strides along r,
+        each vector contiguous) -> (S1, S2).  eom_ccsd.py:268-385 for every r at once."""
         U = {"u1": U1, "u2": U2}
-        S1 = torch.zeros_like(U1)
+        r = U2.shape[0]
+        if out is None:
+            S1, S2 = bk.zeros(*U1.shape), bk.empty(*U2.shape)
+        else:
+            S1, S2 = out
+            for k in range(r):
+                S1[k].zero_()
         self._run(self.programs["s1"], U, S1)
-        Ex = torch.zeros_like(U2)
+        Ex = bk.zeros(*U2.shape)
         self._run(self.programs["s2p"], U, Ex)
-        S2 = torch.empty_like(U2)
-        for r in range(U2.shape[0]):                                   # eom_ccsd.py:377
-            bk.sym_baji(Ex[r], S2[r], accumulate=False)
+        for k in range(r):                                             # eom_ccsd.py:377
+            bk.sym_baji(Ex[k], S2[k], accumulate=False)
         del Ex
         self._run(self.programs["s2n"], U, S2)
         return S1, S2
+
+    def apply_packed(self, X):
+        """Same for vectors packed as rows [singles | doubles] of X [r, v*o + v*v*o*o]."""
+        no, nv = self.no, self.nv
+        n1 = nv * no
+        r = X.shape[0]
+        Y = bk.empty(r, X.shape[1])
+        self.apply(X[:, :n1].view(r, nv, no), X[:, n1:].view(r, nv, nv, no, no),
+                   out=(Y[:, :n1].view(r, nv, no), Y[:, n1:].view(r, nv, nv, no, no)))
+        return Y
 
 
 # --------------------------------------------------------------------------

@@ -96,6 +96,14 @@ class FakeLib:
         win[offs - lo] = new
         return 0
 
+    def pmb_cdiv_shifted(self, n, diag, zr, zi, shift, xr, xi, yr, yi, stream):
+        self.launches += 1
+        x = _window(_val(xr), n) + 1j * _window(_val(xi), n)
+        y = x / (complex(zr, zi) - _window(_val(diag), n) + shift)
+        _window(_val(yr), n)[:] = y.real
+        _window(_val(yi), n)[:] = y.imag
+        return 0
+
     def pmb_bdot(self, dref, stream):
         d = dref._obj
         self.launches += 1

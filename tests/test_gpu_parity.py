@@ -90,6 +90,14 @@ def test_eom_davidson_roots(tag):
     host.test_eom_davidson_roots(None, tag)
 
 
+def test_feast_linear_solve_matches_reference_gcrot():
+    host.test_feast_linear_solve_matches_reference_gcrot(None)
+
+
+def test_feast_batched_systems_and_seeded_iteration():
+    host.test_feast_batched_systems_and_seeded_iteration(None)
+
+
 # --------------------------------------------------------------------------
 # contraction engine: every tile configuration, both load mappings, ragged edges,
 # split-K, multi-term accumulation, strided views

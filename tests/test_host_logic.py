@@ -351,3 +351,67 @@ def test_eom_davidson_roots(cpu_abi, tag):
     q1, q2 = eom.QR([g["ccsd_t1"], 2 * g["ccsd_t1"] + 1.0], [g["ccsd_t2"], g["ccsd_t2"] ** 2])
     gram = [[np.vdot(q1[a], q1[b]) + np.vdot(q2[a], q2[b]) for b in range(2)] for a in range(2)]
     np.testing.assert_allclose(gram, np.eye(2), atol=1e-13)
+
+
+# --------------------------------------------------------------------------
+# FEAST-EOM-CCSD: batched shifted linear solves and the contour iteration
+# --------------------------------------------------------------------------
+def _feast_inputs():
+    from pymes_b200.solver import ccsd
+    from pymes_b200.integral.partition import part_2_body_int
+    g, m = golden("feast_LiH"), golden("mol_LiH_321g")
+    no = 2
+    cc = ccsd.CCSD(no)
+    dV = part_2_body_int(no, m["V"])
+    ft = cc.get_T1_dressed_fock(m["fock"], g["t1"], dV)
+    dVt = cc.get_T1_dressed_V(g["t1"], dV)
+    return g, no, ft, dVt
+
+
+def test_feast_linear_solve_matches_reference_gcrot(cpu_abi):
+    """One (z - H-bar) Q = u solve against the reference's scipy GCROT(m,k) result
+    (feast_eom_ccsd.py:293-350, tol 1e-4): same Krylov space -> same iterate."""
+    from pymes_b200.solver import feast_eom_ccsd
+    g, no, ft, dVt = _feast_inputs()
+    fe = feast_eom_ccsd.FEAST_EOM_CCSD(no, e_c=float(g["e_c"]), e_r=float(g["e_r"]), n_trial=2, max_iter=3)
+    d1, d2 = fe.get_diag_singles(ft, dVt, g["t2"]), fe.get_diag_doubles(ft, dVt, g["t2"])
+    np.testing.assert_allclose(d1, g["diag1"], **TOL)
+    np.testing.assert_allclose(d2, g["diag2"], **TOL)
+    fe.u_singles, fe.u_doubles = [g["u1"].copy()], [g["u2"].copy()]
+    q1, q2 = fe._gcrotmk(0, complex(g["z"]), d1, d2, ft, dVt, g["t2"])
+    assert fe.ls_residuals[0] < 1e-4
+    nrm = np.sqrt(np.sum(abs(g["q1"]) ** 2) + np.sum(abs(g["q2"]) ** 2))
+    err = np.sqrt(np.sum(abs(q1 - g["q1"]) ** 2) + np.sum(abs(q2 - g["q2"]) ** 2)) / nrm
+    assert err < 1e-6, err
+
+
+def test_feast_batched_systems_and_seeded_iteration(cpu_abi):
+    from pymes_b200.solver import feast_eom_ccsd
+    from pymes_b200 import backend as bk
+    from oracle import cc_oracle as oc
+    g, no, ft, dVt = _feast_inputs()
+    fe = feast_eom_ccsd.FEAST_EOM_CCSD(no, e_c=0.13, e_r=0.05, n_trial=2, max_iter=3)
+    plan = fe.plan(ft, dVt, g["t2"])
+    nv = plan.nv
+    diag = np.concatenate([g["diag1"].ravel(), g["diag2"].ravel()])
+    rng = np.random.default_rng(2)
+    zs = [0.13 + 0.05 * np.exp(1j * t) for t in (0.3, 1.1, 2.5)] * 2
+    rhs = [rng.standard_normal(diag.size) for _ in range(6)]
+    fe.ls_tol = 1e-9
+    sol = fe.solve_shifted_systems(plan, _t(diag), zs, [_t(b) for b in rhs])
+    n1 = nv * no
+    dVn = {k: np.asarray(v) for k, v in dVt.items() if v is not None}
+    for z, b, s in zip(zs, rhs, sol):
+        x = _n(s.re) + 1j * _n(s.im)
+        x1, x2 = x[:n1].reshape(nv, no), x[n1:].reshape(nv, nv, no, no)
+        hx = np.concatenate([oc.eom_sigma_singles(no, ft, dVn, x1, x2, g["t2"]).ravel(),
+                             oc.eom_sigma_doubles(no, ft, dVn, x1, x2, g["t2"]).ravel()])
+        assert np.linalg.norm(z * x - hx - b) < 1e-8 * np.linalg.norm(b)
+    # seeded 3-iteration FEAST run of the golden generator (np.random.seed(5), feast:89-91)
+    np.random.seed(5)
+    fe2 = feast_eom_ccsd.FEAST_EOM_CCSD(no, e_c=0.13, e_r=0.05, n_trial=2, max_iter=3)
+    ev = fe2.solve(ft, dVt, g["t2"])
+    np.testing.assert_allclose(np.sort(ev.real), np.sort(g["eigvals"].real), rtol=0, atol=1e-5)
+    assert np.abs(ev.imag).max() < 1e-8
+    x, w = feast_eom_ccsd.get_gauss_legendre_quadrature(8)
+    assert abs(w.sum() - 2.0) < 1e-14
