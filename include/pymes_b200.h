@@ -100,6 +100,10 @@ int pmb_contract(const pmb_contract_t *d, void *ws, size_t ws_bytes,
 /* tuning/diagnostic knobs: force a tile configuration (-1 = heuristic) and   */
 /* a split-K factor (0 = heuristic).                                         */
 void pmb_contract_set_tuning(int tile_config, int split_k);
+/* L2 budget (bytes) for one operand's k window; contractions whose smaller      */
+/* operand exceeds it are issued as a fixed-order sequence of k-window launches */
+/* accumulating in C.  0 disables the windows.  Default 40 MiB.                  */
+void pmb_contract_set_panel_bytes(long long bytes);
 
 /* ------------------------------------------------------------------------ */
 /* HBM-bound elementwise / reduction kernels                                 */

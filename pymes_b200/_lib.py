@@ -50,6 +50,7 @@ _SIGS = {
     "pmb_contract_workspace": (C.c_size_t, [C.POINTER(Contract)]),
     "pmb_contract": (C.c_int, [C.POINTER(Contract), C.c_void_p, C.c_size_t, C.c_void_p]),
     "pmb_contract_set_tuning": (None, [C.c_int, C.c_int]),
+    "pmb_contract_set_panel_bytes": (None, [C.c_longlong]),
     "pmb_axpby4": (C.c_int, [I64x4, C.c_double, C.c_void_p, I64x4, C.c_double, C.c_void_p, I64x4, C.c_void_p]),
     "pmb_mp2_amplitudes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
                                      I64x4, C.c_void_p, C.c_void_p]),

@@ -55,6 +55,7 @@ struct Params {
     double beta;
     int tiles_m, tiles_n;
     int total_ktiles, ktiles_per_split, nsplit;
+    int kt_base, kt_limit;   // k-tile window of this launch (K-panel), [0, total_ktiles) if not panelled
     double *ws;
     TermDev t[PMB_MAX_TERMS];
 };
@@ -159,8 +160,8 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
     const int tile_n = blockIdx.x % p.tiles_n, tile_m = blockIdx.x / p.tiles_n;
     const int m0 = tile_m * BM, n0 = tile_n * BN;
     const int mrem = p.M - m0, nrem = p.N - n0;
-    const int kt_lo = blockIdx.y * p.ktiles_per_split;
-    const int kt_hi = min(kt_lo + p.ktiles_per_split, p.total_ktiles);
+    const int kt_lo = p.kt_base + blockIdx.y * p.ktiles_per_split;
+    const int kt_hi = min(kt_lo + p.ktiles_per_split, p.kt_limit);
 
     // term that owns global k-tile g (terms are laid out back to back along k)
     auto term_of = [&](int g) {
@@ -359,6 +360,7 @@ constexpr int kNumCfg = 5;
 
 static int g_force_cfg = -1;
 static int g_force_split = 0;
+static long long g_panel_bytes = 40LL << 20;   // L2 budget for one operand window (0 = off)
 
 template <int BM, int BN, int STAGES>
 constexpr size_t smem_bytes(int nterms) {
@@ -487,8 +489,28 @@ static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
     if (nsplit < 1) nsplit = 1;
     p.ktiles_per_split = (kt + nsplit - 1) / nsplit;
     p.nsplit = (kt + p.ktiles_per_split - 1) / p.ktiles_per_split;
+    p.kt_base = 0;
+    p.kt_limit = kt;
     p.ws = nullptr;
     return 0;
+}
+
+// K-panels.  Every CTA streams (BM + BN) x K operand elements; CTAs of one wave share them
+// only through L2, and only while they work on the same k range.  When neither operand fits
+// in L2 (pp ladder at v >= 250: T2 is 0.6-1.4 GB) CTAs drift apart and the small operand is
+// re-read from HBM once per row tile (ncu, profiles/: 1.31 TB for 79 GB algorithmic).  The
+// contraction is therefore issued as a sequence of launches over k windows whose slice of the
+// smaller operand stays L2-resident; partial sums accumulate in C (beta = 1 after the first
+// window, fixed order, deterministic).
+static int panel_ktiles(const Params &p) {
+    if (p.nsplit > 1 || g_panel_bytes <= 0) return p.total_ktiles;
+    const double small_rows = (double)(p.M < p.N ? p.M : p.N);
+    const double small_bytes = small_rows * (double)p.total_ktiles * BK * 8.0;
+    if (small_bytes <= (double)g_panel_bytes) return p.total_ktiles;
+    long long kt = (long long)((double)g_panel_bytes / (small_rows * BK * 8.0));
+    if (kt < 64) kt = 64;
+    const int npanel = (int)((p.total_ktiles + kt - 1) / kt);
+    return (p.total_ktiles + npanel - 1) / npanel;      // equal windows
 }
 
 }  // namespace pmb
@@ -499,6 +521,8 @@ extern "C" void pmb_contract_set_tuning(int tile_config, int split_k) {
     g_force_cfg = tile_config;
     g_force_split = split_k;
 }
+
+extern "C" void pmb_contract_set_panel_bytes(long long bytes) { g_panel_bytes = bytes; }
 
 extern "C" size_t pmb_contract_workspace(const pmb_contract_t *d) {
     Params p;
@@ -524,12 +548,21 @@ extern "C" int pmb_contract(const pmb_contract_t *d, void *ws, size_t ws_bytes, 
     // owns the SM (cfg 0), costs registers/occupancy otherwise.  Tuning bit 8 flips it.
     bool il = (cfg == 0);
     if (g_force_cfg >= 0 && (g_force_cfg & 8)) il = !il;
-    switch (cfg) {
-        case 0: rc = launch_cfg<128, 128, 4, 2, 4, 1>(p, grid, s, il); break;
-        case 1: rc = launch_cfg<128, 64, 4, 2, 4, 1>(p, grid, s, il); break;
-        case 2: rc = launch_cfg<64, 64, 2, 2, 3, 3>(p, grid, s, il); break;
-        case 4: rc = launch_cfg<128, 64, 2, 2, 3, 2>(p, grid, s, il); break;
-        default: rc = launch_cfg<64, 32, 2, 2, 3, 3>(p, grid, s, il); break;
+    const int window = panel_ktiles(p);
+    for (int base = 0; base < p.total_ktiles && rc == 0; base += window) {
+        if (window < p.total_ktiles) {
+            p.kt_base = base;
+            p.kt_limit = base + window < p.total_ktiles ? base + window : p.total_ktiles;
+            p.ktiles_per_split = window;
+            if (base > 0) p.beta = 1.0;
+        }
+        switch (cfg) {
+            case 0: rc = launch_cfg<128, 128, 4, 2, 4, 1>(p, grid, s, il); break;
+            case 1: rc = launch_cfg<128, 64, 4, 2, 4, 1>(p, grid, s, il); break;
+            case 2: rc = launch_cfg<64, 64, 2, 2, 3, 3>(p, grid, s, il); break;
+            case 4: rc = launch_cfg<128, 64, 2, 2, 3, 2>(p, grid, s, il); break;
+            default: rc = launch_cfg<64, 32, 2, 2, 3, 3>(p, grid, s, il); break;
+        }
     }
     if (rc != 0) return rc;
     if (p.nsplit > 1) {

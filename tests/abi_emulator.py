@@ -69,6 +69,9 @@ class FakeLib:
     def pmb_contract_set_tuning(self, a, b):
         return None
 
+    def pmb_contract_set_panel_bytes(self, n):
+        return None
+
     # ---- contraction ------------------------------------------------
     def pmb_contract(self, dref, ws, ws_bytes, stream):
         d = dref._obj
