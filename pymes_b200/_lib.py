@@ -7,7 +7,9 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libpymes_b200.so")
+# PYMES_B200_LIB overrides the library path (A/B runs of kernel variants in tools/); the
+# default is the in-tree build
+LIB_PATH = os.environ.get("PYMES_B200_LIB") or os.path.join(_PKG, "libpymes_b200.so")
 
 MAX_DIMS = 4
 MAX_TERMS = 8

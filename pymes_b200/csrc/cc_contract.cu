@@ -82,11 +82,14 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
         : "d"(a), "d"(b));
 }
 
-// 8-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the
-// destination, which is how ragged tile edges are handled without branches.
-__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, int src_bytes) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes));
+// 8-byte asynchronous global->shared copies (LDGSTS).  Shared addresses are 32-bit
+// shared-window byte addresses so that the per-copy offset folds into the instruction.
+__device__ __forceinline__ void cp_async8(unsigned smem_addr, const double *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_addr), "l"(gsrc));
+}
+// src_bytes = 0 zero-fills the destination: ragged tile edges need no branches
+__device__ __forceinline__ void cp_async8z(unsigned smem_addr, const double *gsrc, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_addr), "l"(gsrc), "r"(src_bytes));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
@@ -100,37 +103,55 @@ __device__ __forceinline__ void cp_async_wait() {
 // s_x: per-row element offsets of this term (0 for rows outside the tensor),
 // s_k: per-k element offsets of this k-tile (0 beyond K).
 // The copies of one tile are issued in NPARTS slices (PART = 0..NPARTS-1) so that the
-// main loop can interleave them with its DMMA sub-steps.
+// main loop can interleave them with its DMMA sub-steps.  In both mappings the shared
+// destination of copy `it` is (thread base) + it * (compile-time constant); interior tiles
+// (xrem >= BX, krem >= BK) take the unpredicated path.
 template <int BX, int NT, int PART, int NPARTS>
-__device__ __forceinline__ void gather_tile(double *S, const double *__restrict__ G,
+__device__ __forceinline__ void gather_tile(unsigned S, const double *__restrict__ G,
                                             const long long *s_x, const long long *s_k, int xrem,
                                             int krem, bool kfast, int tid) {
     constexpr int PER = BX * BK / NT;
     constexpr int LD = BX + SPAD;
     static_assert(PER % NPARTS == 0, "tile copies must split evenly");
     constexpr int IT0 = PART * (PER / NPARTS), IT1 = IT0 + PER / NPARTS;
+    const bool full = xrem >= BX && krem >= BK;
     if (!kfast) {
+        constexpr int KSTEP = NT / BX;
         const int x = tid % BX;
         const int kb = tid / BX;
-        const bool xok = x < xrem;
         const double *gx = G + s_x[x];
+        const unsigned sd = S + (unsigned)((kb * LD + x) * 8);
+        if (full) {
 #pragma unroll
-        for (int it = IT0; it < IT1; ++it) {
-            const int kk = it * (NT / BX) + kb;
-            cp_async8(S + kk * LD + x, gx + s_k[kk], (xok && kk < krem) ? 8 : 0);
+            for (int it = IT0; it < IT1; ++it) cp_async8(sd + it * (KSTEP * LD * 8), gx + s_k[it * KSTEP + kb]);
+        } else {
+            const bool xok = x < xrem;
+#pragma unroll
+            for (int it = IT0; it < IT1; ++it) {
+                const int kk = it * KSTEP + kb;
+                cp_async8z(sd + it * (KSTEP * LD * 8), gx + s_k[kk], (xok && kk < krem) ? 8 : 0);
+            }
         }
     } else {
         const int lane = tid & 31, warp = tid >> 5;
         constexpr int KQ = BK / 4;
         constexpr int NW = NT / 32;
         static_assert(NW % KQ == 0, "warps must tile the k quads");
+        constexpr int XSTEP = (NW / KQ) * 8;
         const int kk = (warp % KQ) * 4 + (lane & 3);
-        const bool kok = kk < krem;
+        const int x0 = (warp / KQ) * 8 + (lane >> 2);
         const double *gk = G + s_k[kk];
+        const unsigned sd = S + (unsigned)((kk * LD + x0) * 8);
+        if (full) {
 #pragma unroll
-        for (int it = IT0; it < IT1; ++it) {
-            const int x = ((it * NW + warp) / KQ) * 8 + (lane >> 2);
-            cp_async8(S + kk * LD + x, gk + s_x[x], (kok && x < xrem) ? 8 : 0);
+            for (int it = IT0; it < IT1; ++it) cp_async8(sd + it * (XSTEP * 8), gk + s_x[x0 + it * XSTEP]);
+        } else {
+            const bool kok = kk < krem;
+#pragma unroll
+            for (int it = IT0; it < IT1; ++it) {
+                const int x = x0 + it * XSTEP;
+                cp_async8z(sd + it * (XSTEP * 8), gk + s_x[x], (kok && x < xrem) ? 8 : 0);
+            }
         }
     }
 }
@@ -154,6 +175,8 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
     long long *s_am = s_k + KSLOTS * 2 * BK;               // [nterms][BM]
     long long *s_bn = s_am + p.nterms * BM;                // [nterms][BN]
 
+    const unsigned as_base = (unsigned)__cvta_generic_to_shared(As);
+    const unsigned bs_base = (unsigned)__cvta_generic_to_shared(Bs);
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int warp_m = warp % WARPS_M, warp_n = warp / WARPS_M;
@@ -185,7 +208,7 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
     struct TileRef {                 // everything the copies of one k-tile need, resolved once
         const double *A, *B;
         const long long *am, *bn, *ko;
-        double *as, *bs;
+        unsigned as, bs;     // shared-window byte addresses of the destination stage
         int krem;
         bool akf, bkf, valid;
     };
@@ -201,8 +224,8 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
             r.am = s_am + ti * BM;
             r.bn = s_bn + ti * BN;
             r.ko = s_k + (g % KSLOTS) * 2 * BK;
-            r.as = As + st * BK * LDA;
-            r.bs = Bs + st * BK * LDB;
+            r.as = as_base + (unsigned)(st * BK * LDA * 8);
+            r.bs = bs_base + (unsigned)(st * BK * LDB * 8);
             r.krem = t.K - (g - t.kt_begin) * BK;
             r.akf = t.a_kfast != 0;
             r.bkf = t.b_kfast != 0;
@@ -244,6 +267,9 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
 #pragma unroll
         for (int j = 0; j < NTL; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    // The accumulators hold (sum so far) / alpha of the current term, so no operand is ever
+    // scaled in the inner loop: at a term boundary they are rescaled by alpha_old / alpha_new
+    // (terms with alpha == 0 are dropped on the host) and once more by alpha in the epilogue.
     int cur_term = term_of(kt_lo);
     double alpha = p.t[cur_term].alpha;
     int term_end = p.t[cur_term].kt_begin + p.t[cur_term].nkt;
@@ -257,8 +283,18 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
         koffs(g + STAGES);
         if (g >= term_end) {
             cur_term = term_of(g);
+            const double ratio = alpha / p.t[cur_term].alpha;
             alpha = p.t[cur_term].alpha;
             term_end = p.t[cur_term].kt_begin + p.t[cur_term].nkt;
+            if (ratio != 1.0) {
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < NTL; ++j) {
+                        acc[i][j][0] *= ratio;
+                        acc[i][j][1] *= ratio;
+                    }
+            }
         }
         const int st = (g - kt_lo) % STAGES;
         const double *a = As + st * BK * LDA + warp_m * WM + (lane >> 2);
@@ -268,7 +304,7 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
             const int row = ks * 4 + (lane & 3);
             double af[MT], bf[NTL];
 #pragma unroll
-            for (int i = 0; i < MT; ++i) af[i] = a[row * LDA + i * 8] * alpha;
+            for (int i = 0; i < MT; ++i) af[i] = a[row * LDA + i * 8];
 #pragma unroll
             for (int j = 0; j < NTL; ++j) bf[j] = b[row * LDB + j * 8];
             if (INTERLEAVE) issue_part(nxt, part);   // overlaps the fragment-load latency
@@ -282,6 +318,15 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
         substep(IntC<2>{});
         substep(IntC<3>{});
         if (INTERLEAVE) cp_async_commit();
+    }
+    if (alpha != 1.0) {
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NTL; ++j) {
+                acc[i][j][0] *= alpha;
+                acc[i][j][1] *= alpha;
+            }
     }
     cp_async_wait<0>();
 
@@ -438,10 +483,13 @@ static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
     p.C = d->C;
     p.beta = d->beta;
     int kt = 0;
+    int nkeep = 0;
     for (int ti = 0; ti < d->nterms; ++ti) {
         const pmb_term_t &s = d->terms[ti];
-        TermDev &t = p.t[ti];
         if (!s.A || !s.B || s.nk < 0 || s.nk > PMB_MAX_DIMS) return PMB_E_BADARG;
+        // a zero coefficient contributes nothing; keep one such term only if nothing else is left
+        if (s.alpha == 0.0 && !(ti == d->nterms - 1 && nkeep == 0)) continue;
+        TermDev &t = p.t[nkeep++];
         int64_t K;
         if (!prod_fits(s.k_ext, s.nk, &K)) return PMB_E_BADARG;
         t.A = s.A;
@@ -471,6 +519,7 @@ static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
         t.nkt = (t.K + BK - 1) / BK;
         kt += t.nkt;
     }
+    p.nterms = nkeep;
     p.total_ktiles = kt;
     cfg = choose_cfg(M, N);
     p.tiles_m = (int)((M + kCfg[cfg].bm - 1) / kCfg[cfg].bm);

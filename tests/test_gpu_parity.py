@@ -178,7 +178,7 @@ def test_contract_k_windows(cfg):
     V, T = rng.standard_normal((nv,) * 4), rng.standard_normal((nv, nv, no, no))
     Xa, Xb = rng.standard_normal((nv, nv, no, no)), rng.standard_normal((no, no, no, no))
     ref = np.einsum("abcd,cdij->abij", V, T, optimize=True) - 0.5 * np.einsum("abkl,klij->abij", Xa, Xb, optimize=True)
-    lib.pmb_contract_set_tuning(cfg, 0)
+    lib.pmb_contract_set_tuning(cfg, 1)              # no split-K: windows apply to unsplit launches
     lib.pmb_contract_set_panel_bytes(1)
     try:
         before = bk.launch_count()
