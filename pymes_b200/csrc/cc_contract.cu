@@ -76,8 +76,7 @@ __device__ __forceinline__ long long decomp(int idx, int nd, const int *ext,
 }
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
-    asm volatile(
-        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
         : "+d"(c[0]), "+d"(c[1])
         : "d"(a), "d"(b));
 }
@@ -94,65 +93,58 @@ __device__ __forceinline__ void cp_async8z(unsigned smem_addr, const double *gsr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// Issue the asynchronous gather of one [BK][BX] operand tile into shared memory.
-//   x-fast: consecutive threads walk x (the operand is unit-stride along m/n)
-//   k-fast: every 4 lanes read 4 consecutive k (one 32 B sector), 8 x per warp
-// s_x: per-row element offsets of this term (0 for rows outside the tensor),
-// s_k: per-k element offsets of this k-tile (0 beyond K).
-// The copies of one tile are issued in NPARTS slices (PART = 0..NPARTS-1) so that the
-// main loop can interleave them with its DMMA sub-steps.  In both mappings the shared
-// destination of copy `it` is (thread base) + it * (compile-time constant); interior tiles
-// (xrem >= BX, krem >= BK) take the unpredicated path.
-template <int BX, int NT, int PART, int NPARTS>
-__device__ __forceinline__ void gather_tile(unsigned S, const double *__restrict__ G,
-                                            const long long *s_x, const long long *s_k, int xrem,
-                                            int krem, bool kfast, int tid) {
-    constexpr int PER = BX * BK / NT;
+// Per-thread description of the asynchronous gather of one [BK][BX] operand tile.
+// Two thread->element mappings exist, chosen per operand by its unit-stride direction:
+//   x-fast: consecutive threads walk x (the operand is unit-stride along m/n); a thread
+//           keeps x and steps k by NT/BX per copy,
+//   k-fast: every 4 lanes read 4 consecutive k (one 32 B sector), 8 x per warp; a thread
+//           keeps k and steps x per copy.
+// Both reduce to the same straight-line code: address = base + tab[it * tstep], shared
+// destination = sdst + it * dstep, so the k-tile loop has no mapping- or edge-dependent
+// branches and ptxas can place the copies in the issue shadow of the DMMAs.
+// Rows/columns outside the tensor have table offset 0: they read valid memory and only feed
+// accumulator rows/columns that are never stored.  Only k >= K must be zero-filled
+// (src-size 0), which also turns the copies of tiles beyond the k range into no-ops.
+struct Gat {
+    const double *base;     // operand + fixed part of the offset
+    const long long *tab;   // varying part (shared): tab[it * tstep]
+    unsigned sdst;          // shared-window byte address of copy 0
+    int tstep, dstep;       // per-copy increments (table elements, shared bytes)
+    int k0, kinc;           // k index of copy `it` is k0 + it * kinc
+};
+
+template <int BX, int NT>
+__device__ __forceinline__ Gat make_gat(unsigned S, const double *__restrict__ G, const long long *s_x,
+                                        const long long *s_k, bool kfast, int tid) {
     constexpr int LD = BX + SPAD;
-    static_assert(PER % NPARTS == 0, "tile copies must split evenly");
-    constexpr int IT0 = PART * (PER / NPARTS), IT1 = IT0 + PER / NPARTS;
-    const bool full = xrem >= BX && krem >= BK;
-    if (!kfast) {
-        constexpr int KSTEP = NT / BX;
-        const int x = tid % BX;
-        const int kb = tid / BX;
-        const double *gx = G + s_x[x];
-        const unsigned sd = S + (unsigned)((kb * LD + x) * 8);
-        if (full) {
+    constexpr int KSTEP = NT / BX;
+    constexpr int KQ = BK / 4, NW = NT / 32;
+    static_assert(NW % KQ == 0, "warps must tile the k quads");
+    constexpr int XSTEP = (NW / KQ) * 8;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int x = kfast ? (warp / KQ) * 8 + (lane >> 2) : tid % BX;
+    const int k = kfast ? (warp % KQ) * 4 + (lane & 3) : tid / BX;
+    const long long *fixed = kfast ? s_k + k : s_x + x;
+    Gat g;
+    g.base = G + *fixed;
+    g.tab = kfast ? s_x + x : s_k + k;
+    g.tstep = kfast ? XSTEP : KSTEP;
+    g.sdst = S + (unsigned)((k * LD + x) * 8);
+    g.dstep = kfast ? XSTEP * 8 : KSTEP * LD * 8;
+    g.k0 = k;
+    g.kinc = kfast ? 0 : KSTEP;
+    return g;
+}
+
+template <int IT0, int IT1>
+__device__ __forceinline__ void gat_issue(const Gat &g, int krem) {
 #pragma unroll
-            for (int it = IT0; it < IT1; ++it) cp_async8(sd + it * (KSTEP * LD * 8), gx + s_k[it * KSTEP + kb]);
-        } else {
-            const bool xok = x < xrem;
-#pragma unroll
-            for (int it = IT0; it < IT1; ++it) {
-                const int kk = it * KSTEP + kb;
-                cp_async8z(sd + it * (KSTEP * LD * 8), gx + s_k[kk], (xok && kk < krem) ? 8 : 0);
-            }
-        }
-    } else {
-        const int lane = tid & 31, warp = tid >> 5;
-        constexpr int KQ = BK / 4;
-        constexpr int NW = NT / 32;
-        static_assert(NW % KQ == 0, "warps must tile the k quads");
-        constexpr int XSTEP = (NW / KQ) * 8;
-        const int kk = (warp % KQ) * 4 + (lane & 3);
-        const int x0 = (warp / KQ) * 8 + (lane >> 2);
-        const double *gk = G + s_k[kk];
-        const unsigned sd = S + (unsigned)((kk * LD + x0) * 8);
-        if (full) {
-#pragma unroll
-            for (int it = IT0; it < IT1; ++it) cp_async8(sd + it * (XSTEP * 8), gk + s_x[x0 + it * XSTEP]);
-        } else {
-            const bool kok = kk < krem;
-#pragma unroll
-            for (int it = IT0; it < IT1; ++it) {
-                const int x = x0 + it * XSTEP;
-                cp_async8z(sd + it * (XSTEP * 8), gk + s_x[x], (kok && x < xrem) ? 8 : 0);
-            }
-        }
+    for (int it = IT0; it < IT1; ++it) {
+        const long long off = g.tab[it * g.tstep];
+        cp_async8z(g.sdst + (unsigned)(it * g.dstep), g.base + off, (g.k0 + it * g.kinc < krem) ? 8 : 0);
     }
 }
 
@@ -163,16 +155,19 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
     constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
     constexpr int MT = WM / 8, NTL = WN / 8;
     constexpr int LDA = BM + SPAD, LDB = BN + SPAD;
-    constexpr int KSLOTS = STAGES + 1;
+    constexpr int TPB = NT / (2 * BK);   // k-offset tiles produced per batch (one warp each)
+    constexpr int KRING = 2 * TPB;       // ring of k-offset tiles
+    constexpr int PER_A = BM * BK / NT, PER_B = BN * BK / NT;
+    constexpr int NPARTS = BK / 4;       // one slice of the next tile's copies per DMMA sub-step
     static_assert(NT % BM == 0 && NT % BN == 0, "x-fast mapping needs NT % BX == 0");
-    static_assert((BM * BK) % NT == 0 && (BN * BK) % NT == 0, "tile/threads");
-    static_assert(NT >= 2 * BK, "k-offset producers");
+    static_assert(PER_A % NPARTS == 0 && PER_B % NPARTS == 0, "tile copies must split evenly");
+    static_assert(TPB >= STAGES && (KRING & (KRING - 1)) == 0, "k-offset ring");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *As = reinterpret_cast<double *>(smem_raw);    // [STAGES][BK][LDA]
     double *Bs = As + STAGES * BK * LDA;                   // [STAGES][BK][LDB]
-    long long *s_k = reinterpret_cast<long long *>(Bs + STAGES * BK * LDB);  // [KSLOTS][2][BK]
-    long long *s_am = s_k + KSLOTS * 2 * BK;               // [nterms][BM]
+    long long *s_k = reinterpret_cast<long long *>(Bs + STAGES * BK * LDB);  // [KRING][2][BK]
+    long long *s_am = s_k + KRING * 2 * BK;                // [nterms][BM]
     long long *s_bn = s_am + p.nterms * BM;                // [nterms][BN]
 
     const unsigned as_base = (unsigned)__cvta_generic_to_shared(As);
@@ -192,60 +187,36 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
         while (ti + 1 < p.nterms && g >= p.t[ti + 1].kt_begin) ++ti;
         return ti;
     };
-    // element offsets of the BK contracted indices of k-tile g, both operands
+    // Element offsets of the BK contracted indices of k-tile g, both operands: one warp per
+    // tile (lanes 0-15 operand A, 16-31 operand B).  Every warp of the CTA produces one tile
+    // of a batch, so no warp falls behind the others at the k-tile barrier.
     auto koffs = [&](int g) {
-        if (tid < 2 * BK && g < kt_hi) {
+        if (g < kt_hi) {
             const TermDev &t = p.t[term_of(g)];
-            const int kk = tid & (BK - 1);
+            const int kk = lane & (BK - 1);
             const int k = (g - t.kt_begin) * BK + kk;
-            const bool isb = tid >= BK;
             long long off = 0;
-            if (k < t.K) off = decomp(k, t.nk, t.k_ext, isb ? t.b_kstr : t.a_kstr);
-            s_k[(g % KSLOTS) * 2 * BK + tid] = off;
+            if (k < t.K) off = decomp(k, t.nk, t.k_ext, lane >= BK ? t.b_kstr : t.a_kstr);
+            s_k[(g & (KRING - 1)) * 2 * BK + lane] = off;
         }
     };
-    constexpr int NPARTS = BK / 4;   // one slice of the next tile's copies per DMMA sub-step
-    struct TileRef {                 // everything the copies of one k-tile need, resolved once
-        const double *A, *B;
-        const long long *am, *bn, *ko;
-        unsigned as, bs;     // shared-window byte addresses of the destination stage
+    struct TileGat {
+        Gat a, b;
         int krem;
-        bool akf, bkf, valid;
     };
-    auto tile_ref = [&](int g) {
-        TileRef r;
-        r.valid = g < kt_hi;
-        if (r.valid) {
-            const int ti = term_of(g);
-            const TermDev &t = p.t[ti];
-            const int st = (g - kt_lo) % STAGES;
-            r.A = t.A;
-            r.B = t.B;
-            r.am = s_am + ti * BM;
-            r.bn = s_bn + ti * BN;
-            r.ko = s_k + (g % KSLOTS) * 2 * BK;
-            r.as = as_base + (unsigned)(st * BK * LDA * 8);
-            r.bs = bs_base + (unsigned)(st * BK * LDB * 8);
-            r.krem = t.K - (g - t.kt_begin) * BK;
-            r.akf = t.a_kfast != 0;
-            r.bkf = t.b_kfast != 0;
-        }
+    // gather descriptors of k-tile g into pipeline stage st; tiles beyond the range become
+    // zero-fill no-ops (krem = 0)
+    auto tile_gat = [&](int g, int st) {
+        const int ti = term_of(g < kt_hi ? g : kt_lo);
+        const TermDev &t = p.t[ti];
+        const long long *ko = s_k + (g & (KRING - 1)) * 2 * BK;
+        TileGat r;
+        r.a = make_gat<BM, NT>(as_base + (unsigned)(st * BK * LDA * 8), t.A, s_am + ti * BM, ko,
+                               t.a_kfast != 0, tid);
+        r.b = make_gat<BN, NT>(bs_base + (unsigned)(st * BK * LDB * 8), t.B, s_bn + ti * BN, ko + BK,
+                               t.b_kfast != 0, tid);
+        r.krem = g < kt_hi ? t.K - (g - t.kt_begin) * BK : 0;
         return r;
-    };
-    auto issue_part = [&](const TileRef &r, auto part) {
-        constexpr int PART = decltype(part)::value;
-        if (r.valid) {
-            gather_tile<BM, NT, PART, NPARTS>(r.as, r.A, r.am, r.ko, mrem, r.krem, r.akf, tid);
-            gather_tile<BN, NT, PART, NPARTS>(r.bs, r.B, r.bn, r.ko + BK, nrem, r.krem, r.bkf, tid);
-        }
-    };
-    auto issue = [&](int g) {
-        const TileRef r = tile_ref(g);
-        if (r.valid) {
-            gather_tile<BM, NT, 0, 1>(r.as, r.A, r.am, r.ko, mrem, r.krem, r.akf, tid);
-            gather_tile<BN, NT, 0, 1>(r.bs, r.B, r.bn, r.ko + BK, nrem, r.krem, r.bkf, tid);
-        }
-        cp_async_commit();
     };
 
     for (int ti = 0; ti < p.nterms; ++ti) {
@@ -255,11 +226,15 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
         for (int i = tid; i < BN; i += NT)
             s_bn[ti * BN + i] = (i < nrem) ? decomp(n0 + i, p.nn, p.n_ext, t.b_nstr) : 0;
     }
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) koffs(kt_lo + s);
+    if (warp < STAGES) koffs(kt_lo + warp);
     __syncthreads();
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) issue(kt_lo + s);
+    for (int s = 0; s < STAGES - 1; ++s) {
+        const TileGat r = tile_gat(kt_lo + s, s);
+        gat_issue<0, PER_A>(r.a, r.krem);
+        gat_issue<0, PER_B>(r.b, r.krem);
+        cp_async_commit();
+    }
 
     double acc[MT][NTL][2];
 #pragma unroll
@@ -273,14 +248,20 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
     int cur_term = term_of(kt_lo);
     double alpha = p.t[cur_term].alpha;
     int term_end = p.t[cur_term].kt_begin + p.t[cur_term].nkt;
+    int st = 0;                    // pipeline stage of tile g
+    int st_next = STAGES - 1;      // stage that tile g + STAGES - 1 goes to
+    int batch = 0;                 // position of g in the current k-offset batch
     for (int g = kt_lo; g < kt_hi; ++g) {
         cp_async_wait<STAGES - 2>();   // tile g has landed (this thread's copies)
         __syncthreads();               // ... everyone's; stage (g-1) is free again
-        TileRef nxt;
-        nxt.valid = false;
-        if (INTERLEAVE) nxt = tile_ref(g + STAGES - 1);
-        else issue(g + STAGES - 1);
-        koffs(g + STAGES);
+        if (batch == 0) koffs(g + STAGES + warp);
+        batch = batch + 1 == TPB ? 0 : batch + 1;
+        const TileGat nxt = tile_gat(g + STAGES - 1, st_next);
+        if (!INTERLEAVE) {
+            gat_issue<0, PER_A>(nxt.a, nxt.krem);
+            gat_issue<0, PER_B>(nxt.b, nxt.krem);
+            cp_async_commit();
+        }
         if (g >= term_end) {
             cur_term = term_of(g);
             const double ratio = alpha / p.t[cur_term].alpha;
@@ -296,18 +277,19 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
                     }
             }
         }
-        const int st = (g - kt_lo) % STAGES;
-        const double *a = As + st * BK * LDA + warp_m * WM + (lane >> 2);
-        const double *b = Bs + st * BK * LDB + warp_n * WN + (lane >> 2);
+        const double *a = As + st * BK * LDA + warp_m * WM + (lane >> 2) + (lane & 3) * LDA;
+        const double *b = Bs + st * BK * LDB + warp_n * WN + (lane >> 2) + (lane & 3) * LDB;
         auto substep = [&](auto part) {
             constexpr int ks = decltype(part)::value;
-            const int row = ks * 4 + (lane & 3);
             double af[MT], bf[NTL];
 #pragma unroll
-            for (int i = 0; i < MT; ++i) af[i] = a[row * LDA + i * 8];
+            for (int i = 0; i < MT; ++i) af[i] = a[ks * 4 * LDA + i * 8];
 #pragma unroll
-            for (int j = 0; j < NTL; ++j) bf[j] = b[row * LDB + j * 8];
-            if (INTERLEAVE) issue_part(nxt, part);   // overlaps the fragment-load latency
+            for (int j = 0; j < NTL; ++j) bf[j] = b[ks * 4 * LDB + j * 8];
+            if (INTERLEAVE) {
+                gat_issue<ks *(PER_A / NPARTS), (ks + 1) * (PER_A / NPARTS)>(nxt.a, nxt.krem);
+                gat_issue<ks *(PER_B / NPARTS), (ks + 1) * (PER_B / NPARTS)>(nxt.b, nxt.krem);
+            }
 #pragma unroll
             for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -318,6 +300,8 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
         substep(IntC<2>{});
         substep(IntC<3>{});
         if (INTERLEAVE) cp_async_commit();
+        st = st + 1 == STAGES ? 0 : st + 1;
+        st_next = st_next + 1 == STAGES ? 0 : st_next + 1;
     }
     if (alpha != 1.0) {
 #pragma unroll
@@ -407,20 +391,20 @@ static int g_force_cfg = -1;
 static int g_force_split = 0;
 static long long g_panel_bytes = 40LL << 20;   // L2 budget for one operand window (0 = off)
 
-template <int BM, int BN, int STAGES>
+template <int BM, int BN, int STAGES, int NT>
 constexpr size_t smem_bytes(int nterms) {
     return sizeof(double) * STAGES * BK * (BM + SPAD + BN + SPAD) +
-           sizeof(long long) * ((size_t)nterms * (BM + BN) + (STAGES + 1) * 2 * BK);
+           sizeof(long long) * ((size_t)nterms * (BM + BN) + 2 * (NT / (2 * BK)) * 2 * BK);
 }
 
 template <int BM, int BN, int WMW, int WNW, int STAGES, int MINB, bool IL>
 static int launch_one(const Params &p, dim3 grid, cudaStream_t s) {
     auto kern = contract_kernel<BM, BN, WMW, WNW, STAGES, MINB, IL>;
-    const size_t sm = smem_bytes<BM, BN, STAGES>(p.nterms);
+    const size_t sm = smem_bytes<BM, BN, STAGES, WMW * WNW * 32>(p.nterms);
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem_bytes<BM, BN, STAGES>(PMB_MAX_TERMS));
+                                             (int)smem_bytes<BM, BN, STAGES, WMW * WNW * 32>(PMB_MAX_TERMS));
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
