@@ -102,7 +102,9 @@ int pmb_contract(const pmb_contract_t *d, void *ws, size_t ws_bytes,
 void pmb_contract_set_tuning(int tile_config, int split_k);
 /* L2 budget (bytes) for one operand's k window; contractions whose smaller      */
 /* operand exceeds it are issued as a fixed-order sequence of k-window launches */
-/* accumulating in C.  0 disables the windows.  Default 40 MiB.                  */
+/* accumulating in C.  0 disables the windows, a negative value restores the     */
+/* defaults (40 MiB for the single-role tile kernels, off for the               */
+/* warp-specialised kernel).                                                    */
 void pmb_contract_set_panel_bytes(long long bytes);
 
 /* ------------------------------------------------------------------------ */

@@ -147,6 +147,80 @@ __device__ __forceinline__ void gat_issue(const Gat &g, int krem) {
         cp_async8z(g.sdst + (unsigned)(it * g.dstep), g.base + off, (g.k0 + it * g.kinc < krem) ? 8 : 0);
     }
 }
+// same, with the table look-ups of CHUNK copies issued back to back before the copies that
+// depend on them (the dedicated producer warps have the registers for it)
+template <int PER, int CHUNK>
+__device__ __forceinline__ void gat_issue_batched(const Gat &g, int krem) {
+    static_assert(PER % CHUNK == 0, "copies must split into whole chunks");
+#pragma unroll
+    for (int c0 = 0; c0 < PER; c0 += CHUNK) {
+        long long off[CHUNK];
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) off[j] = g.tab[(c0 + j) * g.tstep];
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) {
+            const int it = c0 + j;
+            cp_async8z(g.sdst + (unsigned)(it * g.dstep), g.base + off[j], (g.k0 + it * g.kinc < krem) ? 8 : 0);
+        }
+    }
+}
+
+// Epilogue shared by both kernels.  DMMA C fragment: row = lane/4, cols = 2*(lane%4) + {0,1}.
+// `row0` / `col0` are this lane's first row / column inside the CTA tile.  With beta != 0 the
+// old values of one fragment row (2*NTL elements) are all loaded before anything is stored:
+// the loads are independent, so one row costs one memory round trip instead of 2*NTL
+// dependent read-modify-write chains (k-window launches pay this once per window).
+template <int MT, int NTL>
+__device__ __forceinline__ void store_tile(const Params &p, double (&acc)[MT][NTL][2], const long long *s_cm,
+                                           const long long *s_cn, int row0, int col0, int mrem, int nrem) {
+    const bool rd = p.beta != 0.0;
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const int ml = row0 + i * 8;
+        if (ml >= mrem) continue;
+        double *crow = p.C + s_cm[ml];
+        if (rd) {
+            double old[NTL][2];
+#pragma unroll
+            for (int j = 0; j < NTL; ++j)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int nl = col0 + j * 8 + c;
+                    old[j][c] = nl < nrem ? crow[s_cn[nl]] : 0.0;
+                }
+#pragma unroll
+            for (int j = 0; j < NTL; ++j)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) acc[i][j][c] += p.beta * old[j][c];
+        }
+#pragma unroll
+        for (int j = 0; j < NTL; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int nl = col0 + j * 8 + c;
+                if (nl < nrem) crow[s_cn[nl]] = acc[i][j][c];
+            }
+    }
+}
+
+// split-K partial sums: plain row-major [split][M][N] workspace
+template <int MT, int NTL>
+__device__ __forceinline__ void store_partial(const Params &p, const double (&acc)[MT][NTL][2], int m0, int n0,
+                                              int row0, int col0, int mrem, int nrem) {
+    double *ws = p.ws + (size_t)blockIdx.y * (size_t)p.M * (size_t)p.N;
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const int ml = row0 + i * 8;
+        if (ml >= mrem) continue;
+        double *row = ws + (size_t)(m0 + ml) * (size_t)p.N + n0;
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) {
+            const int nl = col0 + j * 8;
+            if (nl < nrem) row[nl] = acc[i][j][0];
+            if (nl + 1 < nrem) row[nl + 1] = acc[i][j][1];
+        }
+    }
+}
 
 template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, int MINB, bool INTERLEAVE>
 __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
@@ -315,21 +389,9 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
     cp_async_wait<0>();
 
     // ---- epilogue -------------------------------------------------------
-    // DMMA C fragment: row = lane/4, cols = 2*(lane%4) + {0,1}
+    const int row0 = warp_m * WM + (lane >> 2), col0 = warp_n * WN + (lane & 3) * 2;
     if (p.nsplit > 1) {
-        double *ws = p.ws + (size_t)blockIdx.y * (size_t)p.M * (size_t)p.N;
-#pragma unroll
-        for (int i = 0; i < MT; ++i) {
-            const int ml = warp_m * WM + i * 8 + (lane >> 2);
-            if (ml >= mrem) continue;
-            double *row = ws + (size_t)(m0 + ml) * (size_t)p.N + n0;
-#pragma unroll
-            for (int j = 0; j < NTL; ++j) {
-                const int nl = warp_n * WN + j * 8 + (lane & 3) * 2;
-                if (nl < nrem) row[nl] = acc[i][j][0];
-                if (nl + 1 < nrem) row[nl + 1] = acc[i][j][1];
-            }
-        }
+        store_partial<MT, NTL>(p, acc, m0, n0, row0, col0, mrem, nrem);
         return;
     }
     __syncthreads();
@@ -338,26 +400,287 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
     for (int i = tid; i < BN; i += NT)
         s_bn[i] = (i < nrem) ? decomp(n0 + i, p.nn, p.n_ext, p.c_nstr) : 0;
     __syncthreads();
-    const bool rd = p.beta != 0.0;
+    store_tile<MT, NTL>(p, acc, s_am, s_bn, row0, col0, mrem, nrem);
+}
+
+// ---------------------------------------------------------------------------
+// Warp-specialised variant (the large-shape path).
+//
+// tools/micro/dmma_issue.cu shows that 8 warps running nothing but the fragment LDS + DMMA
+// sub-steps reach 99 % of the FP64 tensor peak, while contract_kernel above sits at ~70 %:
+// its warps spend issue time on offset tables, 64-bit gather addresses and LDGSTS between
+// the DMMA bursts, and meet at a CTA-wide barrier every k-tile.  Here the two jobs are
+// separate warps that only talk through shared-memory mbarriers:
+//   * producer warps (one warpgroup, 128 threads, 72 registers) own the k-offset tables,
+//     the gather descriptors and the cp.async copies; a stage is published with
+//     cp.async.mbarrier.arrive.noinc on full[stage] (the barrier completes when the copies
+//     of all 128 threads have landed);
+//   * consumer warps (WARPS_M x WARPS_N, 208 registers) wait on full[stage], run the four
+//     LDS + DMMA sub-steps and release the stage with one arrive per warp on empty[stage].
+// There is no __syncthreads in the k loop and the consumers' instruction stream is the
+// microbenchmark's.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// one non-blocking test of the phase (no "memory" clobber: the caller orders its loads)
+__device__ __forceinline__ unsigned mbar_probe(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity));
+    return ok;
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(bar) : "memory");
+}
+// arrive on `bar` once every cp.async issued so far by this thread has completed
+__device__ __forceinline__ void cp_async_arrive(unsigned bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+
+constexpr int kWsProducerThreads = 128;
+constexpr int kWsKRing = 16;     // k-offset tiles kept in shared memory (4 batches of 4)
+
+template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES>
+__global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
+    contract_ws_kernel(const __grid_constant__ Params p) {
+    constexpr int NC = WARPS_M * WARPS_N * 32;     // consumer threads
+    constexpr int NP = kWsProducerThreads;
+    constexpr int NCW = NC / 32;
+    constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
+    constexpr int MT = WM / 8, NTL = WN / 8;
+    constexpr int LDA = BM + SPAD, LDB = BN + SPAD;
+    constexpr int TPB = NP / 32;                   // k-offset tiles per batch, one warp each
+    constexpr int KRING = kWsKRing;
+    constexpr int PER_A = BM * BK / NP, PER_B = BN * BK / NP;
+    static_assert(NC % 128 == 0, "setmaxnreg works on whole warpgroups");
+    static_assert(NP % BM == 0 && NP % BN == 0, "x-fast mapping needs NP % BX == 0");
+    static_assert(KRING == 4 * TPB, "ring must hold four batches (see the hazard note below)");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);   // full[S], empty[S]
+    double *As = reinterpret_cast<double *>(smem_raw + 128);   // [STAGES][BK][LDA]
+    double *Bs = As + STAGES * BK * LDA;                        // [STAGES][BK][LDB]
+    long long *s_k = reinterpret_cast<long long *>(Bs + STAGES * BK * LDB);  // [KRING][2][BK]
+    long long *s_cm = s_k + KRING * 2 * BK;                     // [BM]  C row offsets
+    long long *s_cn = s_cm + BM;                                // [BN]  C column offsets
+    long long *s_am = s_cn + BN;                                // [nterms][BM]
+    long long *s_bn = s_am + p.nterms * BM;                     // [nterms][BN]
+
+    const unsigned bar_base = (unsigned)__cvta_generic_to_shared(bars);
+    const unsigned as_base = (unsigned)__cvta_generic_to_shared(As);
+    const unsigned bs_base = (unsigned)__cvta_generic_to_shared(Bs);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int tile_n = blockIdx.x % p.tiles_n, tile_m = blockIdx.x / p.tiles_n;
+    const int m0 = tile_m * BM, n0 = tile_n * BN;
+    const int mrem = p.M - m0, nrem = p.N - n0;
+    const int kt_lo = p.kt_base + blockIdx.y * p.ktiles_per_split;
+    const int kt_hi = min(kt_lo + p.ktiles_per_split, p.kt_limit);
+
+    auto term_of = [&](int g) {
+        int ti = 0;
+        while (ti + 1 < p.nterms && g >= p.t[ti + 1].kt_begin) ++ti;
+        return ti;
+    };
+
+    // ---- common prologue: offset tables of this output tile, barriers ----
+    for (int ti = 0; ti < p.nterms; ++ti) {
+        const TermDev &t = p.t[ti];
+        for (int i = tid; i < BM; i += NC + NP)
+            s_am[ti * BM + i] = (i < mrem) ? decomp(m0 + i, p.nm, p.m_ext, t.a_mstr) : 0;
+        for (int i = tid; i < BN; i += NC + NP)
+            s_bn[ti * BN + i] = (i < nrem) ? decomp(n0 + i, p.nn, p.n_ext, t.b_nstr) : 0;
+    }
+    for (int i = tid; i < BM; i += NC + NP)
+        s_cm[i] = (i < mrem) ? decomp(m0 + i, p.nm, p.m_ext, p.c_mstr) : 0;
+    for (int i = tid; i < BN; i += NC + NP)
+        s_cn[i] = (i < nrem) ? decomp(n0 + i, p.nn, p.n_ext, p.c_nstr) : 0;
+    if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < MT; ++i) {
-        const int ml = warp_m * WM + i * 8 + (lane >> 2);
-        if (ml >= mrem) continue;
-        double *crow = p.C + s_am[ml];
-#pragma unroll
-        for (int j = 0; j < NTL; ++j) {
-            const int nl = warp_n * WN + j * 8 + (lane & 3) * 2;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                if (nl + c < nrem) {
-                    double *dst = crow + s_bn[nl + c];
-                    double v = acc[i][j][c];
-                    if (rd) v += p.beta * (*dst);
-                    *dst = v;
-                }
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_base + s * 8, NP);                    // full[s]: every producer thread
+            mbar_init(bar_base + (STAGES + s) * 8, NCW);        // empty[s]: every consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= NCW) {
+        // =========================== producers ===========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
+        const int ptid = tid - NC, pwarp = warp - NCW;
+        // Element offsets of the BK contracted indices of k-tile g (lanes 0-15 operand A,
+        // 16-31 operand B), ring slot (g - kt_lo) mod KRING.  Batch b+1 (four tiles) is
+        // written just before the producer barrier that opens batch b and is first read after
+        // the barrier that opens batch b+1; the slots it overwrites belonged to batch b-3,
+        // which every producer had finished when this warp passed the barrier of batch b-1.
+        auto koffs = [&](int g) {
+            if (g < kt_hi) {
+                const TermDev &t = p.t[term_of(g)];
+                const int kk = lane & (BK - 1);
+                const int k = (g - t.kt_begin) * BK + kk;
+                long long off = 0;
+                if (k < t.K) off = decomp(k, t.nk, t.k_ext, lane >= BK ? t.b_kstr : t.a_kstr);
+                s_k[((g - kt_lo) & (KRING - 1)) * 2 * BK + lane] = off;
+            }
+        };
+        koffs(kt_lo + pwarp);
+        int st = 0, batch = 0;
+        unsigned empty_parity = 1;     // first pass over the ring: the stages are free
+        for (int g = kt_lo; g < kt_hi; ++g) {
+            if (batch == 0) {
+                koffs(g + TPB + pwarp);
+                producer_sync();
+            }
+            batch = batch + 1 == TPB ? 0 : batch + 1;
+            mbar_wait(bar_base + (STAGES + st) * 8, empty_parity);
+            const int ti = term_of(g);
+            const TermDev &t = p.t[ti];
+            const long long *ko = s_k + ((g - kt_lo) & (KRING - 1)) * 2 * BK;
+            const int krem = t.K - (g - t.kt_begin) * BK;
+            const Gat ga = make_gat<BM, NP>(as_base + (unsigned)(st * BK * LDA * 8), t.A, s_am + ti * BM, ko,
+                                            t.a_kfast != 0, ptid);
+            const Gat gb = make_gat<BN, NP>(bs_base + (unsigned)(st * BK * LDB * 8), t.B, s_bn + ti * BN,
+                                            ko + BK, t.b_kfast != 0, ptid);
+            gat_issue_batched<PER_A, 8>(ga, krem);
+            gat_issue_batched<PER_B, 8>(gb, krem);
+            cp_async_arrive(bar_base + st * 8);
+            if (++st == STAGES) {
+                st = 0;
+                empty_parity ^= 1;
             }
         }
+        cp_async_wait<0>();
+        return;
     }
+
+    // ============================= consumers =============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;\n");
+    const int warp_m = warp % WARPS_M, warp_n = warp / WARPS_M;
+    double acc[MT][NTL][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // accumulators hold (sum so far) / alpha of the current term (see contract_kernel)
+    int cur_term = term_of(kt_lo);
+    double alpha = p.t[cur_term].alpha;
+    int term_end = p.t[cur_term].kt_begin + p.t[cur_term].nkt;
+    int st = 0;
+    unsigned full_parity = 0;
+    const double *a0 = As + warp_m * WM + (lane >> 2) + (lane & 3) * LDA;
+    const double *b0 = Bs + warp_n * WN + (lane >> 2) + (lane & 3) * LDB;
+    // number of 8-row / 8-column fragments of this warp's tile that intersect C
+    const int mact = max(0, min(MT, (mrem - warp_m * WM + 7) >> 3));
+    const int nact = max(0, min(NTL, (nrem - warp_n * WN + 7) >> 3));
+    const bool interior = mact == MT && nact == NTL;
+    auto substep_full = [&](const double *a, const double *b, auto part) {
+        constexpr int ks = decltype(part)::value;
+        double af[MT], bf[NTL];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) af[i] = a[ks * 4 * LDA + i * 8];
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) bf[j] = b[ks * 4 * LDB + j * 8];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NTL; ++j) dmma(acc[i][j], af[i], bf[j]);
+    };
+    // ragged tile: 8x8 fragments that lie entirely outside C are skipped (warp-uniform)
+    auto substep_edge = [&](const double *a, const double *b, auto part) {
+        constexpr int ks = decltype(part)::value;
+        double af[MT], bf[NTL];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) af[i] = i < mact ? a[ks * 4 * LDA + i * 8] : 0.0;
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) bf[j] = j < nact ? b[ks * 4 * LDB + j * 8] : 0.0;
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NTL; ++j)
+                if (i < mact && j < nact) dmma(acc[i][j], af[i], bf[j]);
+    };
+    unsigned ready = 0;
+    for (int g = kt_lo; g < kt_hi; ++g) {
+        if (g >= term_end) {
+            cur_term = term_of(g);
+            const double ratio = alpha / p.t[cur_term].alpha;
+            alpha = p.t[cur_term].alpha;
+            term_end = p.t[cur_term].kt_begin + p.t[cur_term].nkt;
+            if (ratio != 1.0) {
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < NTL; ++j) {
+                        acc[i][j][0] *= ratio;
+                        acc[i][j][1] *= ratio;
+                    }
+            }
+        }
+        if (!ready) mbar_wait(bar_base + st * 8, full_parity);
+        asm volatile("" ::: "memory");
+        const double *a = a0 + st * BK * LDA;
+        const double *b = b0 + st * BK * LDB;
+        // The barrier of the next stage is probed while the last sub-step still has DMMAs to
+        // issue, so the round trip of the try_wait is hidden; a failed probe falls back to the
+        // spinning wait at the top of the next iteration.
+        const int nst = st + 1 == STAGES ? 0 : st + 1;
+        const unsigned npar = nst == 0 ? full_parity ^ 1u : full_parity;
+        if (interior) {
+            substep_full(a, b, IntC<0>{});
+            substep_full(a, b, IntC<1>{});
+            substep_full(a, b, IntC<2>{});
+            ready = mbar_probe(bar_base + nst * 8, npar);
+            substep_full(a, b, IntC<3>{});
+        } else {
+            substep_edge(a, b, IntC<0>{});
+            substep_edge(a, b, IntC<1>{});
+            substep_edge(a, b, IntC<2>{});
+            ready = mbar_probe(bar_base + nst * 8, npar);
+            substep_edge(a, b, IntC<3>{});
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_base + (STAGES + st) * 8);
+        if (++st == STAGES) {
+            st = 0;
+            full_parity ^= 1;
+        }
+    }
+    if (alpha != 1.0) {
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NTL; ++j) {
+                acc[i][j][0] *= alpha;
+                acc[i][j][1] *= alpha;
+            }
+    }
+
+    // ---- epilogue (consumers only) ----
+    const int row0 = warp_m * WM + (lane >> 2), col0 = warp_n * WN + (lane & 3) * 2;
+    if (p.nsplit > 1)
+        store_partial<MT, NTL>(p, acc, m0, n0, row0, col0, mrem, nrem);
+    else
+        store_tile<MT, NTL>(p, acc, s_cm, s_cn, row0, col0, mrem, nrem);
 }
 
 // C[m,n] = beta*C[m,n] + sum_s ws[s][m][n]  (split-K second stage, fixed order)
@@ -384,12 +707,19 @@ struct TileCfg {
 static const TileCfg kCfg[] = {
     // eff = measured pp-ladder rate relative to the best config (profiles/r1_tile_sweep.md)
     {128, 128, 256, 1.00}, {128, 64, 256, 0.90}, {64, 64, 128, 1.00}, {64, 32, 128, 0.80},
-    {128, 64, 128, 0.90}};
-constexpr int kNumCfg = 5;
+    {128, 64, 128, 0.90},
+    // warp-specialised kernels (384 threads: 8 consumer + 4 producer warps, one CTA per SM)
+    {128, 128, 384, 1.30}, {128, 128, 384, 1.00}};
+constexpr int kNumCfg = 7;
 
 static int g_force_cfg = -1;
 static int g_force_split = 0;
-static long long g_panel_bytes = 40LL << 20;   // L2 budget for one operand window (0 = off)
+// L2 budget for one operand's k window (0 = no windows).  The warp-specialised kernel runs
+// without windows: its producers prefetch four k-tiles deep, DRAM is at 6 % utilisation even
+// with the smaller operand re-read per row tile (profiles/pp_ladder_ws_v200_ncu.md), and a
+// window costs a read-modify-write of C (measured: ring terms 33.0 vs 30.4 TFLOP/s).
+constexpr long long kPanelDefault = 40LL << 20, kPanelDefaultWs = 0;
+static long long g_panel_bytes = kPanelDefault, g_panel_bytes_ws = kPanelDefaultWs;
 
 template <int BM, int BN, int STAGES, int NT>
 constexpr size_t smem_bytes(int nterms) {
@@ -409,6 +739,27 @@ static int launch_one(const Params &p, dim3 grid, cudaStream_t s) {
         attr_done = true;
     }
     kern<<<grid, WMW * WNW * 32, sm, s>>>(p);
+    count_launch();
+    return cuda_status();
+}
+
+template <int BM, int BN, int STAGES>
+constexpr size_t ws_smem_bytes(int nterms) {
+    return 128 + sizeof(double) * STAGES * BK * (BM + SPAD + BN + SPAD) +
+           sizeof(long long) * ((size_t)kWsKRing * 2 * BK + (size_t)(nterms + 1) * (BM + BN));
+}
+
+template <int BM, int BN, int WMW, int WNW, int STAGES>
+static int launch_ws(const Params &p, dim3 grid, cudaStream_t s) {
+    auto kern = contract_ws_kernel<BM, BN, WMW, WNW, STAGES>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)ws_smem_bytes<BM, BN, STAGES>(PMB_MAX_TERMS));
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    kern<<<grid, WMW * WNW * 32 + kWsProducerThreads, ws_smem_bytes<BM, BN, STAGES>(p.nterms), s>>>(p);
     count_launch();
     return cuda_status();
 }
@@ -535,7 +886,8 @@ static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
 // contraction is therefore issued as a sequence of launches over k windows whose slice of the
 // smaller operand stays L2-resident; partial sums accumulate in C (beta = 1 after the first
 // window, fixed order, deterministic).
-static int panel_ktiles(const Params &p) {
+static int panel_ktiles(const Params &p, int cfg) {
+    const long long g_panel_bytes = cfg >= 5 ? g_panel_bytes_ws : pmb::g_panel_bytes;
     if (p.nsplit > 1 || g_panel_bytes <= 0) return p.total_ktiles;
     const double small_rows = (double)(p.M < p.N ? p.M : p.N);
     const double small_bytes = small_rows * (double)p.total_ktiles * BK * 8.0;
@@ -555,7 +907,10 @@ extern "C" void pmb_contract_set_tuning(int tile_config, int split_k) {
     g_force_split = split_k;
 }
 
-extern "C" void pmb_contract_set_panel_bytes(long long bytes) { g_panel_bytes = bytes; }
+extern "C" void pmb_contract_set_panel_bytes(long long bytes) {
+    g_panel_bytes = bytes < 0 ? kPanelDefault : bytes;
+    g_panel_bytes_ws = bytes < 0 ? kPanelDefaultWs : bytes;
+}
 
 extern "C" size_t pmb_contract_workspace(const pmb_contract_t *d) {
     Params p;
@@ -581,7 +936,7 @@ extern "C" int pmb_contract(const pmb_contract_t *d, void *ws, size_t ws_bytes, 
     // owns the SM (cfg 0), costs registers/occupancy otherwise.  Tuning bit 8 flips it.
     bool il = (cfg == 0);
     if (g_force_cfg >= 0 && (g_force_cfg & 8)) il = !il;
-    const int window = panel_ktiles(p);
+    const int window = panel_ktiles(p, cfg);
     for (int base = 0; base < p.total_ktiles && rc == 0; base += window) {
         if (window < p.total_ktiles) {
             p.kt_base = base;
@@ -594,6 +949,8 @@ extern "C" int pmb_contract(const pmb_contract_t *d, void *ws, size_t ws_bytes, 
             case 1: rc = launch_cfg<128, 64, 4, 2, 4, 1>(p, grid, s, il); break;
             case 2: rc = launch_cfg<64, 64, 2, 2, 3, 3>(p, grid, s, il); break;
             case 4: rc = launch_cfg<128, 64, 2, 2, 3, 2>(p, grid, s, il); break;
+            case 5: rc = launch_ws<128, 128, 4, 2, 4>(p, grid, s); break;
+            case 6: rc = launch_ws<128, 128, 4, 2, 6>(p, grid, s); break;
             default: rc = launch_cfg<64, 32, 2, 2, 3, 3>(p, grid, s, il); break;
         }
     }

@@ -130,7 +130,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("cfg", [-1, 0, 1, 2, 3, 4])
+@pytest.mark.parametrize("cfg", [-1, 0, 1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("spec,shapes", CASES)
 def test_contract_engine(spec, shapes, cfg):
     from pymes_b200 import _lib, backend as bk
@@ -152,14 +152,15 @@ def test_contract_engine(spec, shapes, cfg):
         _lib.load().pmb_contract_set_tuning(-1, 0)
 
 
+@pytest.mark.parametrize("cfg", [-1, 5])
 @pytest.mark.parametrize("split", [1, 2, 3, 7, 16])
-def test_contract_split_k(split):
+def test_contract_split_k(split, cfg):
     from pymes_b200 import _lib, backend as bk
     rng = np.random.default_rng(split)
     A = rng.standard_normal((6, 6, 41, 41))
     B = rng.standard_normal((41, 41, 6, 6))
     ref = np.einsum("klcd,cdij->klij", A, B, optimize=True)
-    _lib.load().pmb_contract_set_tuning(-1, split)
+    _lib.load().pmb_contract_set_tuning(cfg, split)
     try:
         out = bk.asdev(np.ones_like(ref))
         bk.contract("klcd,cdij->klij", A, B, out=out, beta=2.0)
@@ -168,7 +169,7 @@ def test_contract_split_k(split):
         _lib.load().pmb_contract_set_tuning(-1, 0)
 
 
-@pytest.mark.parametrize("cfg", [0, 2])
+@pytest.mark.parametrize("cfg", [0, 2, 5])
 def test_contract_k_windows(cfg):
     """K-window launches (L2 residency of the smaller operand) accumulate in C in fixed order."""
     from pymes_b200 import _lib, backend as bk
@@ -191,7 +192,7 @@ def test_contract_k_windows(cfg):
         assert _rel(got.cpu().numpy(), np.einsum("abcd,cdij->abij", V, T, optimize=True)) < 1e-13
     finally:
         lib.pmb_contract_set_tuning(-1, 0)
-        lib.pmb_contract_set_panel_bytes(40 << 20)
+        lib.pmb_contract_set_panel_bytes(-1)
 
 
 def test_contract_views_of_V_pqrs_no_symmetry():

@@ -10,7 +10,7 @@ v = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 o = int(sys.argv[2]) if len(sys.argv) > 2 else 27
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 cfg = int(sys.argv[4]) if len(sys.argv) > 4 else -1
-panel_mb = float(sys.argv[5]) if len(sys.argv) > 5 else 40.0
+panel_mb = float(sys.argv[5]) if len(sys.argv) > 5 else -1.0
 torch.cuda.set_device(0)
 _lib.load().pmb_contract_set_tuning(cfg, 0)
 _lib.load().pmb_contract_set_panel_bytes(int(panel_mb * (1 << 20)))

@@ -1,7 +1,7 @@
 """Time every contraction launch of the CCD doubles residual separately (random dense
 operands, CUDA events) and print TFLOP/s per launch.  Not a bench value: it shows which
 index patterns the gather pipeline handles badly.
-usage: profile_terms.py [v] [o] [reps] [only_tag]"""
+usage: profile_terms.py [v] [o] [reps] [only_tag|-] [panel_MB] [cfg]"""
 import sys
 import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -11,7 +11,13 @@ from pymes_b200 import backend as bk
 v = int(sys.argv[1]) if len(sys.argv) > 1 else 314
 o = int(sys.argv[2]) if len(sys.argv) > 2 else 27
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-only = sys.argv[4] if len(sys.argv) > 4 else None
+only = sys.argv[4] if len(sys.argv) > 4 and sys.argv[4] != "-" else None
+if len(sys.argv) > 5:
+    from pymes_b200 import _lib
+    _lib.load().pmb_contract_set_panel_bytes(int(float(sys.argv[5]) * (1 << 20)))
+if len(sys.argv) > 6:
+    from pymes_b200 import _lib
+    _lib.load().pmb_contract_set_tuning(int(sys.argv[6]), 0)
 torch.cuda.set_device(0)
 torch.manual_seed(0)
 
