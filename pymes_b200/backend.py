@@ -104,12 +104,24 @@ def launch_count():
 # optional per-region device timing (CUDA events on the launching stream; used by
 # bench.py for the roofline of the dominant kernel -- no synchronisation is added)
 # --------------------------------------------------------------------------
-_timing = {"on": False, "events": {}}
+_timing = {"on": False, "events": {}, "trace": None}
 
 
 def enable_timing(flag=True):
     _timing["on"] = bool(flag)
     _timing["events"] = {}
+
+
+def enable_trace(flag=True):
+    """Record a (label, start, stop) event triple around EVERY contraction launch
+    (tools/profile_sweep.py: which index patterns of a whole CCSD sweep cost what)."""
+    _timing["trace"] = [] if flag else None
+
+
+def trace_report():
+    """[(label, flops, milliseconds)] in launch order (synchronises the device)."""
+    torch.cuda.synchronize()
+    return [(lab, fl, a.elapsed_time(b)) for lab, fl, a, b in (_timing["trace"] or [])]
 
 
 class timed:
@@ -258,7 +270,21 @@ def contract_terms(out_sub, terms, out=None, beta=0.0):
     d, out, _operands = describe_contraction(out_sub, terms, out, beta)
     need = lib.pmb_contract_workspace(C.byref(d))
     ws = scratch().splitk_ws(need) if need else None
+    trace = _timing["trace"]
+    if trace is not None:
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(torch.cuda.current_stream())
     rc = lib.pmb_contract(C.byref(d), _ptr(ws) if ws is not None else None, need, _stream())
+    if trace is not None:
+        t1.record(torch.cuda.current_stream())
+        flops = 0.0
+        for _a, sa, A, sb, B in _operands:
+            n = 2.0
+            for ch, e in {**dict(zip(sa, A.shape)), **dict(zip(sb, B.shape))}.items():
+                n *= e
+            flops += n
+        label = " + ".join("%s,%s" % (t[1], t[3]) for t in _operands) + "->" + out_sub
+        trace.append((label + (" [split-K]" if need else ""), flops, t0, t1))
     _lib.check(rc, "pmb_contract")
     return out
 

@@ -865,9 +865,13 @@ static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
     if (g_force_split > 0) {
         nsplit = g_force_split;
     } else if (tiles * 2 <= kSmCount && kt >= 8) {
-        nsplit = (int)((kSmCount + tiles - 1) / tiles);
+        // enough CTAs for every SM to hold its co-resident complement (3 for the 128-thread
+        // tiles): skinny outputs with a long k (Fock-like terms, o.v^3 blocks against T1) are
+        // HBM-bound and need the bytes in flight of several CTAs per SM
+        const int64_t slots = (int64_t)kSmCount * (kCfg[cfg].threads == 128 ? 3 : 1);
+        nsplit = (int)((slots + tiles - 1) / tiles);
         if (nsplit > kt / 4) nsplit = kt / 4;
-        if (nsplit > 64) nsplit = 64;
+        if (nsplit > 192) nsplit = 192;
     }
     if (nsplit > kt) nsplit = kt;
     if (nsplit < 1) nsplit = 1;

@@ -109,7 +109,9 @@ def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abc
             (+1.0, "acik", Tta, "kbcj", V_iabj)]                     # ccd.py:235
     if ccd:                                                          # ccd.py:238-240
         Xp = ct("alci", [(1.0, "klcd", V_ijab, "daki", T2b)])
-        ring += [(-1.0, "alci", Xp, "cblj", T2), (+1.0, "alci", Xp, "bclj", T2)]
+        # -Xp.T_cblj + Xp.T_bclj = Xp.(T^{ba} - T)_cblj and T^{ba} - T = T - Tt: one ring
+        # contraction instead of two (one HBM pass builds the combined operand)
+        ring.append((+1.0, "alci", Xp, "cblj", bk.lincomb([1.0, -1.0], [T2, Tt])))
     ct("abij", ring, out=Ex, beta=1.0)
     ct("abij", [(-1.0, "kbic", V_iajb, "ackj", T2a)], out=Ex, beta=1.0)   # ccd.py:234
 
