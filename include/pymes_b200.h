@@ -69,6 +69,8 @@ const char *pmb_error_string(int code);
 /*   T1 dressing ccsd.py:257-286,322-419 ; singles residual ccsd.py:428-436   */
 /*   EOM sigma   eom_ccsd.py:288-308,332-383                                  */
 /* ------------------------------------------------------------------------ */
+struct pmb_ueg_operand;              /* generated operand, declared below    */
+
 typedef struct {
     const double *A;
     const double *B;
@@ -80,6 +82,11 @@ typedef struct {
     int64_t a_mstr[PMB_MAX_DIMS];    /* strides of A along the M indices     */
     int64_t b_nstr[PMB_MAX_DIMS];    /* strides of B along the N indices     */
     double alpha;
+    /* NULL: A is read from memory.  Otherwise A is never stored: the tiles of */
+    /* this term's A operand are EVALUATED by the producer warps of the kernel */
+    /* (UEG integrals, see pmb_ueg_operand_t); `A`, a_kstr and a_mstr are then  */
+    /* ignored.  At most one term of a contraction may have a generated A.     */
+    const struct pmb_ueg_operand *a_gen;
 } pmb_term_t;
 
 typedef struct {
@@ -259,6 +266,35 @@ int pmb_ueg_pair_tables(const pmb_ueg_t *u, int mode, const double *umat_pr,
 int pmb_ueg_build_block(const pmb_ueg_t *u, const double *W0a, const double *W1a,
                         const double *W0s, const int32_t lo[4], const int32_t ext[4],
                         double *out, pmb_stream_t stream);
+
+/* ------------------------------------------------------------------------ */
+/* Never-materialised UEG integrals.                          */
+/*                                                                          */
+/* The v^4 block V_abcd of the 54-electron / ~500-orbital UEG is 300-450 GB  */
+/* of which one element in v is non-zero.  Instead of being written to HBM    */
+/* by pmb_ueg_build_block and read back by the particle-particle ladder       */
+/* "abcd,cdij->abij" (ccd.py:187), it can be handed to pmb_contract as a      */
+/* GENERATED A operand: the producer warps fill the shared-memory tile with   */
+/* exactly the values pmb_ueg_build_block would have stored (same formula,    */
+/* same rounding), so results are bit-identical to the materialised path and  */
+/* the block costs no memory and no HBM traffic.                              */
+/*                                                                          */
+/* The operand is the sub-block V[lo[0]+.., lo[1]+.., lo[2]+.., lo[3]+..] of  */
+/* the (p,q,r,s) tensor; m_axis[d] / k_axis[d] say which of the four V axes   */
+/* (0 = p .. 3 = s) the d-th M index / K index of the contraction runs over   */
+/* (extents come from the contraction descriptor).  Every axis must appear    */
+/* exactly once.  Limits: n_orb <= 2047, imax <= 27.                          */
+/* ------------------------------------------------------------------------ */
+typedef struct pmb_ueg_operand {
+    pmb_ueg_t ueg;
+    const double *W0a;        /* pair tables as for pmb_ueg_build_block        */
+    const double *W1a;        /*   (W1a, W0s may be NULL)                      */
+    const double *W0s;
+    const int32_t *lin;       /* [nP] n^2 kx + n ky + kz, n = 2 imax + 1 (dev) */
+    int32_t lo[4];
+    int32_t m_axis[PMB_MAX_DIMS];
+    int32_t k_axis[PMB_MAX_DIMS];
+} pmb_ueg_operand_t;
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,8 @@ I32x4 = C.c_int32 * 4
 class Term(C.Structure):
     _fields_ = [("A", C.c_void_p), ("B", C.c_void_p), ("nk", C.c_int32), ("_pad", C.c_int32),
                 ("k_ext", I64x4), ("a_kstr", I64x4), ("b_kstr", I64x4),
-                ("a_mstr", I64x4), ("b_nstr", I64x4), ("alpha", C.c_double)]
+                ("a_mstr", I64x4), ("b_nstr", I64x4), ("alpha", C.c_double),
+                ("a_gen", C.c_void_p)]      # const pmb_ueg_operand_t * (generated A operand) or NULL
 
 
 class Contract(C.Structure):
@@ -41,6 +42,11 @@ class Ueg(C.Structure):
     _fields_ = [("n_orb", C.c_int32), ("imax", C.c_int32), ("n_occ", C.c_int32), ("n_ele", C.c_int32),
                 ("omega", C.c_double), ("u_table", C.c_void_p), ("u_table_len", C.c_int32),
                 ("_pad", C.c_int32), ("kvec", C.c_void_p), ("kp", C.c_void_p), ("index_map", C.c_void_p)]
+
+
+class UegOperand(C.Structure):
+    _fields_ = [("ueg", Ueg), ("W0a", C.c_void_p), ("W1a", C.c_void_p), ("W0s", C.c_void_p),
+                ("lin", C.c_void_p), ("lo", I32x4), ("m_axis", I32x4), ("k_axis", I32x4)]
 
 
 _SIGS = {

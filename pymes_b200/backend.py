@@ -31,8 +31,37 @@ def device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+class GeneratedOperand:
+    """An operand of :func:`contract_terms` that is never stored: the kernel's producer warps
+    evaluate its tiles (``pmb_term_t.a_gen``).  Subclasses describe one source -- today the
+    momentum-conserving UEG integrals (``model.ueg.VirtualBlock``).  It quacks like a tensor
+    as far as the host-side index classification needs (shape / dim / C-order strides)."""
+
+    shape = ()
+
+    def dim(self):
+        return len(self.shape)
+
+    def stride(self):
+        st, acc = [], 1
+        for n in reversed(self.shape):
+            st.append(acc)
+            acc *= int(n)
+        return tuple(reversed(st))
+
+    def data_ptr(self):
+        return 0
+
+    def gen_descriptor(self, sub, m_ord, k_ord):
+        """ctypes ``pmb_ueg_operand_t`` for this operand indexed by ``sub`` with the M / K index
+        groups ordered (fastest first) as ``m_ord`` / ``k_ord``."""
+        raise NotImplementedError
+
+
 def asdev(x):
     """numpy array / torch tensor -> float64 CUDA tensor (views keep their strides)."""
+    if isinstance(x, GeneratedOperand):
+        return x
     if isinstance(x, torch.Tensor):
         if x.dtype != F64:
             x = x.to(F64)
@@ -246,7 +275,16 @@ def describe_contraction(out_sub, terms, out=None, beta=0.0, conv=None, alloc=No
         else:
             k_ord = sorted(ks, key=lambda ch: (bstr[ch], ch))
         t = d.terms[i]
+        if isinstance(B, GeneratedOperand):
+            raise ValueError("a generated operand must end up as the A (row) operand of the "
+                             "contraction; here the output layout puts it on the column side")
         t.A, t.B, t.nk, t.alpha = A.data_ptr(), B.data_ptr(), len(k_ord), alpha
+        if isinstance(A, GeneratedOperand):
+            gen = A.gen_descriptor(sa, m_ord, k_ord)
+            keep = getattr(d, "_keep", [])
+            keep.append(gen)
+            d._keep = keep                      # the descriptor points into it
+            t.a_gen = C.addressof(gen)
         _fill(t.k_ext, [ext[ch] for ch in k_ord])
         _fill(t.a_kstr, [astr[ch] for ch in k_ord])
         _fill(t.b_kstr, [bstr[ch] for ch in k_ord])

@@ -22,6 +22,7 @@
 //     direction (x-fast or k-fast) so global accesses stay coalesced to full
 //     32 B sectors for any permutation.
 #include "common.cuh"
+#include "ueg_device.cuh"
 
 namespace pmb {
 
@@ -58,7 +59,56 @@ struct Params {
     int kt_base, kt_limit;   // k-tile window of this launch (K-panel), [0, total_ktiles) if not panelled
     double *ws;
     TermDev t[PMB_MAX_TERMS];
+    // generated A operand (never-materialised UEG integrals): term index or -1
+    int gen_term;
+    int gen_n3;                       // (2 imax + 1)^3, size of the index map
+    int gen_l0;                       // imax (n^2 + n + 1)
+    int gen_lo[4];
+    int gen_m_axis[PMB_MAX_DIMS], gen_k_axis[PMB_MAX_DIMS];
+    pmb_ueg_t gen_ueg;
+    const double *gen_W0a, *gen_W1a, *gen_W0s;
+    const int *gen_lin;
 };
+
+// Generated operand: table entries are not element offsets but packed 64-bit words
+//   [63..44] partial sum of the flattened index-map location  +L(p) +L(q) -L(r)  (signed)
+//   [43..33] p   [32..22] q   [21..11] r   [10..0] s          (orbital indices, 11 bits each)
+// Every V axis belongs to either the M or the K group, so (row word + k word) is the full
+// description of one element: the orbital fields are disjoint and the signed location parts
+// add in two's complement.  The element is non-zero iff index_map[loc] == s -- exactly the
+// reference's test (ueg.py:397-407), flattened bounds check included.
+constexpr int kGenLocShift = 44, kGenFieldBits = 11, kGenFieldMask = (1 << kGenFieldBits) - 1;
+
+__device__ __forceinline__ long long gen_decomp(const Params &p, int idx, int nd, const int *ext, const int *axis) {
+    long long e = 0;
+#pragma unroll
+    for (int d = 0; d < PMB_MAX_DIMS; ++d) {
+        if (d < nd) {
+            const int x = ext[d];
+            const int q = idx / x;
+            const int ax = axis[d];
+            const int orb = p.gen_lo[ax] + (idx - q * x);
+            const int sign = ax == 2 ? -1 : (ax == 3 ? 0 : 1);
+            e += (long long)(sign * p.gen_lin[orb]) * (1LL << kGenLocShift);
+            e += (long long)orb << (kGenFieldBits * (3 - ax));
+            idx = q;
+        }
+    }
+    return e;
+}
+
+// the orbital the index map holds at this element's location (-1: none / outside the map)
+__device__ __forceinline__ int gen_sstar(const Params &p, long long e) {
+    const int loc = (int)(e >> kGenLocShift);
+    return (unsigned)loc < (unsigned)p.gen_n3 ? __ldg(p.gen_ueg.index_map + loc) : -1;
+}
+// value of the element given that orbital: one element in n_orb is non-zero
+__device__ __forceinline__ double gen_value(const Params &p, long long e, int sstar) {
+    const int s = (int)e & kGenFieldMask;
+    if (sstar != s) return 0.0;
+    return ueg_value(p.gen_ueg, p.gen_W0a, p.gen_W1a, p.gen_W0s, (int)(e >> (3 * kGenFieldBits)) & kGenFieldMask,
+                     (int)(e >> (2 * kGenFieldBits)) & kGenFieldMask, (int)(e >> kGenFieldBits) & kGenFieldMask, s);
+}
 
 __device__ __forceinline__ long long decomp(int idx, int nd, const int *ext,
                                             const long long *str) {
@@ -504,8 +554,16 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
     // ---- common prologue: offset tables of this output tile, barriers ----
     for (int ti = 0; ti < p.nterms; ++ti) {
         const TermDev &t = p.t[ti];
-        for (int i = tid; i < BM; i += NC + NP)
-            s_am[ti * BM + i] = (i < mrem) ? decomp(m0 + i, p.nm, p.m_ext, t.a_mstr) : 0;
+        if (ti == p.gen_term) {
+            // generated operand: packed (location, orbitals) words, L0 enters on the row side
+            for (int i = tid; i < BM; i += NC + NP)
+                s_am[ti * BM + i] = (i < mrem) ? gen_decomp(p, m0 + i, p.nm, p.m_ext, p.gen_m_axis) +
+                                                     (long long)p.gen_l0 * (1LL << kGenLocShift)
+                                               : 0;
+        } else {
+            for (int i = tid; i < BM; i += NC + NP)
+                s_am[ti * BM + i] = (i < mrem) ? decomp(m0 + i, p.nm, p.m_ext, t.a_mstr) : 0;
+        }
         for (int i = tid; i < BN; i += NC + NP)
             s_bn[ti * BN + i] = (i < nrem) ? decomp(n0 + i, p.nn, p.n_ext, t.b_nstr) : 0;
     }
@@ -516,7 +574,10 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bar_base + s * 8, NP);                    // full[s]: every producer thread
+            // full[s]: every producer thread, once through its cp.async group and -- when a
+            // term has a generated operand -- once more by a plain (release) arrive that
+            // orders its st.shared tile writes before the consumers' reads
+            mbar_init(bar_base + s * 8, p.gen_term >= 0 ? 2 * NP : NP);
             mbar_init(bar_base + (STAGES + s) * 8, NCW);        // empty[s]: every consumer warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -538,7 +599,12 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
                 const int kk = lane & (BK - 1);
                 const int k = (g - t.kt_begin) * BK + kk;
                 long long off = 0;
-                if (k < t.K) off = decomp(k, t.nk, t.k_ext, lane >= BK ? t.b_kstr : t.a_kstr);
+                if (k < t.K) {
+                    if (lane < BK && term_of(g) == p.gen_term)
+                        off = gen_decomp(p, k, t.nk, t.k_ext, p.gen_k_axis);
+                    else
+                        off = decomp(k, t.nk, t.k_ext, lane >= BK ? t.b_kstr : t.a_kstr);
+                }
                 s_k[((g - kt_lo) & (KRING - 1)) * 2 * BK + lane] = off;
             }
         };
@@ -556,12 +622,34 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
             const TermDev &t = p.t[ti];
             const long long *ko = s_k + ((g - kt_lo) & (KRING - 1)) * 2 * BK;
             const int krem = t.K - (g - t.kt_begin) * BK;
-            const Gat ga = make_gat<BM, NP>(as_base + (unsigned)(st * BK * LDA * 8), t.A, s_am + ti * BM, ko,
-                                            t.a_kfast != 0, ptid);
             const Gat gb = make_gat<BN, NP>(bs_base + (unsigned)(st * BK * LDB * 8), t.B, s_bn + ti * BN,
                                             ko + BK, t.b_kfast != 0, ptid);
-            gat_issue_batched<PER_A, 8>(ga, krem);
-            gat_issue_batched<PER_B, 8>(gb, krem);
+            if (ti == p.gen_term) {
+                // B first: its copies are in flight while the A tile is evaluated.  x-fast
+                // mapping (conflict-free stores): this thread owns row x and every KSTEP-th k.
+                gat_issue_batched<PER_B, 8>(gb, krem);
+                constexpr int KSTEP = NP / BM;
+                const int x = ptid % BM, k0 = ptid / BM;
+                const long long em = s_am[ti * BM + x];
+                double *dst = As + st * BK * LDA + k0 * LDA + x;
+                // all index-map look-ups of the tile column first (independent loads), then
+                // the compare / rare evaluation and the stores
+                int ss[PER_A];
+#pragma unroll
+                for (int it = 0; it < PER_A; ++it) {
+                    const int k = k0 + it * KSTEP;
+                    ss[it] = k < krem ? gen_sstar(p, em + ko[k]) : -1;
+                }
+#pragma unroll
+                for (int it = 0; it < PER_A; ++it)
+                    dst[it * KSTEP * LDA] = gen_value(p, em + ko[k0 + it * KSTEP], ss[it]);
+            } else {
+                const Gat ga = make_gat<BM, NP>(as_base + (unsigned)(st * BK * LDA * 8), t.A, s_am + ti * BM, ko,
+                                                t.a_kfast != 0, ptid);
+                gat_issue_batched<PER_A, 8>(ga, krem);
+                gat_issue_batched<PER_B, 8>(gb, krem);
+            }
+            if (p.gen_term >= 0) mbar_arrive(bar_base + st * 8);
             cp_async_arrive(bar_base + st * 8);
             if (++st == STAGES) {
                 st = 0;
@@ -819,9 +907,10 @@ static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
     p.beta = d->beta;
     int kt = 0;
     int nkeep = 0;
+    p.gen_term = -1;
     for (int ti = 0; ti < d->nterms; ++ti) {
         const pmb_term_t &s = d->terms[ti];
-        if (!s.A || !s.B || s.nk < 0 || s.nk > PMB_MAX_DIMS) return PMB_E_BADARG;
+        if ((!s.A && !s.a_gen) || !s.B || s.nk < 0 || s.nk > PMB_MAX_DIMS) return PMB_E_BADARG;
         // a zero coefficient contributes nothing; keep one such term only if nothing else is left
         if (s.alpha == 0.0 && !(ti == d->nterms - 1 && nkeep == 0)) continue;
         TermDev &t = p.t[nkeep++];
@@ -839,6 +928,40 @@ static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
             t.b_nstr[i] = i < d->nn ? s.b_nstr[i] : 0;
         }
         t.alpha = s.alpha;
+        if (s.a_gen) {
+            // generated A operand: validate the axis assignment and the packing limits
+            const pmb_ueg_operand_t &g = *s.a_gen;
+            if (p.gen_term >= 0) return PMB_E_UNSUPPORTED;         // one per contraction
+            if (!g.W0a && !g.W0s) return PMB_E_BADARG;
+            if (!g.lin || !g.ueg.index_map || !g.ueg.kp || g.ueg.n_orb <= 0) return PMB_E_BADARG;
+            if (g.ueg.n_orb > kGenFieldMask || g.ueg.imax < 0 || g.ueg.imax > 27) return PMB_E_UNSUPPORTED;
+            int seen = 0;
+            for (int i = 0; i < d->nm; ++i) {
+                const int ax = g.m_axis[i];
+                if (ax < 0 || ax > 3 || (seen >> ax & 1)) return PMB_E_BADARG;
+                if (g.lo[ax] < 0 || g.lo[ax] + d->m_ext[i] > g.ueg.n_orb) return PMB_E_BADARG;
+                seen |= 1 << ax;
+                p.gen_m_axis[i] = ax;
+            }
+            for (int i = 0; i < s.nk; ++i) {
+                const int ax = g.k_axis[i];
+                if (ax < 0 || ax > 3 || (seen >> ax & 1)) return PMB_E_BADARG;
+                if (g.lo[ax] < 0 || g.lo[ax] + s.k_ext[i] > g.ueg.n_orb) return PMB_E_BADARG;
+                seen |= 1 << ax;
+                p.gen_k_axis[i] = ax;
+            }
+            if (seen != 15) return PMB_E_BADARG;
+            const int n = 2 * g.ueg.imax + 1;
+            p.gen_term = nkeep - 1;
+            p.gen_n3 = n * n * n;
+            p.gen_l0 = g.ueg.imax * (n * n + n + 1);
+            for (int i = 0; i < 4; ++i) p.gen_lo[i] = g.lo[i];
+            p.gen_ueg = g.ueg;
+            p.gen_W0a = g.W0a;
+            p.gen_W1a = g.W1a;
+            p.gen_W0s = g.W0s;
+            p.gen_lin = g.lin;
+        }
         // follow the unit-stride direction of each operand
         auto kfast = [](int nk, const int64_t *kstr, const int64_t *kext, int nx, const int64_t *xstr) {
             if (nk == 0) return 0;
@@ -857,6 +980,8 @@ static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
     p.nterms = nkeep;
     p.total_ktiles = kt;
     cfg = choose_cfg(M, N);
+    // only the warp-specialised kernel has producer warps that can evaluate an operand
+    if (p.gen_term >= 0 && cfg < 5) cfg = 5;
     p.tiles_m = (int)((M + kCfg[cfg].bm - 1) / kCfg[cfg].bm);
     p.tiles_n = (int)((N + kCfg[cfg].bn - 1) / kCfg[cfg].bn);
     // split-K when the output has too few tiles to fill the machine

@@ -67,22 +67,52 @@ __global__ void __launch_bounds__(256) axpby4_kernel(Str4 g, double alpha, const
     }
 }
 
+// Index split of one element of an [a,b,i,j] row block, 32-bit arithmetic: the CTA-uniform
+// 64-bit division (first element of the pass -> pair ab0, remainder rem0) is done once per
+// pass, the per-element part fits in 32 bits.
+struct Abij {
+    int a, b, i, j;
+};
+__device__ __forceinline__ Abij split_abij(size_t ab0, unsigned local, unsigned oo, unsigned no, unsigned nv) {
+    const unsigned dab = local / oo, ij = local - dab * oo;
+    const size_t ab = ab0 + dab;
+    Abij r;
+    r.a = (int)(ab / nv);
+    r.b = (int)(ab - (size_t)r.a * nv);
+    r.i = (int)(ij / no);
+    r.j = (int)(ij - (unsigned)r.i * no);
+    return r;
+}
+
+constexpr int kEwUnroll = 4;   // independent 8-byte loads in flight per thread and stream
+
 // T2 = V_abij / (e_i + e_j - e_a - e_b + shift)
 __global__ void __launch_bounds__(256)
     mp2_kernel(int no, int nv, int a_lo, int na, const double *__restrict__ ei, const double *__restrict__ ea,
                double shift, const double *__restrict__ V, Str4 g, double *__restrict__ T2) {
     const size_t n = (size_t)na * nv * no * no;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-         idx += (size_t)gridDim.x * blockDim.x) {
-        size_t r = idx;
-        const int j = r % no;
-        r /= no;
-        const int i = r % no;
-        r /= no;
-        const int b = r % nv;
-        const int a = (int)(r / nv);
-        const double d = ei[i] + ei[j] - ea[a_lo + a] - ea[b] + shift;
-        T2[idx] = V[a * g.si[0] + b * g.si[1] + i * g.si[2] + j * g.si[3]] / d;
+    const unsigned oo = (unsigned)no * no;
+    const size_t pass = (size_t)blockDim.x * kEwUnroll;
+    for (size_t base = (size_t)blockIdx.x * pass; base < n; base += (size_t)gridDim.x * pass) {
+        const size_t ab0 = base / oo;
+        const unsigned rem0 = (unsigned)(base - ab0 * oo);
+        double v[kEwUnroll], d[kEwUnroll];
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) {
+            const unsigned off = u * blockDim.x + threadIdx.x;
+            v[u] = 0.0;
+            d[u] = 1.0;
+            if (base + off < n) {
+                const Abij x = split_abij(ab0, rem0 + off, oo, no, nv);
+                v[u] = V[x.a * g.si[0] + x.b * g.si[1] + x.i * g.si[2] + x.j * g.si[3]];
+                d[u] = ei[x.i] + ei[x.j] - ea[a_lo + x.a] - ea[x.b] + shift;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) {
+            const size_t idx = base + u * blockDim.x + threadIdx.x;
+            if (idx < n) T2[idx] = v[u] / d[u];
+        }
     }
 }
 
@@ -93,21 +123,32 @@ __global__ void __launch_bounds__(kReduceThreads)
                           const double *__restrict__ R, double *__restrict__ dT, double *__restrict__ T2,
                           double *ws) {
     const size_t n = (size_t)na * nv * no * no;
+    const unsigned oo = (unsigned)no * no;
+    const size_t pass = (size_t)blockDim.x * kEwUnroll;
     double s[1] = {0.0};
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-         idx += (size_t)gridDim.x * blockDim.x) {
-        size_t r = idx;
-        const int j = r % no;
-        r /= no;
-        const int i = r % no;
-        r /= no;
-        const int b = r % nv;
-        const int a = (int)(r / nv);
-        const double dinv = 1.0 / (ei[i] + ei[j] - ea[a_lo + a] - ea[b] + shift);
-        const double d = R[idx] * dinv;
-        dT[idx] = d;
-        T2[idx] += delta * d;
-        s[0] += d * d;
+    for (size_t base = (size_t)blockIdx.x * pass; base < n; base += (size_t)gridDim.x * pass) {
+        const size_t ab0 = base / oo;
+        const unsigned rem0 = (unsigned)(base - ab0 * oo);
+        double r[kEwUnroll], t[kEwUnroll];
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) {
+            const size_t idx = base + u * blockDim.x + threadIdx.x;
+            r[u] = idx < n ? R[idx] : 0.0;
+            t[u] = idx < n ? T2[idx] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) {
+            const unsigned off = u * blockDim.x + threadIdx.x;
+            const size_t idx = base + off;
+            if (idx < n) {
+                const Abij x = split_abij(ab0, rem0 + off, oo, no, nv);
+                const double dinv = 1.0 / (ei[x.i] + ei[x.j] - ea[a_lo + x.a] - ea[x.b] + shift);
+                const double d = r[u] * dinv;
+                dT[idx] = d;
+                T2[idx] = t[u] + delta * d;
+                s[0] += d * d;
+            }
+        }
     }
     block_reduce_store<1>(s, ws);
 }
@@ -152,6 +193,63 @@ __global__ void __launch_bounds__(kReduceThreads)
         s[0] += tau * vd;
         s[1] += tau * vx;
         s[2] += t * t;
+    }
+    block_reduce_store<3>(s, ws);
+}
+
+// Tiled form of the same sums for the ccd.py exchange (V[i,j,b,a]).  A CTA owns one row a,
+// 32 columns b and 32 pairs ij per pass: the V[ij,a,b] tile is read with b along the lanes
+// (the unit-stride direction of V_ijab), T2[a,b,ij] with ij along the lanes, and the tile is
+// turned through shared memory -- every global access of the direct term is a full 256 B row
+// segment.  The exchange tile V[ij,b,a] has stride nv between lanes; consecutive tiles in the
+// launch order differ in a only, so its 32 B sectors are shared through L2 by the CTAs that
+// run side by side (a .. a+3 live in one sector).
+constexpr int kEt = 32;
+__global__ void __launch_bounds__(kReduceThreads)
+    energy_tiled_kernel(int no, int nv, int a_lo, int na, const double *__restrict__ T2,
+                        const double *__restrict__ T1, const double *__restrict__ V, Str4 g, double *ws) {
+    __shared__ double Vd[kEt][kEt + 1], Vx[kEt][kEt + 1];
+    const int oo = no * no;
+    const int tb = (nv + kEt - 1) / kEt, tij = (oo + kEt - 1) / kEt;
+    const long long tiles = (long long)na * tb * tij;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = kReduceThreads / 32;
+    double s[3] = {0.0, 0.0, 0.0};
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int al = (int)(t % na);
+        const long long rest = t / na;
+        const int b0 = (int)(rest % tb) * kEt, ij0 = (int)(rest / tb) * kEt;
+        const int a = a_lo + al;
+        const int b = b0 + lane;
+        __syncthreads();               // previous pass has consumed the tiles
+#pragma unroll
+        for (int k = 0; k < kEt / NW; ++k) {
+            const int r = warp + k * NW, ij = ij0 + r;
+            double vd = 0.0, vx = 0.0;
+            if (ij < oo && b < nv) {
+                const int i = ij / no, j = ij - i * no;
+                const long long o = i * g.si[0] + j * g.si[1];
+                vd = V[o + a * g.si[2] + b * g.si[3]];
+                vx = V[o + b * g.si[2] + a * g.si[3]];
+            }
+            Vd[r][lane] = vd;
+            Vx[r][lane] = vx;
+        }
+        __syncthreads();
+        const int ij = ij0 + lane;
+        const int i = ij / no, j = ij - i * no;
+#pragma unroll
+        for (int k = 0; k < kEt / NW; ++k) {
+            const int r = warp + k * NW, bb = b0 + r;
+            if (ij < oo && bb < nv) {
+                const double tv = T2[((size_t)al * nv + bb) * oo + ij];
+                double tau = tv;
+                if (T1) tau += T1[a * no + i] * T1[bb * no + j];
+                s[0] += tau * Vd[lane][r];
+                s[1] += tau * Vx[lane][r];
+                s[2] += tv * tv;
+            }
+        }
     }
     block_reduce_store<3>(s, ws);
 }
@@ -391,8 +489,12 @@ extern "C" int pmb_energy_doubles(int no, int nv, int a_lo, int na, const double
     if (!ws || ws_bytes < pmb_reduce_workspace()) return PMB_E_WORKSPACE;
     const size_t n = (size_t)na * nv * no * no;
     const int blocks = grid_for(n, kReduceThreads, kReduceBlocks);
-    energy_kernel<<<blocks, kReduceThreads, 0, (cudaStream_t)stream>>>(
-        no, nv, a_lo, na, T2, T1, V_ijab, make_str(nullptr, v_str, nullptr), mp2_form, (double *)ws);
+    if (mp2_form)
+        energy_kernel<<<blocks, kReduceThreads, 0, (cudaStream_t)stream>>>(
+            no, nv, a_lo, na, T2, T1, V_ijab, make_str(nullptr, v_str, nullptr), mp2_form, (double *)ws);
+    else
+        energy_tiled_kernel<<<blocks, kReduceThreads, 0, (cudaStream_t)stream>>>(
+            no, nv, a_lo, na, T2, T1, V_ijab, make_str(nullptr, v_str, nullptr), (double *)ws);
     count_launch();
     int rc = cuda_status();
     if (rc) return rc;

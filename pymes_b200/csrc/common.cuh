@@ -21,7 +21,7 @@ inline int cuda_status() {
 }
 
 constexpr int kSmCount = 148;          // B200: 2 dies x 74 SMs
-constexpr int kReduceBlocks = 4 * kSmCount;
+constexpr int kReduceBlocks = 8 * kSmCount;   // 2048 resident threads per SM
 constexpr int kReduceThreads = 256;
 constexpr int kMaxScalars = 8;
 

@@ -7,6 +7,7 @@
 // 128 B lines per instruction).  The q-dependent heavy sums (u_mat: a
 // 226 981-term lattice sum per distinct transfer vector) run as one CTA per q.
 #include "common.cuh"
+#include "ueg_device.cuh"
 
 namespace pmb {
 
@@ -160,7 +161,6 @@ __global__ void __launch_bounds__(256)
     const int lane = threadIdx.x & 31;
     const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long rows = (long long)g.ext[0] * g.ext[1] * g.ext[2];
-    const int nP = u.n_orb;
     for (long long row = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < rows; row += warps) {
         const int r = g.lo[2] + (int)(row % g.ext[2]);
         const int q = g.lo[1] + (int)((row / g.ext[2]) % g.ext[1]);
@@ -168,21 +168,7 @@ __global__ void __launch_bounds__(256)
         const int s = conserving_s(u, p, q, r);
         double w = 0.0;
         const int sl = s - g.lo[3];
-        if (s >= 0 && sl >= 0 && sl < g.ext[3]) {
-            const int pr = p * nP + r;
-            if (W0a) w = W0a[pr];
-            if (W1a) {
-                const double w1 = W1a[pr];
-                if (w1 != 0.0) {
-                    const double dx = u.kp[3 * r] - u.kp[3 * p], dy = u.kp[3 * r + 1] - u.kp[3 * p + 1],
-                                 dz = u.kp[3 * r + 2] - u.kp[3 * p + 2];
-                    const double ex = u.kp[3 * r] - u.kp[3 * s], ey = u.kp[3 * r + 1] - u.kp[3 * s + 1],
-                                 ez = u.kp[3 * r + 2] - u.kp[3 * s + 2];
-                    w += w1 * (ex * dx + ey * dy + ez * dz);
-                }
-            }
-            if (W0s) w += 0.5 * (W0s[pr] + W0s[q * nP + s]);
-        }
+        if (s >= 0 && sl >= 0 && sl < g.ext[3]) w = ueg_value(u, W0a, W1a, W0s, p, q, r, s);
         double *dst = out + row * (long long)g.ext[3];
         for (int c = lane; c < g.ext[3]; c += 32) dst[c] = (c == sl) ? w : 0.0;
     }

@@ -225,13 +225,20 @@ class UEG:
         print_logging_info("{:.3f} s spent on ".format(time.time() - t0) + __name__, level=1)
         return out
 
-    def eval_2b_blocks(self, no, keys, parts, ranges=None):
+    def virtual_block(self, lo, ext, W0a=None, W1a=None, W0s=None):
+        """The block ``build_block`` would write, as a never-materialised operand:
+        handed to ``backend.contract_terms`` in place of a tensor, its tiles are evaluated by the
+        contraction kernel's producer warps -- no memory, no HBM traffic, bit-identical values."""
+        return VirtualBlock(self, lo, ext, W0a, W1a, W0s)
+
+    def eval_2b_blocks(self, no, keys, parts, ranges=None, virtual=()):
         """Named sub-blocks (partition.py keys, e.g. "abcd") of a SUM of integral kinds,
         built directly on the device: ``parts`` is a list of ``(mode, correlator)``;
         ``effect_2b`` parts enter symmetrised exactly as in
         test_symmetrised_2body_integral.py:141-145.  ``ranges`` = ``{key: {dim: (lo, n)}}`` restricts
         a dimension of a block to absolute orbital indices [lo, lo+n) (the row block one rank of
-        a sharded run owns).  Returns ``{key: cuda tensor}``."""
+        a sharded run owns).  Keys listed in ``virtual`` (e.g. ``("abcd",)``) come back as
+        :class:`VirtualBlock` operands instead of tensors.  Returns ``{key: cuda tensor}``."""
         nP = self.n_orb
         tabs = []
         for mode, corr in parts:
@@ -251,7 +258,8 @@ class UEG:
             ext = [no if ch in OCCUPIED else nP - no for ch in key]
             for dim, (r_lo, r_n) in (ranges or {}).get(key, {}).items():
                 lo[dim], ext[dim] = int(r_lo), int(r_n)
-            out[key] = self.build_block(tuple(lo), tuple(ext), W0a=W0a, W1a=W1a, W0s=W0s)
+            make = self.virtual_block if key in virtual else self.build_block
+            out[key] = make(tuple(lo), tuple(ext), W0a=W0a, W1a=W1a, W0s=W0s)
         return out
 
     # ------------------------------------------------- 3-body mean-field parts
@@ -352,3 +360,50 @@ class UEG:
         if k2.ndim == 0:
             return -0.0 if (1e-12 < k2 < kc2) else -(4 * np.pi / float(k2) ** 2)
         return -np.divide(4 * np.pi, k2 ** 2, out=np.zeros_like(k2), where=(k2 >= kc2))
+
+
+class VirtualBlock(bk.GeneratedOperand):
+    """Sub-block ``V[lo:lo+ext]`` of the UEG integrals that exists only as its pair tables
+    (``include/pymes_b200.h: pmb_ueg_operand_t``).  Usable as the row operand of a
+    contraction, e.g. the particle-particle ladder ``abcd,cdij->abij`` (ccd.py:187)."""
+
+    def __init__(self, model, lo, ext, W0a=None, W1a=None, W0s=None):
+        if W0a is None and W0s is None:
+            raise ValueError("a virtual block needs pair tables (W0a and/or W0s)")
+        if model.n_orb > 2047 or model.imax > 27:
+            raise ValueError("generated operands support n_orb <= 2047 and imax <= 27")
+        self.model, self.lo, self.shape = model, tuple(int(x) for x in lo), tuple(int(x) for x in ext)
+        self.tables = (W0a, W1a, W0s)
+        st = model._device_state()
+        if "lin" not in st:
+            n = 2 * model.imax + 1
+            k = model.k_int().astype(np.int64)
+            lin = (n * n * k[:, 0] + n * k[:, 1] + k[:, 2]).astype(np.int32)
+            st["lin"] = torch.from_numpy(lin).to(bk.device())
+        self.lin = st["lin"]
+
+    def rows(self, dim, lo, n):
+        """The same block restricted along ``dim`` to LOCAL indices [lo, lo+n)."""
+        new_lo, new_ext = list(self.lo), list(self.shape)
+        new_lo[dim] += int(lo)
+        new_ext[dim] = int(n)
+        return VirtualBlock(self.model, new_lo, new_ext, *self.tables)
+
+    def materialise(self):
+        """The dense tensor (tests / small systems)."""
+        W0a, W1a, W0s = self.tables
+        return self.model.build_block(self.lo, self.shape, W0a=W0a, W1a=W1a, W0s=W0s)
+
+    def gen_descriptor(self, sub, m_ord, k_ord):
+        g = _lib.UegOperand()
+        g.ueg = self.model._descriptor()
+        p = lambda t: t.data_ptr() if t is not None else None
+        g.W0a, g.W1a, g.W0s = (p(t) for t in self.tables)
+        g.lin = self.lin.data_ptr()
+        axis = {ch: i for i, ch in enumerate(sub)}
+        for i in range(4):
+            g.lo[i] = self.lo[i]
+            g.m_axis[i] = axis[m_ord[i]] if i < len(m_ord) else -1
+            g.k_axis[i] = axis[k_ord[i]] if i < len(k_ord) else -1
+        g._keep = (self.tables, self.lin, self.model._dev)
+        return g

@@ -102,14 +102,15 @@ def shard_blocks(dV_full, shard):
     return out
 
 
-def build_sharded_hamiltonian(m, no, comm, parts):
+def build_sharded_hamiltonian(m, no, comm, parts, virtual=()):
     """UEG integral blocks built directly as this rank's row blocks (no communication):
-    the v^4 / o.v^3 blocks only for a in [lo, lo+na).  ``parts`` as in UEG.eval_2b_blocks."""
+    the v^4 / o.v^3 blocks only for a in [lo, lo+na).  ``parts`` and ``virtual`` (keys kept as
+    never-materialised operands, e.g. ``("abcd",)``) as in UEG.eval_2b_blocks."""
     from .integral.partition import KEYS
     nv = m.n_orb - no
     shard = Shard(comm, nv)
     ranges = {k: {SHARD_DIMS[k]: (no + shard.lo, shard.na)} for k in SHARD_DIMS}
-    return m.eval_2b_blocks(no, list(KEYS), parts, ranges=ranges)
+    return m.eval_2b_blocks(no, list(KEYS), parts, ranges=ranges, virtual=virtual)
 
 
 class ShardedCCSD(ccsd.CCSD):

@@ -88,7 +88,10 @@ class FakeLib:
             ak = _offsets(k_ext, [t.a_kstr[i] for i in range(t.nk)])
             bk_ = _offsets(k_ext, [t.b_kstr[i] for i in range(t.nk)])
             bn = _offsets(n_ext, [t.b_nstr[i] for i in range(d.nn)])
-            A, _, _ = _gather(t.A, (am[:, None] + ak[None, :]).reshape(-1))
+            if t.a_gen:
+                A = self._generated(t.a_gen, m_ext, k_ext)
+            else:
+                A, _, _ = _gather(t.A, (am[:, None] + ak[None, :]).reshape(-1))
             B, _, _ = _gather(t.B, (bk_[:, None] + bn[None, :]).reshape(-1))
             acc += t.alpha * (A.reshape(M, -1) @ B.reshape(-1, N))
         cm = _offsets(m_ext, [d.c_mstr[i] for i in range(d.nm)])
@@ -225,7 +228,7 @@ class FakeLib:
     # ---- UEG --------------------------------------------------------
     @staticmethod
     def _ueg(u):
-        u = u._obj
+        u = getattr(u, "_obj", u)          # byref(...) from the shim, or the struct itself
         nP = u.n_orb
         kvec = np.ctypeslib.as_array((C.c_int32 * (3 * nP)).from_address(u.kvec)).reshape(nP, 3)
         kp = _window(u.kp, 3 * nP).reshape(nP, 3)
@@ -312,13 +315,32 @@ class FakeLib:
             _window(_val(W1), nP * nP)[:] = w1.reshape(-1)
         return 0
 
+    def _generated(self, addr, m_ext, k_ext):
+        """A[M,K] of a generated operand (pmb_ueg_operand_t): the block pmb_ueg_build_block
+        would write, with its axes arranged as the M / K index groups (first listed fastest)."""
+        from pymes_b200 import _lib
+        g = _lib.UegOperand.from_address(addr)
+        axes = [g.m_axis[i] for i in range(len(m_ext))] + [g.k_axis[i] for i in range(len(k_ext))]
+        assert sorted(axes) == [0, 1, 2, 3]
+        ext = [0] * 4
+        for ax, e in zip(axes, list(m_ext) + list(k_ext)):
+            ext[ax] = e
+        blk = self._block(g.ueg, g.W0a, g.W1a, g.W0s, [g.lo[i] for i in range(4)], ext)
+        nm = len(m_ext)
+        order = axes[:nm][::-1] + axes[nm:][::-1]           # slowest first, M group then K group
+        M = int(np.prod(m_ext)) if m_ext else 1
+        return np.ascontiguousarray(blk.transpose(order)).reshape(M, -1).reshape(-1)
+
     def pmb_ueg_build_block(self, u, W0a, W1a, W0s, lo, ext, out, stream):
         self.launches += 1
+        blk = self._block(u, W0a, W1a, W0s, [lo[i] for i in range(4)], [ext[i] for i in range(4)])
+        _window(_val(out), blk.size)[:] = blk.reshape(-1)
+        return 0
+
+    def _block(self, u, W0a, W1a, W0s, lo, ext):
         u, nP, kvec, kp, imap, tab = self._ueg(u)
         get = lambda p: _window(_val(p), nP * nP).reshape(nP, nP) if _val(p) else None
         W0a, W1a, W0s = get(W0a), get(W1a), get(W0s)
-        lo = [lo[i] for i in range(4)]
-        ext = [ext[i] for i in range(4)]
         blk = np.zeros(ext)
         n = 2 * u.imax + 1
         for p in range(lo[0], lo[0] + ext[0]):
@@ -339,8 +361,7 @@ class FakeLib:
                     if W0s is not None:
                         w += 0.5 * (W0s[p, r] + W0s[q, s])
                     blk[p - lo[0], q - lo[1], r - lo[2], s - lo[3]] = w
-        _window(_val(out), blk.size)[:] = blk.reshape(-1)
-        return 0
+        return blk
 
 
 def install(monkeypatch):
@@ -360,6 +381,8 @@ def install(monkeypatch):
     monkeypatch.setattr(bk, "_device_key", lambda: "cpu-emulator")
 
     def asdev(x):
+        if isinstance(x, bk.GeneratedOperand):
+            return x
         if isinstance(x, torch.Tensor):
             return x.to(torch.float64)
         a = np.asarray(x, dtype=np.float64)

@@ -372,6 +372,89 @@ def test_ueg_tc_full_build_and_ccd():
     assert _rel(blocks["iajb"].cpu().numpy(), Vn[:7, 7:, :7, 7:]) < 1e-13
 
 
+def test_ueg_virtual_block_host_cases():
+    host.test_ueg_virtual_block_descriptor(None)
+
+
+def _tc_model(n_ele, cutoff, rs=0.5):
+    from pymes_b200.model import ueg
+    m = ueg.UEG(n_ele, n_ele // 2, n_ele // 2, rs)
+    m.init_single_basis(cutoff)
+    m.k_cutoff, m.gamma = 1.0, None
+    return m
+
+
+@pytest.mark.parametrize("n_ele,cutoff", [(14, 5.0), (14, 9.0), (54, 7.0)])
+def test_ueg_virtual_pp_ladder_bit_identical(n_ele, cutoff):
+    """Never-materialised V_abcd: the pp ladder with the operand generated in
+    the kernel's producer warps equals the ladder on the block pmb_ueg_build_block wrote --
+    bit for bit when both run the same (warp-specialised) kernel, because the generated tile
+    holds the very same doubles.  TC integrals (non-hermitian W1 term + symmetrised W0s)."""
+    from pymes_b200 import _lib, backend as bk
+    m = _tc_model(n_ele, cutoff)
+    no, nP = n_ele // 2, m.n_orb
+    nv = nP - no
+    parts = [("only_2b", m.trunc), ("effect_2b", m.trunc)]
+    virt = m.eval_2b_blocks(no, ["abcd"], parts, virtual=("abcd",))["abcd"]
+    dense = m.eval_2b_blocks(no, ["abcd"], parts)["abcd"]
+    assert torch.equal(virt.materialise(), dense) and float(dense.abs().max()) > 0
+    g = torch.Generator(device="cuda").manual_seed(1)
+    tau = torch.randn(nv, nv, no, no, dtype=torch.float64, device="cuda", generator=g)
+    lib = _lib.load()
+    try:
+        lib.pmb_contract_set_tuning(5, 0)
+        ref = bk.contract("abcd,cdij->abij", dense, tau)
+        got = bk.contract("abcd,cdij->abij", virt, tau)
+        assert torch.equal(got, ref)
+        lib.pmb_contract_set_tuning(6, 0)                 # 6-stage ring
+        assert torch.equal(bk.contract("abcd,cdij->abij", virt, tau), bk.contract("abcd,cdij->abij", dense, tau))
+        # split-K: partial sums of the generated operand
+        lib.pmb_contract_set_tuning(5, 3)
+        assert torch.equal(bk.contract("abcd,cdij->abij", virt, tau), bk.contract("abcd,cdij->abij", dense, tau))
+    finally:
+        lib.pmb_contract_set_tuning(-1, 0)
+    # default heuristics (the dense block may pick another tile shape): round-off only
+    ref = bk.contract("abcd,cdij->abij", dense, tau)
+    got = bk.contract("abcd,cdij->abij", virt, tau)
+    assert _rel(got.cpu().numpy(), ref.cpu().numpy()) < 1e-13
+    # against numpy on the host
+    want = dense.cpu().numpy().reshape(nv * nv, -1) @ tau.cpu().numpy().reshape(nv * nv, -1)
+    assert _rel(got.cpu().numpy().reshape(nv * nv, -1), want) < 1e-13
+    # one launch with the hh ladder as a second (memory) term, accumulated into R; row block
+    I = torch.randn(no, no, no, no, dtype=torch.float64, device="cuda", generator=g)
+    lo, na = nv // 3, nv - nv // 3 - 1
+    R0 = torch.randn(na, nv, no, no, dtype=torch.float64, device="cuda", generator=g)
+    Ra, Rb = R0.clone(), R0.clone()
+    taul = tau[lo:lo + na]
+    bk.contract_terms("abij", [(1.0, "klij", I, "abkl", taul), (0.5, "abcd", virt.rows(0, lo, na), "cdij", tau)],
+                      out=Ra, beta=1.0)
+    bk.contract_terms("abij", [(1.0, "klij", I, "abkl", taul), (0.5, "abcd", dense[lo:lo + na], "cdij", tau)],
+                      out=Rb, beta=1.0)
+    assert _rel(Ra.cpu().numpy(), Rb.cpu().numpy()) < 1e-13
+
+
+def test_ueg_virtual_abcd_ccsd_matches_dense():
+    """TC-UEG 14e CCSD with V_abcd never materialised == the same solve on dense blocks,
+    sweep by sweep (energies 1e-12, amplitudes 1e-11 relative)."""
+    from pymes_b200.integral.partition import KEYS
+    from pymes_b200.solver import ccsd
+    g = golden("ueg_tc")
+    m = _tc_model(14, 5.0)
+    m.k_cutoff = float(g["k_cutoff"])
+    parts = [("only_2b", m.trunc), ("effect_2b", m.trunc)]
+    dV = m.eval_2b_blocks(7, list(KEYS), parts)
+    dVv = dict(dV)
+    dVv["abcd"] = m.eval_2b_blocks(7, ["abcd"], parts, virtual=("abcd",))["abcd"]
+    a, b = ccsd.CCSD(7), ccsd.CCSD(7)
+    a.setup(g["fock"], dV)
+    b.setup(g["fock"], dVv)
+    for _ in range(6):
+        ea, eb = a.sweep(), b.sweep()
+        assert abs(sum(ea[:3]) - sum(eb[:3])) < 1e-12
+        assert _rel(b._st["T2"].cpu().numpy(), a._st["T2"].cpu().numpy()) < 1e-11
+        assert _rel(b._st["T1"].cpu().numpy(), a._st["T1"].cpu().numpy()) < 1e-11
+
+
 def test_umat_golden():
     from pymes_b200.model import ueg
     g = golden("ueg_tc")

@@ -298,6 +298,46 @@ def test_ueg_tc_tables_small(cpu_abi):
     np.testing.assert_allclose(m.triple_contractions_in_3_body(), g["zero_body"], rtol=1e-11)
 
 
+def test_ueg_virtual_block_descriptor(cpu_abi):
+    """Never-materialised V block as the row operand of a contraction (pmb_term_t.a_gen):
+    the descriptor's axis assignment for the pp ladder, a permuted o.v^3 pattern and a row
+    block reproduce the contraction with the dense block."""
+    from pymes_b200 import backend as bk
+    from pymes_b200.model import ueg
+    m = ueg.UEG(14, 7, 7, 0.5)
+    m.init_single_basis(2.0)
+    m.gamma, m.k_cutoff = None, 1.0
+    nP, no = m.n_orb, 7
+    nv = nP - no
+    W0a, W1a = m.pair_tables("only_non_hermi_2b", m.trunc)
+    W0s, _ = m.pair_tables("effect_2b", m.trunc)
+    rng = np.random.default_rng(3)
+    tau = _t(rng.standard_normal((nv, nv, no, no)))
+    virt = m.virtual_block((no,) * 4, (nv,) * 4, W0a=W0a, W1a=W1a, W0s=W0s)
+    dense = virt.materialise()
+    assert float(dense.abs().max()) > 0
+    ref = bk.contract("abcd,cdij->abij", dense, tau)
+    got = bk.contract("abcd,cdij->abij", virt, tau)
+    np.testing.assert_allclose(_n(got), _n(ref), rtol=0, atol=1e-13)
+    d, _, _ = bk.describe_contraction("abij", [(1.0, "abcd", virt, "cdij", tau)])
+    g = d._keep[0]
+    assert [g.m_axis[i] for i in range(2)] == [1, 0] and [g.k_axis[i] for i in range(2)] == [3, 2]
+    # row block of a (what one rank of a sharded run owns), accumulated into an existing R
+    part = virt.rows(0, 2, 3)
+    R = _t(rng.standard_normal((3, nv, no, no)))
+    want = _n(R) + np.einsum("abcd,cdij->abij", _n(dense)[2:5], _n(tau))
+    bk.contract_terms("abij", [(1.0, "abcd", part, "cdij", tau)], out=R, beta=1.0)
+    np.testing.assert_allclose(_n(R), want, rtol=0, atol=1e-13)
+    # o.v^3 block with the occupied index in the row group: "kbcd,cdij->kbij"
+    v2 = m.virtual_block((0, no, no, no), (no, nv, nv, nv), W0a=W0a, W1a=W1a, W0s=W0s)
+    got = bk.contract("kbcd,cdij->kbij", v2, tau)
+    np.testing.assert_allclose(_n(got), np.einsum("kbcd,cdij->kbij", _n(v2.materialise()), _n(tau)),
+                               rtol=0, atol=1e-13)
+    # a generated operand on the column side is refused, not silently mis-evaluated
+    with pytest.raises(ValueError, match="generated operand"):
+        bk.contract("abcd,cdij->abij", virt, tau, out=bk.empty(no, no, nv, nv).permute(2, 3, 0, 1))
+
+
 # --------------------------------------------------------------------------
 # EOM-CCSD: compiled sigma program, batching, diagonals, Davidson
 # --------------------------------------------------------------------------

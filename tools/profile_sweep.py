@@ -1,7 +1,7 @@
 """Per-contraction timing of ONE CCSD+DIIS sweep on the bench workload (TC-UEG 54e, N=1):
 every pmb_contract launch bracketed by CUDA events, grouped by index pattern.  Not a bench
 value (the extra events serialise nothing, but the run is a diagnostic, not the timed step).
-usage: profile_sweep.py [cutoff]"""
+usage: profile_sweep.py [cutoff] [dense]   (dense: store V_abcd instead of generating it)"""
 import collections
 import os
 import sys
@@ -22,7 +22,8 @@ m.init_single_basis(cutoff)
 m.k_cutoff, m.gamma = bench.K_CUTOFF, None
 fock = bench.build_fock(m, no)
 cc = ccsd.CCSD(no)
-dV = m.eval_2b_blocks(no, list(KEYS), bench.tc_parts(m))
+dense = len(sys.argv) > 2 and sys.argv[2] == "dense"
+dV = m.eval_2b_blocks(no, list(KEYS), bench.tc_parts(m), virtual=() if dense else ("abcd",))
 cc.setup(fock, dV)
 for _ in range(2):
     cc.sweep()
