@@ -193,6 +193,46 @@ def _fill(arr, vals):
         arr[i] = int(v)
 
 
+ALIGN_K_MIN_ELEMENTS = 1 << 16
+
+
+def _unit_index(sub, t):
+    """The index along which ``t`` is unit-stride (extent > 1), or None."""
+    for ch, n, st in zip(sub, t.shape, t.stride()):
+        if st == 1 and n > 1:
+            return ch
+    return None
+
+
+def _align_k(sa, A, sb, B):
+    """Both operands stream their tiles along the contracted (K) indices in ONE common order.
+    When each operand is unit-stride along a *different* contracted index (e.g.
+    ``abjk,jkcb->ac``: T2 runs along k, V_ijab along b), any order leaves one of them gathering
+    single 8-byte words out of 32-byte sectors, strides apart (measured: 3 TFLOP/s and 90 GB/s
+    on o.v^3-sized operands).  The smaller operand is then re-laid out once -- its contracted
+    indices in the other operand's order, innermost -- which costs one HBM-bound pass."""
+    if isinstance(A, GeneratedOperand) or isinstance(B, GeneratedOperand):
+        return sa, A, sb, B
+    ks = set(sa) & set(sb)
+    ua, ub = _unit_index(sa, A), _unit_index(sb, B)
+    if ua is None or ub is None or ua == ub or ua not in ks or ub not in ks:
+        return sa, A, sb, B
+    if min(A.numel(), B.numel()) < ALIGN_K_MIN_ELEMENTS:
+        return sa, A, sb, B                      # small enough to live in L2 either way
+
+    def relaid(s_small, small, s_big, big):
+        bstr = dict(zip(s_big, big.stride()))
+        k_ord = sorted((ch for ch in s_small if ch in ks), key=lambda ch: -bstr[ch])
+        new_sub = "".join(ch for ch in s_small if ch not in ks) + "".join(k_ord)
+        return new_sub, copy(small.permute(*[s_small.index(ch) for ch in new_sub]))
+
+    if B.numel() <= A.numel():
+        sb, B = relaid(sb, B, sa, A)
+    else:
+        sa, A = relaid(sa, A, sb, B)
+    return sa, A, sb, B
+
+
 def describe_contraction(out_sub, terms, out=None, beta=0.0, conv=None, alloc=None):
     """Build the ``pmb_contract_t`` descriptor for ``contract_terms`` (pure host logic:
     index classification, operand swaps, group ordering, strides).  Returns
@@ -208,6 +248,7 @@ def describe_contraction(out_sub, terms, out=None, beta=0.0, conv=None, alloc=No
         A, B = conv(A), conv(B)
         if A.dim() != len(sa) or B.dim() != len(sb):
             raise ValueError("subscripts %s,%s do not match operand ranks" % (sa, sb))
+        sa, A, sb, B = _align_k(sa, A, sb, B)
         for s, t in ((sa, A), (sb, B)):
             if len(set(s)) != len(s):
                 raise ValueError("repeated index in %s is not supported" % s)

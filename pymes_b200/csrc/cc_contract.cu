@@ -21,6 +21,9 @@
 //   * thread->element mapping of the loads follows the operand's unit-stride
 //     direction (x-fast or k-fast) so global accesses stay coalesced to full
 //     32 B sectors for any permutation.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "ueg_device.cuh"
 
@@ -62,6 +65,7 @@ struct Params {
     // generated A operand (never-materialised UEG integrals): term index or -1
     int gen_term;
     int gen_n3;                       // (2 imax + 1)^3, size of the index map
+    int gen_map_smem;                 // the index map is staged in shared memory
     int gen_l0;                       // imax (n^2 + n + 1)
     int gen_lo[4];
     int gen_m_axis[PMB_MAX_DIMS], gen_k_axis[PMB_MAX_DIMS];
@@ -97,17 +101,18 @@ __device__ __forceinline__ long long gen_decomp(const Params &p, int idx, int nd
     return e;
 }
 
-// the orbital the index map holds at this element's location (-1: none / outside the map)
-__device__ __forceinline__ int gen_sstar(const Params &p, long long e) {
+// Is the element described by word e non-zero?  `map` is the index map (shared-memory copy
+// when it fits, else global).
+__device__ __forceinline__ bool gen_hit(const Params &p, const int *map, long long e) {
     const int loc = (int)(e >> kGenLocShift);
-    return (unsigned)loc < (unsigned)p.gen_n3 ? __ldg(p.gen_ueg.index_map + loc) : -1;
+    const int sstar = (unsigned)loc < (unsigned)p.gen_n3 ? map[loc] : -1;
+    return sstar == ((int)e & kGenFieldMask);
 }
-// value of the element given that orbital: one element in n_orb is non-zero
-__device__ __forceinline__ double gen_value(const Params &p, long long e, int sstar) {
-    const int s = (int)e & kGenFieldMask;
-    if (sstar != s) return 0.0;
+// value of a non-zero element
+__device__ __forceinline__ double gen_value(const Params &p, long long e) {
     return ueg_value(p.gen_ueg, p.gen_W0a, p.gen_W1a, p.gen_W0s, (int)(e >> (3 * kGenFieldBits)) & kGenFieldMask,
-                     (int)(e >> (2 * kGenFieldBits)) & kGenFieldMask, (int)(e >> kGenFieldBits) & kGenFieldMask, s);
+                     (int)(e >> (2 * kGenFieldBits)) & kGenFieldMask, (int)(e >> kGenFieldBits) & kGenFieldMask,
+                     (int)e & kGenFieldMask);
 }
 
 __device__ __forceinline__ long long decomp(int idx, int nd, const int *ext,
@@ -533,6 +538,9 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
     long long *s_cn = s_cm + BM;                                // [BN]  C column offsets
     long long *s_am = s_cn + BN;                                // [nterms][BM]
     long long *s_bn = s_am + p.nterms * BM;                     // [nterms][BN]
+    // generated operand only: plane-wave vectors [3 n_orb] and the index map [gen_n3 + 1]
+    double *s_kp = reinterpret_cast<double *>(s_bn + p.nterms * BN);
+    int *s_map = reinterpret_cast<int *>(s_kp + 3 * p.gen_ueg.n_orb);
 
     const unsigned bar_base = (unsigned)__cvta_generic_to_shared(bars);
     const unsigned as_base = (unsigned)__cvta_generic_to_shared(As);
@@ -567,6 +575,11 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
         for (int i = tid; i < BN; i += NC + NP)
             s_bn[ti * BN + i] = (i < nrem) ? decomp(n0 + i, p.nn, p.n_ext, t.b_nstr) : 0;
     }
+    if (p.gen_term >= 0 && p.gen_map_smem) {
+        for (int i = tid; i <= p.gen_n3; i += NC + NP)
+            s_map[i] = i < p.gen_n3 ? __ldg(p.gen_ueg.index_map + i) : -1;   // [n3] = sentinel
+        for (int i = tid; i < 3 * p.gen_ueg.n_orb; i += NC + NP) s_kp[i] = __ldg(p.gen_ueg.kp + i);
+    }
     for (int i = tid; i < BM; i += NC + NP)
         s_cm[i] = (i < mrem) ? decomp(m0 + i, p.nm, p.m_ext, p.c_mstr) : 0;
     for (int i = tid; i < BN; i += NC + NP)
@@ -574,10 +587,10 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
-            // full[s]: every producer thread, once through its cp.async group and -- when a
-            // term has a generated operand -- once more by a plain (release) arrive that
-            // orders its st.shared tile writes before the consumers' reads
-            mbar_init(bar_base + s * 8, p.gen_term >= 0 ? 2 * NP : NP);
+            // full[s]: every producer thread through its cp.async group and -- when a term has
+            // a generated operand -- one plain (release) arrive per producer warp, which orders
+            // the warp's st.shared tile writes before the consumers' reads
+            mbar_init(bar_base + s * 8, p.gen_term >= 0 ? NP + NP / 32 : NP);
             mbar_init(bar_base + (STAGES + s) * 8, NCW);        // empty[s]: every consumer warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -609,6 +622,51 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
             }
         };
         koffs(kt_lo + pwarp);
+        // Generated operand, fast path (index map and plane-wave vectors staged in shared
+        // memory).  This thread owns row gx of the tile and every GKSTEP-th k (x-fast mapping:
+        // conflict-free stores).  One element in n_orb is non-zero, so a tile column is 16
+        // zero stores plus, now and then, one evaluated element -- whose four pair-table words
+        // sit in L2 behind the queue of this SM's own operand copies (measured: ~3000 cycles
+        // per load round trip).  The scan for tile g+1 therefore runs at the end of tile g and
+        // issues those loads; they are consumed one tile later, off the critical path.
+        constexpr int GKSTEP = NP / BM;
+        const bool gen_fast = p.gen_term >= 0 && p.gen_map_smem;
+        const int gx = ptid % BM, gk0 = ptid / BM;
+        const long long gem = p.gen_term >= 0 ? s_am[p.gen_term * BM + gx] : 0;
+        unsigned nx_hits = 0;          // bit `it`: element it of the next tile's column is non-zero
+        long long nx_e = 0;            // packed word of its first non-zero element
+        UegWords nx_w = {0.0, 0.0, 0.0, 0.0};
+        auto gen_scan = [&](int g) {
+            nx_hits = 0;
+            if (g >= kt_hi || term_of(g) != p.gen_term) return;
+            const TermDev &t = p.t[p.gen_term];
+            const long long *ko = s_k + ((g - kt_lo) & (KRING - 1)) * 2 * BK;
+            const int krem = t.K - (g - t.kt_begin) * BK;
+            // branch-free, in batches of 8: table words and map entries are independent loads
+            // (out-of-range locations read the -1 sentinel that ends the shared map)
+#pragma unroll
+            for (int h = 0; h < PER_A; h += 8) {
+                long long e[8];
+                int ss[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) e[j] = gem + ko[gk0 + (h + j) * GKSTEP];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    ss[j] = s_map[min((unsigned)(e[j] >> kGenLocShift), (unsigned)p.gen_n3)];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const bool hit = ss[j] == ((int)e[j] & kGenFieldMask) && gk0 + (h + j) * GKSTEP < krem;
+                    nx_hits |= (hit ? 1u : 0u) << (h + j);
+                }
+            }
+            if (nx_hits) {
+                nx_e = gem + ko[gk0 + (__ffs(nx_hits) - 1) * GKSTEP];
+                nx_w = ueg_load_words(p.gen_ueg.n_orb, p.gen_W0a, p.gen_W1a, p.gen_W0s,
+                                      (int)(nx_e >> (3 * kGenFieldBits)) & kGenFieldMask,
+                                      (int)(nx_e >> (2 * kGenFieldBits)) & kGenFieldMask,
+                                      (int)(nx_e >> kGenFieldBits) & kGenFieldMask, (int)nx_e & kGenFieldMask);
+            }
+        };
         int st = 0, batch = 0;
         unsigned empty_parity = 1;     // first pass over the ring: the stages are free
         for (int g = kt_lo; g < kt_hi; ++g) {
@@ -616,6 +674,7 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
                 koffs(g + TPB + pwarp);
                 producer_sync();
             }
+            if (gen_fast && g == kt_lo) gen_scan(g);       // prime the look-ahead
             batch = batch + 1 == TPB ? 0 : batch + 1;
             mbar_wait(bar_base + (STAGES + st) * 8, empty_parity);
             const int ti = term_of(g);
@@ -625,32 +684,53 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
             const Gat gb = make_gat<BN, NP>(bs_base + (unsigned)(st * BK * LDB * 8), t.B, s_bn + ti * BN,
                                             ko + BK, t.b_kfast != 0, ptid);
             if (ti == p.gen_term) {
-                // B first: its copies are in flight while the A tile is evaluated.  x-fast
-                // mapping (conflict-free stores): this thread owns row x and every KSTEP-th k.
+                // B first: its copies are in flight while the A tile is written
                 gat_issue_batched<PER_B, 8>(gb, krem);
-                constexpr int KSTEP = NP / BM;
-                const int x = ptid % BM, k0 = ptid / BM;
-                const long long em = s_am[ti * BM + x];
-                double *dst = As + st * BK * LDA + k0 * LDA + x;
-                // all index-map look-ups of the tile column first (independent loads), then
-                // the compare / rare evaluation and the stores
-                int ss[PER_A];
+                double *dst = As + st * BK * LDA + gk0 * LDA + gx;
+                if (gen_fast) {
+                    unsigned hits = nx_hits;               // scanned one tile ago
 #pragma unroll
-                for (int it = 0; it < PER_A; ++it) {
-                    const int k = k0 + it * KSTEP;
-                    ss[it] = k < krem ? gen_sstar(p, em + ko[k]) : -1;
+                    for (int it = 0; it < PER_A; ++it) dst[it * GKSTEP * LDA] = 0.0;
+                    if (hits) {
+                        const int it = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        dst[it * GKSTEP * LDA] =
+                            ueg_combine(nx_w, p.gen_W1a != nullptr, p.gen_W0s != nullptr, s_kp,
+                                        (int)(nx_e >> (3 * kGenFieldBits)) & kGenFieldMask,
+                                        (int)(nx_e >> kGenFieldBits) & kGenFieldMask, (int)nx_e & kGenFieldMask);
+                    }
+                    while (hits) {                         // a second one in the same column: rare
+                        const int it = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        dst[it * GKSTEP * LDA] = gen_value(p, gem + ko[gk0 + it * GKSTEP]);
+                    }
+                } else {
+                    // fallback (tables too large for shared memory): scan and evaluate in place
+                    unsigned hits = 0;
+#pragma unroll
+                    for (int it = 0; it < PER_A; ++it) {
+                        const int k = gk0 + it * GKSTEP;
+                        if (k < krem && gen_hit(p, p.gen_ueg.index_map, gem + ko[k])) hits |= 1u << it;
+                        dst[it * GKSTEP * LDA] = 0.0;
+                    }
+                    while (hits) {
+                        const int it = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        dst[it * GKSTEP * LDA] = gen_value(p, gem + ko[gk0 + it * GKSTEP]);
+                    }
                 }
-#pragma unroll
-                for (int it = 0; it < PER_A; ++it)
-                    dst[it * KSTEP * LDA] = gen_value(p, em + ko[k0 + it * KSTEP], ss[it]);
             } else {
                 const Gat ga = make_gat<BM, NP>(as_base + (unsigned)(st * BK * LDA * 8), t.A, s_am + ti * BM, ko,
                                                 t.a_kfast != 0, ptid);
                 gat_issue_batched<PER_A, 8>(ga, krem);
                 gat_issue_batched<PER_B, 8>(gb, krem);
             }
-            if (p.gen_term >= 0) mbar_arrive(bar_base + st * 8);
+            if (p.gen_term >= 0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_base + st * 8);
+            }
             cp_async_arrive(bar_base + st * 8);
+            if (gen_fast) gen_scan(g + 1);                 // tile g is published; look ahead
             if (++st == STAGES) {
                 st = 0;
                 empty_parity ^= 1;
@@ -837,19 +917,89 @@ constexpr size_t ws_smem_bytes(int nterms) {
            sizeof(long long) * ((size_t)kWsKRing * 2 * BK + (size_t)(nterms + 1) * (BM + BN));
 }
 
+constexpr size_t kMaxSmemOptin = 232448;   // 227 KB per CTA on sm_100
+
+// The pair tables of a generated operand are a few MB that every CTA keeps hitting at random
+// (W0s[q,s*] once per non-zero element) while GB-sized operands stream through L2 and push them
+// out: without help each hit is a DRAM round trip on the producers' critical path.  The launch
+// therefore carries an access-policy window that keeps the tables in the persisting part of L2.
+// PMB_GEN_L2_PERSIST=0 disables it (A/B measurements).
+static bool gen_l2_window(const Params &p, cudaStream_t s, bool on) {
+    static int enabled = -1;
+    static size_t max_window = 0;
+    if (enabled < 0) {
+        const char *e = getenv("PMB_GEN_L2_PERSIST");
+        enabled = !(e && e[0] == '0');
+        int dev = 0, max_persist = 0, max_win = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev) != cudaSuccess ||
+            max_persist <= 0 || max_win <= 0)
+            enabled = 0;
+        if (enabled) {
+            size_t want = 32u << 20;
+            if (want > (size_t)max_persist) want = (size_t)max_persist;
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) enabled = 0;
+            max_window = want < (size_t)max_win ? want : (size_t)max_win;
+        }
+        cudaGetLastError();
+    }
+    if (!enabled) return false;
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    if (on) {
+        const size_t tab = sizeof(double) * (size_t)p.gen_ueg.n_orb * (size_t)p.gen_ueg.n_orb;
+        const char *lo = nullptr, *hi = nullptr;
+        const double *tabs[3] = {p.gen_W0a, p.gen_W1a, p.gen_W0s};
+        for (const double *t : tabs) {
+            if (!t) continue;
+            const char *b = (const char *)t;
+            if (!lo || b < lo) lo = b;
+            if (!hi || b + tab > hi) hi = b + tab;
+        }
+        // one window: all tables when they were allocated side by side, else the randomly
+        // accessed one (W0s; W0a / W1a are read at CTA-uniform, slowly advancing addresses)
+        if (!lo || (size_t)(hi - lo) > max_window) {
+            lo = (const char *)(p.gen_W0s ? p.gen_W0s : p.gen_W0a);
+            hi = lo + tab;
+            if (tab > max_window) return false;
+        }
+        attr.accessPolicyWindow.base_ptr = const_cast<char *>(lo);
+        attr.accessPolicyWindow.num_bytes = (size_t)(hi - lo);
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    }
+    const bool ok = cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+    cudaGetLastError();
+    return ok;
+}
+
 template <int BM, int BN, int WMW, int WNW, int STAGES>
-static int launch_ws(const Params &p, dim3 grid, cudaStream_t s) {
+static int launch_ws(Params &p, dim3 grid, cudaStream_t s) {
     auto kern = contract_ws_kernel<BM, BN, WMW, WNW, STAGES>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)ws_smem_bytes<BM, BN, STAGES>(PMB_MAX_TERMS));
+                                             (int)kMaxSmemOptin);
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
-    kern<<<grid, WMW * WNW * 32 + kWsProducerThreads, ws_smem_bytes<BM, BN, STAGES>(p.nterms), s>>>(p);
+    size_t smem = ws_smem_bytes<BM, BN, STAGES>(p.nterms);
+    p.gen_map_smem = 0;
+    const size_t gen_extra = sizeof(double) * 3 * (size_t)p.gen_ueg.n_orb + sizeof(int) * ((size_t)p.gen_n3 + 1);
+    if (p.gen_term >= 0 && smem + gen_extra <= kMaxSmemOptin) {
+        // generated operand: the plane-wave vectors (12 KB at 515 orbitals) and the index map
+        // (8.8 KB at imax = 6) ride in shared memory
+        p.gen_map_smem = 1;
+        smem += gen_extra;
+    }
+    const bool window = p.gen_term >= 0 && gen_l2_window(p, s, true);
+    kern<<<grid, WMW * WNW * 32 + kWsProducerThreads, smem, s>>>(p);
     count_launch();
-    return cuda_status();
+    const int rc = cuda_status();
+    if (window) gen_l2_window(p, s, false);      // the launch has captured the attribute
+    return rc;
 }
 
 template <int BM, int BN, int WMW, int WNW, int STAGES, int MINB>
@@ -869,18 +1019,35 @@ static bool prod_fits(const int64_t *ext, int n, int64_t *out) {
     return true;
 }
 
-static int choose_cfg(int64_t M, int64_t N) {
-    if (g_force_cfg >= 0 && (g_force_cfg & 7) < kNumCfg) return g_force_cfg & 7;
+// Split-K factor for `tiles` output tiles on `slots` co-resident CTA slots: skinny outputs
+// with a long k (I_klij, Fock-like terms, o.v^3 blocks against T1) get enough CTAs to fill the
+// machine; outputs that already fill it are never split (the workspace would be output-sized).
+static int split_for(int64_t tiles, int64_t slots, int kt) {
+    if (tiles >= slots || kt < 8) return 1;
+    int64_t n = slots / tiles;
+    if (n > kt / 4) n = kt / 4;
+    if (n > 192) n = 192;
+    return n < 1 ? 1 : (int)n;
+}
+
+// Tile configuration by a cost model: time ~ waves x (CTAs sharing an SM) x tile area / (rate
+// of the configuration x split-K factor), i.e. padded work over the part of the machine the
+// launch can actually fill.
+static int choose_cfg(int64_t M, int64_t N, int kt, int *nsplit) {
     int best = 0;
     double best_cost = 1e300;
     for (int c = 0; c < kNumCfg; ++c) {
-        const double tiles = (double)((M + kCfg[c].bm - 1) / kCfg[c].bm) * (double)((N + kCfg[c].bn - 1) / kCfg[c].bn);
-        const double per_sm = (kCfg[c].threads == 128) ? 3.0 : 1.0;  // co-resident CTAs
-        const double waves = (double)(int64_t)((tiles + kSmCount * per_sm - 1) / (kSmCount * per_sm));
-        const double cost = waves * per_sm * kCfg[c].bm * kCfg[c].bn / kCfg[c].eff;
+        if (g_force_cfg >= 0 && (g_force_cfg & 7) < kNumCfg && c != (g_force_cfg & 7)) continue;
+        const int64_t tiles = ((M + kCfg[c].bm - 1) / kCfg[c].bm) * ((N + kCfg[c].bn - 1) / kCfg[c].bn);
+        const int per_sm = (kCfg[c].threads == 128) ? 3 : 1;   // co-resident CTAs
+        const int64_t slots = (int64_t)kSmCount * per_sm;
+        const int split = split_for(tiles, slots, kt);
+        const double waves = (double)((tiles * split + slots - 1) / slots);
+        const double cost = waves * per_sm * kCfg[c].bm * kCfg[c].bn / (kCfg[c].eff * split);
         if (cost < best_cost * 0.999) {
             best_cost = cost;
             best = c;
+            *nsplit = split;
         }
     }
     return best;
@@ -908,6 +1075,10 @@ static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
     int kt = 0;
     int nkeep = 0;
     p.gen_term = -1;
+    p.gen_n3 = p.gen_l0 = p.gen_map_smem = 0;
+    memset(&p.gen_ueg, 0, sizeof(p.gen_ueg));
+    p.gen_W0a = p.gen_W1a = p.gen_W0s = nullptr;
+    p.gen_lin = nullptr;
     for (int ti = 0; ti < d->nterms; ++ti) {
         const pmb_term_t &s = d->terms[ti];
         if ((!s.A && !s.a_gen) || !s.B || s.nk < 0 || s.nk > PMB_MAX_DIMS) return PMB_E_BADARG;
@@ -979,25 +1150,16 @@ static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
     }
     p.nterms = nkeep;
     p.total_ktiles = kt;
-    cfg = choose_cfg(M, N);
+    int nsplit = 1;
+    cfg = choose_cfg(M, N, kt, &nsplit);
     // only the warp-specialised kernel has producer warps that can evaluate an operand
-    if (p.gen_term >= 0 && cfg < 5) cfg = 5;
+    if (p.gen_term >= 0 && cfg < 5) {
+        cfg = 5;
+        nsplit = split_for((int64_t)((M + 127) / 128) * ((N + 127) / 128), kSmCount, kt);
+    }
     p.tiles_m = (int)((M + kCfg[cfg].bm - 1) / kCfg[cfg].bm);
     p.tiles_n = (int)((N + kCfg[cfg].bn - 1) / kCfg[cfg].bn);
-    // split-K when the output has too few tiles to fill the machine
-    int nsplit = 1;
-    const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
-    if (g_force_split > 0) {
-        nsplit = g_force_split;
-    } else if (tiles * 2 <= kSmCount && kt >= 8) {
-        // enough CTAs for every SM to hold its co-resident complement (3 for the 128-thread
-        // tiles): skinny outputs with a long k (Fock-like terms, o.v^3 blocks against T1) are
-        // HBM-bound and need the bytes in flight of several CTAs per SM
-        const int64_t slots = (int64_t)kSmCount * (kCfg[cfg].threads == 128 ? 3 : 1);
-        nsplit = (int)((slots + tiles - 1) / tiles);
-        if (nsplit > kt / 4) nsplit = kt / 4;
-        if (nsplit > 192) nsplit = 192;
-    }
+    if (g_force_split > 0) nsplit = g_force_split;
     if (nsplit > kt) nsplit = kt;
     if (nsplit < 1) nsplit = 1;
     p.ktiles_per_split = (kt + nsplit - 1) / nsplit;

@@ -7,28 +7,51 @@
 
 namespace pmb {
 
+// The four table words of one element; issued together, consumed by ueg_combine.  The
+// contraction kernel's producers load them one tile ahead of their use.
+struct UegWords {
+    double w0, w1, s0, s1;
+};
+__device__ __forceinline__ UegWords ueg_load_words(int nP, const double *__restrict__ W0a,
+                                                   const double *__restrict__ W1a, const double *__restrict__ W0s,
+                                                   int p, int q, int r, int s) {
+    const int pr = p * nP + r;
+    UegWords w = {0.0, 0.0, 0.0, 0.0};
+    if (W0a) w.w0 = __ldg(W0a + pr);
+    if (W1a) w.w1 = __ldg(W1a + pr);
+    if (W0s) {
+        w.s0 = __ldg(W0s + pr);
+        w.s1 = __ldg(W0s + q * nP + s);
+    }
+    return w;
+}
+
+// V[p,q,r,s] from its table words; kp = [nP][3] plane-wave vectors (global or a shared copy).
+// Every value is consumed unconditionally (the conditions are selects, not branches) so the
+// compiler cannot sink a load behind another load's result.
+__device__ __forceinline__ double ueg_combine(const UegWords &t, bool has_w1, bool has_sym, const double *kp,
+                                              int p, int r, int s) {
+    double dot = 0.0;
+    if (has_w1) {
+        const double rx = kp[3 * r], ry = kp[3 * r + 1], rz = kp[3 * r + 2];
+        const double dx = __dsub_rn(rx, kp[3 * p]), dy = __dsub_rn(ry, kp[3 * p + 1]), dz = __dsub_rn(rz, kp[3 * p + 2]);
+        const double ex = __dsub_rn(rx, kp[3 * s]), ey = __dsub_rn(ry, kp[3 * s + 1]), ez = __dsub_rn(rz, kp[3 * s + 2]);
+        dot = __fma_rn(ez, dz, __fma_rn(ey, dy, __dmul_rn(ex, dx)));
+    }
+    const double f = __fma_rn(t.w1, dot, t.w0);
+    double w = (t.w1 != 0.0) ? f : t.w0;         // reference: the term exists only where w1 != 0
+    const double sym = __dadd_rn(w, __dmul_rn(0.5, __dadd_rn(t.s0, t.s1)));
+    if (has_sym) w = sym;
+    return w;
+}
+
 // V[p,q,r,s] for s = s*(p,q,r), reference pymes/model/ueg.py:411-513:
 //   W0a[p,r] + W1a[p,r] * (k_r - k_s).(k_r - k_p) + 1/2 (W0s[p,r] + W0s[q,s])
 __device__ __forceinline__ double ueg_value(const pmb_ueg_t &u, const double *__restrict__ W0a,
                                             const double *__restrict__ W1a, const double *__restrict__ W0s,
                                             int p, int q, int r, int s) {
-    const int nP = u.n_orb;
-    const int pr = p * nP + r;
-    double w = 0.0;
-    if (W0a) w = W0a[pr];
-    if (W1a) {
-        const double w1 = W1a[pr];
-        if (w1 != 0.0) {
-            const double dx = __dsub_rn(u.kp[3 * r], u.kp[3 * p]), dy = __dsub_rn(u.kp[3 * r + 1], u.kp[3 * p + 1]),
-                         dz = __dsub_rn(u.kp[3 * r + 2], u.kp[3 * p + 2]);
-            const double ex = __dsub_rn(u.kp[3 * r], u.kp[3 * s]), ey = __dsub_rn(u.kp[3 * r + 1], u.kp[3 * s + 1]),
-                         ez = __dsub_rn(u.kp[3 * r + 2], u.kp[3 * s + 2]);
-            const double dot = __fma_rn(ez, dz, __fma_rn(ey, dy, __dmul_rn(ex, dx)));
-            w = __fma_rn(w1, dot, w);
-        }
-    }
-    if (W0s) w = __dadd_rn(w, __dmul_rn(0.5, __dadd_rn(W0s[pr], W0s[q * nP + s])));
-    return w;
+    const UegWords t = ueg_load_words(u.n_orb, W0a, W1a, W0s, p, q, r, s);
+    return ueg_combine(t, W1a != nullptr, W0s != nullptr, u.kp, p, r, s);
 }
 
 }  // namespace pmb

@@ -367,12 +367,20 @@ class VirtualBlock(bk.GeneratedOperand):
     (``include/pymes_b200.h: pmb_ueg_operand_t``).  Usable as the row operand of a
     contraction, e.g. the particle-particle ladder ``abcd,cdij->abij`` (ccd.py:187)."""
 
-    def __init__(self, model, lo, ext, W0a=None, W1a=None, W0s=None):
+    def __init__(self, model, lo, ext, W0a=None, W1a=None, W0s=None, _packed=False):
         if W0a is None and W0s is None:
             raise ValueError("a virtual block needs pair tables (W0a and/or W0s)")
         if model.n_orb > 2047 or model.imax > 27:
             raise ValueError("generated operands support n_orb <= 2047 and imax <= 27")
         self.model, self.lo, self.shape = model, tuple(int(x) for x in lo), tuple(int(x) for x in ext)
+        if not _packed:
+            # the tables side by side in one allocation: one L2 access-policy window covers them
+            given = [t for t in (W0a, W1a, W0s) if t is not None]
+            pack = bk.empty(len(given), model.n_orb * model.n_orb)
+            for row, t in zip(pack, given):
+                row.copy_(t.reshape(-1))
+            rows = iter(pack)
+            W0a, W1a, W0s = (next(rows) if t is not None else None for t in (W0a, W1a, W0s))
         self.tables = (W0a, W1a, W0s)
         st = model._device_state()
         if "lin" not in st:
@@ -387,7 +395,7 @@ class VirtualBlock(bk.GeneratedOperand):
         new_lo, new_ext = list(self.lo), list(self.shape)
         new_lo[dim] += int(lo)
         new_ext[dim] = int(n)
-        return VirtualBlock(self.model, new_lo, new_ext, *self.tables)
+        return VirtualBlock(self.model, new_lo, new_ext, *self.tables, _packed=True)
 
     def materialise(self):
         """The dense tensor (tests / small systems)."""

@@ -49,6 +49,10 @@ def test_multi_operand_einsum():
     host.test_multi_operand_einsum(None)
 
 
+def test_contract_realigns_conflicting_unit_strides(monkeypatch):
+    host.test_contract_realigns_conflicting_unit_strides(None, monkeypatch)
+
+
 @pytest.mark.parametrize("tag", ["a", "b"])
 def test_ccd_residual_energy_mp2(tag):
     host.test_ccd_residual_energy_mp2(None, tag)

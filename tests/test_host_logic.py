@@ -298,6 +298,28 @@ def test_ueg_tc_tables_small(cpu_abi):
     np.testing.assert_allclose(m.triple_contractions_in_3_body(), g["zero_body"], rtol=1e-11)
 
 
+def test_contract_realigns_conflicting_unit_strides(cpu_abi, monkeypatch):
+    """``abjk,jkcb->ac`` (dressed Fock, ccsd.py:264) and ``ajbc,bcij->ai`` (singles residual,
+    ccsd.py:433): the operands are unit-stride along different contracted indices; the
+    smaller one is re-laid out so that both stream along K -- same numbers."""
+    from pymes_b200 import backend as bk
+    monkeypatch.setattr(bk, "ALIGN_K_MIN_ELEMENTS", 0)
+    rng = np.random.default_rng(11)
+    no, nv = 3, 5
+    T2 = rng.standard_normal((nv, nv, no, no))
+    V = rng.standard_normal((no, no, nv, nv))
+    W = rng.standard_normal((nv, no, nv, nv))
+    for spec, A, B in (("abjk,jkcb->ac", T2, V), ("ajbc,bcij->ai", W, T2)):
+        sa, sb = spec.split("->")[0].split(",")
+        a2, A2, b2, B2 = bk._align_k(sa, _t(A), sb, _t(B))
+        assert (a2, b2) != (sa, sb)                       # one operand was re-laid out
+        ks = set(sa) & set(sb)
+        assert bk._unit_index(a2, A2) == bk._unit_index(b2, B2) and bk._unit_index(a2, A2) in ks
+        np.testing.assert_allclose(_n(bk.contract(spec, _t(A), _t(B))), np.einsum(spec, A, B), **TOL)
+    # nothing to do when one operand's unit-stride index is an output index
+    assert bk._align_k("abcd", _t(rng.standard_normal((4, 4, 4, 4))), "cdij", _t(T2[:4, :4]))[0] == "abcd"
+
+
 def test_ueg_virtual_block_descriptor(cpu_abi):
     """Never-materialised V block as the row operand of a contraction (pmb_term_t.a_gen):
     the descriptor's axis assignment for the pp ladder, a permuted o.v^3 pattern and a row
