@@ -104,8 +104,10 @@ typedef struct {
 size_t pmb_contract_workspace(const pmb_contract_t *d);
 int pmb_contract(const pmb_contract_t *d, void *ws, size_t ws_bytes,
                  pmb_stream_t stream);
-/* tuning/diagnostic knobs: force a tile configuration (-1 = heuristic) and   */
-/* a split-K factor (0 = heuristic).                                         */
+/* tuning/diagnostic knobs: force a tile configuration (-1 = heuristic; bits   */
+/* 0-2 the configuration, +8 flips the copy interleaving, +16 makes generated  */
+/* operands use the scanning producer instead of the non-zero walker) and      */
+/* a split-K factor (0 = heuristic).                                          */
 void pmb_contract_set_tuning(int tile_config, int split_k);
 /* L2 budget (bytes) for one operand's k window; contractions whose smaller      */
 /* operand exceeds it are issued as a fixed-order sequence of k-window launches */
@@ -261,6 +263,14 @@ int pmb_ueg_umat(const pmb_ueg_t *u, double box_len, int cutoff, int nq,
 int pmb_ueg_pair_tables(const pmb_ueg_t *u, int mode, const double *umat_pr,
                         double *W0, double *W1, pmb_stream_t stream);
 
+/* Momentum-compressed block: out[np][nq][nr] = V[p,q,r,s*(p,q,r)] if s* lies in  */
+/* [lo[3], lo[3]+ext[3]), else 0 -- the one candidate non-zero of every dense    */
+/* row, same formula and rounding as pmb_ueg_build_block (ext[3] / 1 smaller:     */
+/* 0.93 GB instead of 454 GB for V_abcd at 515 orbitals).  8 B per element.       */
+int pmb_ueg_build_nz(const pmb_ueg_t *u, const double *W0a, const double *W1a,
+                     const double *W0s, const int32_t lo[4], const int32_t ext[4],
+                     double *out, pmb_stream_t stream);
+
 /* Dense block out[np][nq][nr][ns] of V for p in [lo[0], lo[0]+ext[0]) etc.    */
 /* W1a and W0s may be NULL.                                                    */
 int pmb_ueg_build_block(const pmb_ueg_t *u, const double *W0a, const double *W1a,
@@ -291,6 +301,11 @@ typedef struct pmb_ueg_operand {
     const double *W1a;        /*   (W1a, W0s may be NULL)                      */
     const double *W0s;
     const int32_t *lin;       /* [nP] n^2 kx + n ky + kz, n = 2 imax + 1 (dev) */
+    /* optional compressed values from pmb_ueg_build_nz for this very block:     */
+    /* nz[(p-lo0, q-lo1, r-lo2)] = V[p,q,r,s*].  With it the producers only LOOK */
+    /* UP the non-zero elements (no FP64 arithmetic next to the DMMA stream, one */
+    /* load requested tiles ahead); NULL: they evaluate the formula in place.    */
+    const double *nz;
     int32_t lo[4];
     int32_t m_axis[PMB_MAX_DIMS];
     int32_t k_axis[PMB_MAX_DIMS];

@@ -46,7 +46,8 @@ class Ueg(C.Structure):
 
 class UegOperand(C.Structure):
     _fields_ = [("ueg", Ueg), ("W0a", C.c_void_p), ("W1a", C.c_void_p), ("W0s", C.c_void_p),
-                ("lin", C.c_void_p), ("lo", I32x4), ("m_axis", I32x4), ("k_axis", I32x4)]
+                ("lin", C.c_void_p), ("nz", C.c_void_p), ("lo", I32x4), ("m_axis", I32x4),
+                ("k_axis", I32x4)]
 
 
 _SIGS = {
@@ -83,6 +84,8 @@ _SIGS = {
                                C.c_void_p]),
     "pmb_ueg_pair_tables": (C.c_int, [C.POINTER(Ueg), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p]),
+    "pmb_ueg_build_nz": (C.c_int, [C.POINTER(Ueg), C.c_void_p, C.c_void_p, C.c_void_p, I32x4, I32x4,
+                                   C.c_void_p, C.c_void_p]),
     "pmb_ueg_build_block": (C.c_int, [C.POINTER(Ueg), C.c_void_p, C.c_void_p, C.c_void_p, I32x4, I32x4,
                                       C.c_void_p, C.c_void_p]),
 }

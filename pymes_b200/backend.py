@@ -89,7 +89,8 @@ def _stream():
 
 
 def _device_key():
-    return torch.cuda.current_device()
+    """Scratch buffers are per (device, stream): launches on different streams may overlap."""
+    return (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
 
 
 def _ptr(t):
@@ -177,6 +178,43 @@ def timing_report():
     """{tag: [milliseconds per recorded region]} (synchronises the device)."""
     torch.cuda.synchronize()
     return {tag: [a.elapsed_time(b) for a, b in ev] for tag, ev in _timing["events"].items()}
+
+
+# --------------------------------------------------------------------------
+# two independent launch sequences side by side
+# --------------------------------------------------------------------------
+_side_streams = {}
+
+
+class side_by_side:
+    """``with side_by_side() as side: main work; side(lambda: other work)`` -- runs ``other
+    work`` on a second CUDA stream, ordered after everything already queued on the current
+    stream, and joins it on exit.  For pairs of independent contractions whose grids are only
+    a few waves long (W1 = V_iabc.tau, W2 = V_aibc.tau: 4.2 waves each): the second kernel's
+    CTAs fill the SMs the first one's last partial wave leaves idle.  Every tensor the side
+    work touches must be allocated beforehand (pass ``out=``): the caching allocator is
+    per stream."""
+
+    def __enter__(self):
+        dev = _device_key()
+        if dev not in _side_streams:
+            _side_streams[dev] = torch.cuda.Stream() if torch.cuda.is_available() else None
+        self.side = _side_streams[dev]
+        self.main = torch.cuda.current_stream() if self.side is not None else None
+        if self.side is not None:
+            self.side.wait_stream(self.main)
+        return self._run
+
+    def _run(self, fn):
+        if self.side is None:                 # host-logic tests without a device
+            return fn()
+        with torch.cuda.stream(self.side):
+            return fn()
+
+    def __exit__(self, *exc):
+        if self.side is not None:
+            self.main.wait_stream(self.side)
+        return False
 
 
 # --------------------------------------------------------------------------

@@ -65,13 +65,16 @@ struct Params {
     // generated A operand (never-materialised UEG integrals): term index or -1
     int gen_term;
     int gen_n3;                       // (2 imax + 1)^3, size of the index map
-    int gen_map_smem;                 // the index map is staged in shared memory
+    int gen_map_smem;                 // index map, plane-wave vectors and lin[] staged in shared memory
+    int gen_walk;                     // K = (s fastest, r): producers walk the non-zeros directly
     int gen_l0;                       // imax (n^2 + n + 1)
     int gen_lo[4];
     int gen_m_axis[PMB_MAX_DIMS], gen_k_axis[PMB_MAX_DIMS];
     pmb_ueg_t gen_ueg;
     const double *gen_W0a, *gen_W1a, *gen_W0s;
     const int *gen_lin;
+    const double *gen_nz;             // compressed values [ext_p][ext_q][ext_r] or NULL
+    int gen_ext[4];                   // block extents along (p, q, r, s)
 };
 
 // Generated operand: table entries are not element offsets but packed 64-bit words
@@ -108,8 +111,16 @@ __device__ __forceinline__ bool gen_hit(const Params &p, const int *map, long lo
     const int sstar = (unsigned)loc < (unsigned)p.gen_n3 ? map[loc] : -1;
     return sstar == ((int)e & kGenFieldMask);
 }
+// position of element (p,q,r,.) in the compressed value table
+__device__ __forceinline__ long long gen_nz_index(const Params &p, int op, int oq, int orr) {
+    return ((long long)(op - p.gen_lo[0]) * p.gen_ext[1] + (oq - p.gen_lo[1])) * p.gen_ext[2] + (orr - p.gen_lo[2]);
+}
 // value of a non-zero element
 __device__ __forceinline__ double gen_value(const Params &p, long long e) {
+    if (p.gen_nz)
+        return __ldg(p.gen_nz + gen_nz_index(p, (int)(e >> (3 * kGenFieldBits)) & kGenFieldMask,
+                                             (int)(e >> (2 * kGenFieldBits)) & kGenFieldMask,
+                                             (int)(e >> kGenFieldBits) & kGenFieldMask));
     return ueg_value(p.gen_ueg, p.gen_W0a, p.gen_W1a, p.gen_W0s, (int)(e >> (3 * kGenFieldBits)) & kGenFieldMask,
                      (int)(e >> (2 * kGenFieldBits)) & kGenFieldMask, (int)(e >> kGenFieldBits) & kGenFieldMask,
                      (int)e & kGenFieldMask);
@@ -541,6 +552,7 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
     // generated operand only: plane-wave vectors [3 n_orb] and the index map [gen_n3 + 1]
     double *s_kp = reinterpret_cast<double *>(s_bn + p.nterms * BN);
     int *s_map = reinterpret_cast<int *>(s_kp + 3 * p.gen_ueg.n_orb);
+    int *s_lin = s_map + p.gen_n3 + 1;                           // [n_orb]
 
     const unsigned bar_base = (unsigned)__cvta_generic_to_shared(bars);
     const unsigned as_base = (unsigned)__cvta_generic_to_shared(As);
@@ -579,6 +591,7 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
         for (int i = tid; i <= p.gen_n3; i += NC + NP)
             s_map[i] = i < p.gen_n3 ? __ldg(p.gen_ueg.index_map + i) : -1;   // [n3] = sentinel
         for (int i = tid; i < 3 * p.gen_ueg.n_orb; i += NC + NP) s_kp[i] = __ldg(p.gen_ueg.kp + i);
+        for (int i = tid; i < p.gen_ueg.n_orb; i += NC + NP) s_lin[i] = __ldg(p.gen_lin + i);
     }
     for (int i = tid; i < BM; i += NC + NP)
         s_cm[i] = (i < mrem) ? decomp(m0 + i, p.nm, p.m_ext, p.c_mstr) : 0;
@@ -661,12 +674,61 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
             }
             if (nx_hits) {
                 nx_e = gem + ko[gk0 + (__ffs(nx_hits) - 1) * GKSTEP];
-                nx_w = ueg_load_words(p.gen_ueg.n_orb, p.gen_W0a, p.gen_W1a, p.gen_W0s,
-                                      (int)(nx_e >> (3 * kGenFieldBits)) & kGenFieldMask,
-                                      (int)(nx_e >> (2 * kGenFieldBits)) & kGenFieldMask,
-                                      (int)(nx_e >> kGenFieldBits) & kGenFieldMask, (int)nx_e & kGenFieldMask);
+                const int op = (int)(nx_e >> (3 * kGenFieldBits)) & kGenFieldMask,
+                          oq = (int)(nx_e >> (2 * kGenFieldBits)) & kGenFieldMask,
+                          orr = (int)(nx_e >> kGenFieldBits) & kGenFieldMask;
+                if (p.gen_nz)
+                    nx_w.w0 = ueg_ld<true>(p.gen_nz + gen_nz_index(p, op, oq, orr));
+                else
+                    nx_w = ueg_load_words<true>(p.gen_ueg.n_orb, p.gen_W0a, p.gen_W1a, p.gen_W0s, op, oq, orr,
+                                                (int)nx_e & kGenFieldMask);
             }
         };
+        // Walker (the pp ladder and every other contraction over K = (r, s) with s fastest):
+        // for a row (p, q) the non-zeros are one per r, at s = s*(p, q, r), i.e. at the
+        // increasing K positions r_l * ext_s + (s* - lo_s).  Instead of testing all 16 elements
+        // of every tile column, the thread keeps the position of its NEXT non-zero: a tile costs
+        // 16 zero stores and one compare, and the pair-table words of a non-zero are requested
+        // when the previous one is placed -- ext_s / 16 tiles before they are needed.
+        static_assert(GKSTEP == 1, "the walker owns whole tile columns");
+        const bool gen_walk = gen_fast && p.gen_walk;
+        const int wk_ext_s = gen_walk ? p.t[p.gen_term].k_ext[0] : 1;
+        const int wk_ext_r = gen_walk ? p.t[p.gen_term].k_ext[1] : 0;
+        const int wk_loc = (int)(gem >> kGenLocShift);      // L0 + L(p) + L(q) of this row
+        const int wk_p = (int)(gem >> (3 * kGenFieldBits)) & kGenFieldMask;
+        const int wk_q = (int)(gem >> (2 * kGenFieldBits)) & kGenFieldMask;
+        const double *wk_nz = p.gen_nz ? p.gen_nz + gen_nz_index(p, wk_p, wk_q, p.gen_lo[2]) : nullptr;
+        int wk_c = 0;                  // next local r to examine
+        int wk_k = 0x7fffffff;         // local K position of the pending non-zero (none: INT_MAX)
+        int wk_r = 0, wk_s = 0;        // its r and s orbitals
+        UegWords wk_w = {0.0, 0.0, 0.0, 0.0};
+        auto wk_advance = [&]() {
+            wk_k = 0x7fffffff;
+            while (wk_c < wk_ext_r) {
+                const int c = wk_c++;
+                const int r = p.gen_lo[2] + c;
+                const int sst = s_map[min((unsigned)(wk_loc - s_lin[r]), (unsigned)p.gen_n3)];
+                const int sl = sst - p.gen_lo[3];
+                if (sst >= 0 && (unsigned)sl < (unsigned)wk_ext_s) {
+                    wk_k = c * wk_ext_s + sl;
+                    wk_r = r;
+                    wk_s = sst;
+                    if (p.gen_nz)
+                        wk_w.w0 = ueg_ld<true>(wk_nz + c);
+                    else
+                        wk_w = ueg_load_words<true>(p.gen_ueg.n_orb, p.gen_W0a, p.gen_W1a, p.gen_W0s, wk_p, wk_q, r,
+                                                    sst);
+                    break;
+                }
+            }
+        };
+        if (gen_walk && gx < mrem) {
+            // first K position this CTA covers inside the generated term (split-K / multi-term)
+            const int kstart = max(kt_lo - p.t[p.gen_term].kt_begin, 0) * BK;
+            wk_c = kstart / wk_ext_s;
+            wk_advance();
+            while (wk_k < kstart) wk_advance();
+        }
         int st = 0, batch = 0;
         unsigned empty_parity = 1;     // first pass over the ring: the stages are free
         for (int g = kt_lo; g < kt_hi; ++g) {
@@ -674,7 +736,7 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
                 koffs(g + TPB + pwarp);
                 producer_sync();
             }
-            if (gen_fast && g == kt_lo) gen_scan(g);       // prime the look-ahead
+            if (gen_fast && !gen_walk && g == kt_lo) gen_scan(g);       // prime the look-ahead
             batch = batch + 1 == TPB ? 0 : batch + 1;
             mbar_wait(bar_base + (STAGES + st) * 8, empty_parity);
             const int ti = term_of(g);
@@ -687,7 +749,18 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
                 // B first: its copies are in flight while the A tile is written
                 gat_issue_batched<PER_B, 8>(gb, krem);
                 double *dst = As + st * BK * LDA + gk0 * LDA + gx;
-                if (gen_fast) {
+                if (gen_walk) {
+                    const int kbase = (g - t.kt_begin) * BK;
+#pragma unroll
+                    for (int it = 0; it < PER_A; ++it) dst[it * LDA] = 0.0;
+                    while (wk_k < kbase + BK) {
+                        dst[(wk_k - kbase) * LDA] =
+                            p.gen_nz ? wk_w.w0
+                                     : ueg_combine(wk_w, p.gen_W1a != nullptr, p.gen_W0s != nullptr, s_kp, wk_p,
+                                                   wk_r, wk_s);
+                        wk_advance();
+                    }
+                } else if (gen_fast) {
                     unsigned hits = nx_hits;               // scanned one tile ago
 #pragma unroll
                     for (int it = 0; it < PER_A; ++it) dst[it * GKSTEP * LDA] = 0.0;
@@ -695,9 +768,11 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
                         const int it = __ffs(hits) - 1;
                         hits &= hits - 1;
                         dst[it * GKSTEP * LDA] =
-                            ueg_combine(nx_w, p.gen_W1a != nullptr, p.gen_W0s != nullptr, s_kp,
-                                        (int)(nx_e >> (3 * kGenFieldBits)) & kGenFieldMask,
-                                        (int)(nx_e >> kGenFieldBits) & kGenFieldMask, (int)nx_e & kGenFieldMask);
+                            p.gen_nz ? nx_w.w0
+                                     : ueg_combine(nx_w, p.gen_W1a != nullptr, p.gen_W0s != nullptr, s_kp,
+                                                   (int)(nx_e >> (3 * kGenFieldBits)) & kGenFieldMask,
+                                                   (int)(nx_e >> kGenFieldBits) & kGenFieldMask,
+                                                   (int)nx_e & kGenFieldMask);
                     }
                     while (hits) {                         // a second one in the same column: rare
                         const int it = __ffs(hits) - 1;
@@ -730,7 +805,7 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
                 if (lane == 0) mbar_arrive(bar_base + st * 8);
             }
             cp_async_arrive(bar_base + st * 8);
-            if (gen_fast) gen_scan(g + 1);                 // tile g is published; look ahead
+            if (gen_fast && !gen_walk) gen_scan(g + 1);    // tile g is published; look ahead
             if (++st == STAGES) {
                 st = 0;
                 empty_parity ^= 1;
@@ -880,6 +955,7 @@ static const TileCfg kCfg[] = {
     {128, 128, 384, 1.30}, {128, 128, 384, 1.00}};
 constexpr int kNumCfg = 7;
 
+static int g_gen_no_walk = 0;      // tuning bit 16: generated operands use the scanning producer
 static int g_force_cfg = -1;
 static int g_force_split = 0;
 // L2 budget for one operand's k window (0 = no windows).  The warp-specialised kernel runs
@@ -987,14 +1063,20 @@ static int launch_ws(Params &p, dim3 grid, cudaStream_t s) {
     }
     size_t smem = ws_smem_bytes<BM, BN, STAGES>(p.nterms);
     p.gen_map_smem = 0;
-    const size_t gen_extra = sizeof(double) * 3 * (size_t)p.gen_ueg.n_orb + sizeof(int) * ((size_t)p.gen_n3 + 1);
+    const size_t gen_extra = sizeof(double) * 3 * (size_t)p.gen_ueg.n_orb +
+                             sizeof(int) * ((size_t)p.gen_n3 + 1 + (size_t)p.gen_ueg.n_orb);
     if (p.gen_term >= 0 && smem + gen_extra <= kMaxSmemOptin) {
         // generated operand: the plane-wave vectors (12 KB at 515 orbitals) and the index map
         // (8.8 KB at imax = 6) ride in shared memory
         p.gen_map_smem = 1;
         smem += gen_extra;
     }
-    const bool window = p.gen_term >= 0 && gen_l2_window(p, s, true);
+    if (p.gen_term >= 0) {
+        const TermDev &t = p.t[p.gen_term];
+        p.gen_walk = t.nk == 2 && p.gen_k_axis[0] == 3 && p.gen_k_axis[1] == 2 && !g_gen_no_walk;
+    }
+    // (with compressed values the pair tables are not read by the kernel at all)
+    const bool window = p.gen_term >= 0 && !p.gen_nz && gen_l2_window(p, s, true);
     kern<<<grid, WMW * WNW * 32 + kWsProducerThreads, smem, s>>>(p);
     count_launch();
     const int rc = cuda_status();
@@ -1075,10 +1157,11 @@ static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
     int kt = 0;
     int nkeep = 0;
     p.gen_term = -1;
-    p.gen_n3 = p.gen_l0 = p.gen_map_smem = 0;
+    p.gen_n3 = p.gen_l0 = p.gen_map_smem = p.gen_walk = 0;
     memset(&p.gen_ueg, 0, sizeof(p.gen_ueg));
     p.gen_W0a = p.gen_W1a = p.gen_W0s = nullptr;
     p.gen_lin = nullptr;
+    p.gen_nz = nullptr;
     for (int ti = 0; ti < d->nterms; ++ti) {
         const pmb_term_t &s = d->terms[ti];
         if ((!s.A && !s.a_gen) || !s.B || s.nk < 0 || s.nk > PMB_MAX_DIMS) return PMB_E_BADARG;
@@ -1103,7 +1186,7 @@ static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
             // generated A operand: validate the axis assignment and the packing limits
             const pmb_ueg_operand_t &g = *s.a_gen;
             if (p.gen_term >= 0) return PMB_E_UNSUPPORTED;         // one per contraction
-            if (!g.W0a && !g.W0s) return PMB_E_BADARG;
+            if (!g.W0a && !g.W0s && !g.nz) return PMB_E_BADARG;
             if (!g.lin || !g.ueg.index_map || !g.ueg.kp || g.ueg.n_orb <= 0) return PMB_E_BADARG;
             if (g.ueg.n_orb > kGenFieldMask || g.ueg.imax < 0 || g.ueg.imax > 27) return PMB_E_UNSUPPORTED;
             int seen = 0;
@@ -1127,6 +1210,9 @@ static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
             p.gen_n3 = n * n * n;
             p.gen_l0 = g.ueg.imax * (n * n + n + 1);
             for (int i = 0; i < 4; ++i) p.gen_lo[i] = g.lo[i];
+            for (int i = 0; i < d->nm; ++i) p.gen_ext[g.m_axis[i]] = (int)d->m_ext[i];
+            for (int i = 0; i < s.nk; ++i) p.gen_ext[g.k_axis[i]] = (int)s.k_ext[i];
+            p.gen_nz = g.nz;
             p.gen_ueg = g.ueg;
             p.gen_W0a = g.W0a;
             p.gen_W1a = g.W1a;
@@ -1194,7 +1280,8 @@ static int panel_ktiles(const Params &p, int cfg) {
 using namespace pmb;
 
 extern "C" void pmb_contract_set_tuning(int tile_config, int split_k) {
-    g_force_cfg = tile_config;
+    g_gen_no_walk = tile_config >= 0 && (tile_config & 16);
+    g_force_cfg = tile_config >= 0 ? (tile_config & 15) : tile_config;
     g_force_split = split_k;
 }
 

@@ -174,9 +174,46 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// one thread per (p,q,r): the candidate non-zero of that dense row (coalesced 8 B stores)
+__global__ void __launch_bounds__(256)
+    build_nz_kernel(pmb_ueg_t u, const double *__restrict__ W0a, const double *__restrict__ W1a,
+                    const double *__restrict__ W0s, BlockGeom g, double *__restrict__ out) {
+    const long long rows = (long long)g.ext[0] * g.ext[1] * g.ext[2];
+    for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < rows;
+         row += (long long)gridDim.x * blockDim.x) {
+        const int r = g.lo[2] + (int)(row % g.ext[2]);
+        const int q = g.lo[1] + (int)((row / g.ext[2]) % g.ext[1]);
+        const int p = g.lo[0] + (int)(row / ((long long)g.ext[2] * g.ext[1]));
+        const int s = conserving_s(u, p, q, r);
+        const int sl = s - g.lo[3];
+        double w = 0.0;
+        if (s >= 0 && sl >= 0 && sl < g.ext[3]) w = ueg_value(u, W0a, W1a, W0s, p, q, r, s);
+        out[row] = w;
+    }
+}
+
 }  // namespace pmb
 
 using namespace pmb;
+
+extern "C" int pmb_ueg_build_nz(const pmb_ueg_t *u, const double *W0a, const double *W1a, const double *W0s,
+                                const int32_t lo[4], const int32_t ext[4], double *out, pmb_stream_t stream) {
+    if (!u || !u->kvec || !u->kp || !u->index_map || !lo || !ext || !out) return PMB_E_BADARG;
+    BlockGeom g;
+    long long rows = 1;
+    for (int d = 0; d < 4; ++d) {
+        if (lo[d] < 0 || ext[d] <= 0 || lo[d] + ext[d] > u->n_orb) return PMB_E_BADARG;
+        g.lo[d] = lo[d];
+        g.ext[d] = ext[d];
+        if (d < 3) rows *= ext[d];
+    }
+    long long blocks = (rows + 255) / 256;
+    const long long cap = (long long)kSmCount * 16;
+    if (blocks > cap) blocks = cap;
+    build_nz_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*u, W0a, W1a, W0s, g, out);
+    count_launch();
+    return cuda_status();
+}
 
 extern "C" int pmb_ueg_umat(const pmb_ueg_t *u, double box_len, int cutoff, int nq, const int32_t *qvec,
                             double *out, pmb_stream_t stream) {

@@ -12,16 +12,30 @@ namespace pmb {
 struct UegWords {
     double w0, w1, s0, s1;
 };
+// PIN: the loads are volatile asm, which the compiler neither deletes nor sinks to the point
+// of use -- a prefetch into registers stays where it was written (plain __ldg loads of
+// read-only memory may legally be moved next to their consumer, which puts the whole memory
+// round trip back on the critical path).
+template <bool PIN>
+__device__ __forceinline__ double ueg_ld(const double *ptr) {
+    if (PIN) {
+        double v;
+        asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(ptr));
+        return v;
+    }
+    return __ldg(ptr);
+}
+template <bool PIN = false>
 __device__ __forceinline__ UegWords ueg_load_words(int nP, const double *__restrict__ W0a,
                                                    const double *__restrict__ W1a, const double *__restrict__ W0s,
                                                    int p, int q, int r, int s) {
     const int pr = p * nP + r;
     UegWords w = {0.0, 0.0, 0.0, 0.0};
-    if (W0a) w.w0 = __ldg(W0a + pr);
-    if (W1a) w.w1 = __ldg(W1a + pr);
+    if (W0a) w.w0 = ueg_ld<PIN>(W0a + pr);
+    if (W1a) w.w1 = ueg_ld<PIN>(W1a + pr);
     if (W0s) {
-        w.s0 = __ldg(W0s + pr);
-        w.s1 = __ldg(W0s + q * nP + s);
+        w.s0 = ueg_ld<PIN>(W0s + pr);
+        w.s1 = ueg_ld<PIN>(W0s + q * nP + s);
     }
     return w;
 }

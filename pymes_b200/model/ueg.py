@@ -179,6 +179,17 @@ class UEG:
                    "pmb_ueg_build_block")
         return out
 
+    def build_nz(self, lo, ext, W0a=None, W1a=None, W0s=None):
+        """Momentum-compressed block [ext0,ext1,ext2]: V[p,q,r,s*(p,q,r)] where s* falls into the
+        block's s range, else 0 (``pmb_ueg_build_nz``) -- the one candidate non-zero per dense row."""
+        lib = _lib.load()
+        out = bk.empty(*ext[:3])
+        desc = self._descriptor()
+        p = lambda t: bk._ptr(t) if t is not None else None
+        _lib.check(lib.pmb_ueg_build_nz(C.byref(desc), p(W0a), p(W1a), p(W0s), _lib.I32x4(*lo),
+                                        _lib.I32x4(*ext), bk._ptr(out), bk._stream()), "pmb_ueg_build_nz")
+        return out
+
     def _mode_of(self, correlator, is_rpa_approx, is_only_2b, is_only_non_hermi_2b, is_only_hermi_2b,
                  is_effect_2b, is_exchange_1, is_exchange_2, is_exchange_3):
         if correlator is None:
@@ -225,11 +236,13 @@ class UEG:
         print_logging_info("{:.3f} s spent on ".format(time.time() - t0) + __name__, level=1)
         return out
 
-    def virtual_block(self, lo, ext, W0a=None, W1a=None, W0s=None):
+    def virtual_block(self, lo, ext, W0a=None, W1a=None, W0s=None, compressed=True):
         """The block ``build_block`` would write, as a never-materialised operand:
-        handed to ``backend.contract_terms`` in place of a tensor, its tiles are evaluated by the
-        contraction kernel's producer warps -- no memory, no HBM traffic, bit-identical values."""
-        return VirtualBlock(self, lo, ext, W0a, W1a, W0s)
+        handed to ``backend.contract_terms`` in place of a tensor, its tiles are produced by the
+        contraction kernel's producer warps, bit-identical to the dense block.  ``compressed``:
+        the non-zero values (one per dense row, ``build_nz``) are stored and looked up; otherwise
+        the producers evaluate the integral formula in place."""
+        return VirtualBlock(self, lo, ext, W0a, W1a, W0s, compressed=compressed)
 
     def eval_2b_blocks(self, no, keys, parts, ranges=None, virtual=()):
         """Named sub-blocks (partition.py keys, e.g. "abcd") of a SUM of integral kinds,
@@ -367,7 +380,7 @@ class VirtualBlock(bk.GeneratedOperand):
     (``include/pymes_b200.h: pmb_ueg_operand_t``).  Usable as the row operand of a
     contraction, e.g. the particle-particle ladder ``abcd,cdij->abij`` (ccd.py:187)."""
 
-    def __init__(self, model, lo, ext, W0a=None, W1a=None, W0s=None, _packed=False):
+    def __init__(self, model, lo, ext, W0a=None, W1a=None, W0s=None, compressed=True, _packed=False):
         if W0a is None and W0s is None:
             raise ValueError("a virtual block needs pair tables (W0a and/or W0s)")
         if model.n_orb > 2047 or model.imax > 27:
@@ -382,6 +395,8 @@ class VirtualBlock(bk.GeneratedOperand):
             rows = iter(pack)
             W0a, W1a, W0s = (next(rows) if t is not None else None for t in (W0a, W1a, W0s))
         self.tables = (W0a, W1a, W0s)
+        self.compressed = bool(compressed)
+        self.nz = model.build_nz(self.lo, self.shape, *self.tables) if self.compressed else None
         st = model._device_state()
         if "lin" not in st:
             n = 2 * model.imax + 1
@@ -395,7 +410,7 @@ class VirtualBlock(bk.GeneratedOperand):
         new_lo, new_ext = list(self.lo), list(self.shape)
         new_lo[dim] += int(lo)
         new_ext[dim] = int(n)
-        return VirtualBlock(self.model, new_lo, new_ext, *self.tables, _packed=True)
+        return VirtualBlock(self.model, new_lo, new_ext, *self.tables, compressed=self.compressed, _packed=True)
 
     def materialise(self):
         """The dense tensor (tests / small systems)."""
@@ -408,10 +423,11 @@ class VirtualBlock(bk.GeneratedOperand):
         p = lambda t: t.data_ptr() if t is not None else None
         g.W0a, g.W1a, g.W0s = (p(t) for t in self.tables)
         g.lin = self.lin.data_ptr()
+        g.nz = self.nz.data_ptr() if self.nz is not None else None
         axis = {ch: i for i, ch in enumerate(sub)}
         for i in range(4):
             g.lo[i] = self.lo[i]
             g.m_axis[i] = axis[m_ord[i]] if i < len(m_ord) else -1
             g.k_axis[i] = axis[k_ord[i]] if i < len(k_ord) else -1
-        g._keep = (self.tables, self.lin, self.model._dev)
+        g._keep = (self.tables, self.lin, self.nz, self.model._dev)
         return g

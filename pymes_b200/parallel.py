@@ -210,11 +210,12 @@ class ShardedCCSD(ccsd.CCSD):
             T1a = sh.rows(T1, 0)
             # W1[k,b,i,j] for b in A from the local V_iabc[:,A], gathered along b
             no = T1.shape[1]
-            w1 = bk.empty(sh.na, no, no, no)
-            ct("kbij", [(1.0, "kbcd", dV["iabc"], "cdij", tau)], out=w1.permute(1, 0, 2, 3))
+            w1, W2 = bk.empty(sh.na, no, no, no), bk.empty(sh.na, no, no, no)
+            with bk.side_by_side() as side:   # two short grids fill each other's last wave
+                ct("kbij", [(1.0, "kbcd", dV["iabc"], "cdij", tau)], out=w1.permute(1, 0, 2, 3))
+                side(lambda: ct("alij", [(1.0, "alcd", dV["aibc"], "cdij", tau)], out=W2))
             W1 = sh.gather_dim1(w1)
             ct("abij", [(-1.0, "ak", T1a, "kbij", W1)], out=R, beta=1.0)
-            W2 = ct("alij", [(1.0, "alcd", dV["aibc"], "cdij", tau)])
             W3 = ct("klij", [(1.0, "klcd", dV["ijab"], "cdij", tau)])
             ct("alij", [(-1.0, "ak", T1a, "klij", W3)], out=W2, beta=1.0)
             ct("abij", [(-1.0, "bl", T1, "alij", W2)], out=R, beta=1.0)

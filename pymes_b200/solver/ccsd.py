@@ -135,9 +135,12 @@ def tau_ladder(T1, dV):
         ct("abij", [(1.0, "ai", T1, "bj", T1)], out=tau, beta=1.0)
         with bk.timed("pp_ladder"):
             ct("abij", [(1.0, "abcd", dV["abcd"], "cdij", tau)], out=R, beta=1.0)
-        W1 = ct("kbij", [(1.0, "kbcd", dV["iabc"], "cdij", tau)])
+        nv, no = T1.shape
+        W1, W2 = bk.empty(no, nv, no, no), bk.empty(nv, no, no, no)
+        with bk.side_by_side() as side:       # two 4-wave grids fill each other's last wave
+            ct("kbij", [(1.0, "kbcd", dV["iabc"], "cdij", tau)], out=W1)
+            side(lambda: ct("alij", [(1.0, "alcd", dV["aibc"], "cdij", tau)], out=W2))
         ct("abij", [(-1.0, "ak", T1, "kbij", W1)], out=R, beta=1.0)
-        W2 = ct("alij", [(1.0, "alcd", dV["aibc"], "cdij", tau)])
         W3 = ct("klij", [(1.0, "klcd", dV["ijab"], "cdij", tau)])
         ct("alij", [(-1.0, "ak", T1, "klij", W3)], out=W2, beta=1.0)
         ct("abij", [(-1.0, "bl", T1, "alij", W2)], out=R, beta=1.0)

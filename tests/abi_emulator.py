@@ -325,11 +325,36 @@ class FakeLib:
         ext = [0] * 4
         for ax, e in zip(axes, list(m_ext) + list(k_ext)):
             ext[ax] = e
-        blk = self._block(g.ueg, g.W0a, g.W1a, g.W0s, [g.lo[i] for i in range(4)], ext)
+        lo = [g.lo[i] for i in range(4)]
+        if g.nz:
+            # compressed values: expand nz[p,q,r] to its dense position s*(p,q,r)
+            u, nP, kvec, kp, imap, tab = self._ueg(g.ueg)
+            nz = _window(g.nz, ext[0] * ext[1] * ext[2]).reshape(ext[:3])
+            blk = np.zeros(ext)
+            n = 2 * u.imax + 1
+            for p in range(ext[0]):
+                for q in range(ext[1]):
+                    for r in range(ext[2]):
+                        v = kvec[lo[1] + q] - (kvec[lo[2] + r] - kvec[lo[0] + p]) + u.imax
+                        loc = n * n * v[0] + n * v[1] + v[2]
+                        if 0 <= loc < n ** 3 and lo[3] <= imap[loc] < lo[3] + ext[3]:
+                            blk[p, q, r, imap[loc] - lo[3]] = nz[p, q, r]
+                        else:
+                            assert nz[p, q, r] == 0.0
+        else:
+            blk = self._block(g.ueg, g.W0a, g.W1a, g.W0s, lo, ext)
         nm = len(m_ext)
         order = axes[:nm][::-1] + axes[nm:][::-1]           # slowest first, M group then K group
         M = int(np.prod(m_ext)) if m_ext else 1
         return np.ascontiguousarray(blk.transpose(order)).reshape(M, -1).reshape(-1)
+
+    def pmb_ueg_build_nz(self, u, W0a, W1a, W0s, lo, ext, out, stream):
+        self.launches += 1
+        blk = self._block(u, W0a, W1a, W0s, [lo[i] for i in range(4)], [ext[i] for i in range(4)])
+        # at most one non-zero per dense row: the row sum IS that element
+        assert (np.count_nonzero(blk, axis=3) <= 1).all()
+        _window(_val(out), blk[..., 0].size)[:] = blk.sum(axis=3).reshape(-1)
+        return 0
 
     def pmb_ueg_build_block(self, u, W0a, W1a, W0s, lo, ext, out, stream):
         self.launches += 1

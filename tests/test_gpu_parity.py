@@ -415,6 +415,23 @@ def test_ueg_virtual_pp_ladder_bit_identical(n_ele, cutoff):
         # split-K: partial sums of the generated operand
         lib.pmb_contract_set_tuning(5, 3)
         assert torch.equal(bk.contract("abcd,cdij->abij", virt, tau), bk.contract("abcd,cdij->abij", dense, tau))
+        # +16: the scanning producer instead of the non-zero walker (what patterns whose
+        # contracted indices are not (r, s) use), alone and with split-K
+        for split in (0, 5):
+            lib.pmb_contract_set_tuning(5 + 16, split)
+            assert torch.equal(bk.contract("abcd,cdij->abij", virt, tau), ref if split == 0 else
+                               bk.contract("abcd,cdij->abij", dense, tau))
+        # contraction over (p, q): the solved index s sits in the row group -> scanning producer
+        lib.pmb_contract_set_tuning(5, 0)
+        assert torch.equal(bk.contract("abcd,abij->cdij", virt, tau), bk.contract("abcd,abij->cdij", dense, tau))
+        # without the compressed value table the producers evaluate the integral formula in
+        # place (walker and scanning variants): still the very same doubles
+        raw = m.virtual_block(virt.lo, virt.shape, *virt.tables, compressed=False)
+        assert virt.nz is not None and raw.nz is None
+        for cfg in (5, 5 + 16):
+            lib.pmb_contract_set_tuning(cfg, 0)
+            assert torch.equal(bk.contract("abcd,cdij->abij", raw, tau), ref)
+        assert torch.equal(bk.contract("abcd,abij->cdij", raw, tau), bk.contract("abcd,abij->cdij", dense, tau))
     finally:
         lib.pmb_contract_set_tuning(-1, 0)
     # default heuristics (the dense block may pick another tile shape): round-off only

@@ -355,6 +355,10 @@ def test_ueg_virtual_block_descriptor(cpu_abi):
     got = bk.contract("kbcd,cdij->kbij", v2, tau)
     np.testing.assert_allclose(_n(got), np.einsum("kbcd,cdij->kbij", _n(v2.materialise()), _n(tau)),
                                rtol=0, atol=1e-13)
+    # formula-evaluating variant (no compressed value table) gives the same numbers
+    raw = m.virtual_block((no,) * 4, (nv,) * 4, W0a=W0a, W1a=W1a, W0s=W0s, compressed=False)
+    assert raw.nz is None and virt.nz is not None
+    np.testing.assert_allclose(_n(bk.contract("abcd,cdij->abij", raw, tau)), _n(ref), rtol=0, atol=1e-13)
     # a generated operand on the column side is refused, not silently mis-evaluated
     with pytest.raises(ValueError, match="generated operand"):
         bk.contract("abcd,cdij->abij", virt, tau, out=bk.empty(no, no, nv, nv).permute(2, 3, 0, 1))
