@@ -289,9 +289,12 @@ def run_ours(args):
                                           if roof["achieved"] else None)
     prof = os.path.join(ROOT, "profiles", "pp_ladder_traffic.json" if args.dense_abcd
                         else "pp_ladder_virtual_traffic.json")
-    if os.path.exists(prof):
-        try:
-            roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+    if os.path.exists(prof) and world == 1:
+        try:                            # ncu capture of the same launch (same v, whole row range)
+            rec = json.load(open(prof))
+            if rec.get("n_virt", nv) == nv:
+                roof["traffic"] = rec.get("dram_bytes_per_launch")
+                roof["traffic_source"] = os.path.relpath(prof, ROOT)
         except Exception:               # noqa: BLE001
             pass
 

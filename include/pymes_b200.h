@@ -106,7 +106,8 @@ int pmb_contract(const pmb_contract_t *d, void *ws, size_t ws_bytes,
                  pmb_stream_t stream);
 /* tuning/diagnostic knobs: force a tile configuration (-1 = heuristic; bits   */
 /* 0-2 the configuration, +8 flips the copy interleaving, +16 makes generated  */
-/* operands use the scanning producer instead of the non-zero walker) and      */
+/* operands use the scanning producer instead of the non-zero walker, +32 keeps */
+/* the n-fastest tile order for launches with a generated operand) and         */
 /* a split-K factor (0 = heuristic).                                          */
 void pmb_contract_set_tuning(int tile_config, int split_k);
 /* L2 budget (bytes) for one operand's k window; contractions whose smaller      */
@@ -201,6 +202,26 @@ typedef struct {
     double alpha, beta;
 } pmb_bdot_t;
 int pmb_bdot(const pmb_bdot_t *d, pmb_stream_t stream);
+
+/* Matrix-vector form of a contraction (no tensor cores; HBM-bound):               */
+/*   out[X] = beta * out[X] + alpha * sum_K vec[K] * B[K, X]                        */
+/* for the einsums of the hot path in which one operand carries NO output index   */
+/* and the other is o.v^3-sized -- the T1 dressing of the Fock matrix             */
+/* "ci,iabc->ab", "ci,iacb->ab", "jacb,bj->ac", "jabc,bj->ac" (ccsd.py:257-286)    */
+/* and of the singles residual (ccsd.py:428-436).  As a 128-row DMMA tile they     */
+/* use 1/128 of the tensor work and gather 8 bytes at a time (measured 0.7 TB/s);  */
+/* here B is streamed once, coalesced along whichever of X / K is its unit-stride  */
+/* direction (first listed index of the group).  Deterministic (fixed order).      */
+typedef struct {
+    const double *vec;
+    const double *B;
+    double *out;
+    int32_t nk, nx;
+    int64_t k_ext[PMB_MAX_DIMS], v_kstr[PMB_MAX_DIMS], b_kstr[PMB_MAX_DIMS];
+    int64_t x_ext[PMB_MAX_DIMS], b_xstr[PMB_MAX_DIMS], o_xstr[PMB_MAX_DIMS];
+    double alpha, beta;
+} pmb_gemv_t;
+int pmb_gemv(const pmb_gemv_t *d, pmb_stream_t stream);
 
 /* Shifted complex diagonal preconditioner of the FEAST linear solves             */
 /* feast_eom_ccsd.py:341-342:  y = x / (z - diag + shift), x = xr + i xi,        */

@@ -38,6 +38,13 @@ class Bdot(C.Structure):
                 ("alpha", C.c_double), ("beta", C.c_double)]
 
 
+class Gemv(C.Structure):
+    _fields_ = [("vec", C.c_void_p), ("B", C.c_void_p), ("out", C.c_void_p), ("nk", C.c_int32), ("nx", C.c_int32),
+                ("k_ext", I64x4), ("v_kstr", I64x4), ("b_kstr", I64x4),
+                ("x_ext", I64x4), ("b_xstr", I64x4), ("o_xstr", I64x4),
+                ("alpha", C.c_double), ("beta", C.c_double)]
+
+
 class Ueg(C.Structure):
     _fields_ = [("n_orb", C.c_int32), ("imax", C.c_int32), ("n_occ", C.c_int32), ("n_ele", C.c_int32),
                 ("omega", C.c_double), ("u_table", C.c_void_p), ("u_table_len", C.c_int32),
@@ -78,6 +85,7 @@ _SIGS = {
                               C.c_void_p, C.c_void_p]),
     "pmb_reduce_workspace": (C.c_size_t, []),
     "pmb_bdot": (C.c_int, [C.POINTER(Bdot), C.c_void_p]),
+    "pmb_gemv": (C.c_int, [C.POINTER(Gemv), C.c_void_p]),
     "pmb_cdiv_shifted": (C.c_int, [C.c_int64, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pmb_ueg_umat": (C.c_int, [C.POINTER(Ueg), C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

@@ -257,6 +257,8 @@ def _align_k(sa, A, sb, B):
         return sa, A, sb, B
     if min(A.numel(), B.numel()) < ALIGN_K_MIN_ELEMENTS:
         return sa, A, sb, B                      # small enough to live in L2 either way
+    if (B if B.numel() <= A.numel() else A).dim() > 4:
+        return sa, A, sb, B                      # the copy kernel handles rank <= 4 (batched sigma: as is)
 
     def relaid(s_small, small, s_big, big):
         bstr = dict(zip(s_big, big.stride()))
@@ -372,6 +374,66 @@ def describe_contraction(out_sub, terms, out=None, beta=0.0, conv=None, alloc=No
     return d, out, norm
 
 
+GEMV_MIN_ELEMENTS = 1 << 22
+
+
+def _try_gemv(out_sub, terms, out, beta):
+    """Matrix-vector contractions (one operand without any output index, the other o.v^3-sized:
+    the T1 dressing of the Fock matrix and of the singles residual) go to ``pmb_gemv``, which
+    streams the big operand once instead of feeding 1-row DMMA tiles.  Returns the result or
+    None when the pattern does not apply."""
+    if len(terms) != 1:
+        return None
+    alpha, sa, A, sb, B = terms[0]
+    A, B = asdev(A), asdev(B)
+    if isinstance(A, GeneratedOperand) or isinstance(B, GeneratedOperand):
+        return None
+    a_out = [ch for ch in sa if ch in out_sub]
+    b_out = [ch for ch in sb if ch in out_sub]
+    if bool(a_out) == bool(b_out):
+        return None
+    vsub, vec, bsub, big = (sa, A, sb, B) if not a_out else (sb, B, sa, A)
+    if big.numel() < GEMV_MIN_ELEMENTS or vec.dim() != len(vsub) or big.dim() != len(bsub):
+        return None
+    if len(set(vsub)) != len(vsub) or len(set(bsub)) != len(bsub) or len(set(out_sub)) != len(out_sub):
+        return None
+    xs = [ch for ch in bsub if ch not in vsub]
+    if set(vsub) - set(bsub) or set(xs) != set(out_sub) or not 1 <= len(vsub) <= 4 or len(xs) > 4:
+        return None
+    ext = dict(zip(bsub, big.shape))
+    if any(ext[ch] != n for ch, n in zip(vsub, vec.shape)):
+        raise ValueError("extent mismatch in %s,%s" % (sa, sb))
+    shape = tuple(ext[ch] for ch in out_sub)
+    if out is None:
+        if beta != 0.0:
+            raise ValueError("beta != 0 needs an output tensor")
+        out = empty(*shape)
+    elif tuple(out.shape) != shape:
+        raise ValueError("output shape %s != %s" % (tuple(out.shape), shape))
+    bstr, vstr, ostr = dict(zip(bsub, big.stride())), dict(zip(vsub, vec.stride())), dict(zip(out_sub, out.stride()))
+    k_ord = sorted(vsub, key=lambda ch: (bstr[ch], ch))
+    x_ord = sorted(xs, key=lambda ch: (bstr[ch], ch))
+    d = _lib.Gemv()
+    d.vec, d.B, d.out = vec.data_ptr(), big.data_ptr(), out.data_ptr()
+    d.nk, d.nx, d.alpha, d.beta = len(k_ord), len(x_ord), float(alpha), float(beta)
+    _fill(d.k_ext, [ext[ch] for ch in k_ord])
+    _fill(d.v_kstr, [vstr[ch] for ch in k_ord])
+    _fill(d.b_kstr, [bstr[ch] for ch in k_ord])
+    _fill(d.x_ext, [ext[ch] for ch in x_ord])
+    _fill(d.b_xstr, [bstr[ch] for ch in x_ord])
+    _fill(d.o_xstr, [ostr[ch] for ch in x_ord])
+    trace = _timing["trace"]
+    if trace is not None:
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(torch.cuda.current_stream())
+    rc = _lib.load().pmb_gemv(C.byref(d), _stream())
+    if trace is not None:
+        t1.record(torch.cuda.current_stream())
+        trace.append(("%s,%s->%s [gemv]" % (sa, sb, out_sub), 2.0 * big.numel(), t0, t1))
+    _lib.check(rc, "pmb_gemv")
+    return out
+
+
 def contract_terms(out_sub, terms, out=None, beta=0.0):
     """out[out_sub] = beta*out + sum_t alpha_t * einsum(subA_t, subB_t -> out_sub).
 
@@ -384,6 +446,9 @@ def contract_terms(out_sub, terms, out=None, beta=0.0):
     if out is not None and out.device != device():
         raise RuntimeError("pymes_b200: output tensor lives on %s, the kernels write to %s "
                            "(there is no CPU fallback)" % (out.device, device()))
+    res = _try_gemv(out_sub, terms, out, beta)
+    if res is not None:
+        return res
     d, out, _operands = describe_contraction(out_sub, terms, out, beta)
     need = lib.pmb_contract_workspace(C.byref(d))
     ws = scratch().splitk_ws(need) if need else None

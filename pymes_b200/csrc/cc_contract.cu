@@ -58,6 +58,7 @@ struct Params {
     double *C;
     double beta;
     int tiles_m, tiles_n;
+    int raster_m_fast;       // consecutive CTAs walk m inside one column of tiles (see launch_ws)
     int total_ktiles, ktiles_per_split, nsplit;
     int kt_base, kt_limit;   // k-tile window of this launch (K-panel), [0, total_ktiles) if not panelled
     double *ws;
@@ -559,7 +560,13 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
     const unsigned bs_base = (unsigned)__cvta_generic_to_shared(Bs);
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int tile_n = blockIdx.x % p.tiles_n, tile_m = blockIdx.x / p.tiles_n;
+    // Tile order.  Default: n fastest -- the CTAs of a wave share A row panels through L2.  With a
+    // generated A there is nothing to share on that side; m fastest makes a whole wave work on
+    // ONE column of tiles, whose equal-sized CTAs start and finish together and therefore
+    // stream the same k range of B at the same time: B is read from HBM once per wave instead
+    // of once per CTA (ncu: 2.64 TB -> see profiles/ for the pp ladder at v = 488).
+    const int tile_n = p.raster_m_fast ? (int)(blockIdx.x / p.tiles_m) : (int)(blockIdx.x % p.tiles_n);
+    const int tile_m = p.raster_m_fast ? (int)(blockIdx.x % p.tiles_m) : (int)(blockIdx.x / p.tiles_n);
     const int m0 = tile_m * BM, n0 = tile_n * BN;
     const int mrem = p.M - m0, nrem = p.N - n0;
     const int kt_lo = p.kt_base + blockIdx.y * p.ktiles_per_split;
@@ -956,6 +963,7 @@ static const TileCfg kCfg[] = {
 constexpr int kNumCfg = 7;
 
 static int g_gen_no_walk = 0;      // tuning bit 16: generated operands use the scanning producer
+static int g_gen_no_mraster = 0;   // tuning bit 32: keep the default tile order for generated operands
 static int g_force_cfg = -1;
 static int g_force_split = 0;
 // L2 budget for one operand's k window (0 = no windows).  The warp-specialised kernel runs
@@ -1245,6 +1253,7 @@ static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
     }
     p.tiles_m = (int)((M + kCfg[cfg].bm - 1) / kCfg[cfg].bm);
     p.tiles_n = (int)((N + kCfg[cfg].bn - 1) / kCfg[cfg].bn);
+    p.raster_m_fast = p.gen_term >= 0 && !g_gen_no_mraster;
     if (g_force_split > 0) nsplit = g_force_split;
     if (nsplit > kt) nsplit = kt;
     if (nsplit < 1) nsplit = 1;
@@ -1281,6 +1290,7 @@ using namespace pmb;
 
 extern "C" void pmb_contract_set_tuning(int tile_config, int split_k) {
     g_gen_no_walk = tile_config >= 0 && (tile_config & 16);
+    g_gen_no_mraster = tile_config >= 0 && (tile_config & 32);
     g_force_cfg = tile_config >= 0 ? (tile_config & 15) : tile_config;
     g_force_split = split_k;
 }

@@ -396,6 +396,98 @@ __global__ void __launch_bounds__(256) bdot_warp_kernel(const __grid_constant__ 
     }
 }
 
+// ---------------------------------------------------------------------------
+// out[X] = beta out[X] + alpha sum_K vec[K] B[K,X]   (pmb_gemv)
+// ---------------------------------------------------------------------------
+struct GemvDev {
+    const double *vec, *B;
+    double *out;
+    int nk, nx;
+    long long K, X;
+    long long k_ext[4], v_kstr[4], b_kstr[4], x_ext[4], b_xstr[4], o_xstr[4];
+    double alpha, beta;
+};
+
+__device__ __forceinline__ void gemv_x_offsets(const GemvDev &d, long long x, long long &bo, long long &oo) {
+    bo = oo = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < d.nx) {
+            const long long e = d.x_ext[k], q = x / e, r = x - q * e;
+            bo += r * d.b_xstr[k];
+            oo += r * d.o_xstr[k];
+            x = q;
+        }
+    }
+}
+
+// B unit-stride along X: one thread per output, consecutive threads read consecutive words
+// of every B row; the k loop is a counter nest (no divisions), 4 rows in flight per thread.
+__global__ void __launch_bounds__(256) gemv_xfast_kernel(const __grid_constant__ GemvDev d) {
+    const long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= d.X) return;
+    long long bo, oo;
+    gemv_x_offsets(d, x, bo, oo);
+    const double *b = d.B + bo;
+    double acc = 0.0;
+    for (long long k3 = 0; k3 < d.k_ext[3]; ++k3)
+        for (long long k2 = 0; k2 < d.k_ext[2]; ++k2)
+            for (long long k1 = 0; k1 < d.k_ext[1]; ++k1) {
+                const double *bb = b + k3 * d.b_kstr[3] + k2 * d.b_kstr[2] + k1 * d.b_kstr[1];
+                const double *vv = d.vec + k3 * d.v_kstr[3] + k2 * d.v_kstr[2] + k1 * d.v_kstr[1];
+                const long long n0 = d.k_ext[0];
+                long long k0 = 0;
+                for (; k0 + 4 <= n0; k0 += 4) {
+                    const double b0 = bb[k0 * d.b_kstr[0]], b1 = bb[(k0 + 1) * d.b_kstr[0]],
+                                 b2 = bb[(k0 + 2) * d.b_kstr[0]], b3 = bb[(k0 + 3) * d.b_kstr[0]];
+                    acc += __ldg(vv + k0 * d.v_kstr[0]) * b0;
+                    acc += __ldg(vv + (k0 + 1) * d.v_kstr[0]) * b1;
+                    acc += __ldg(vv + (k0 + 2) * d.v_kstr[0]) * b2;
+                    acc += __ldg(vv + (k0 + 3) * d.v_kstr[0]) * b3;
+                }
+                for (; k0 < n0; ++k0) acc += __ldg(vv + k0 * d.v_kstr[0]) * bb[k0 * d.b_kstr[0]];
+            }
+    acc *= d.alpha;
+    if (d.beta != 0.0) acc += d.beta * d.out[oo];
+    d.out[oo] = acc;
+}
+
+// B unit-stride along the first K index: one warp per output, lanes walk that index (256 B
+// per warp instruction, 4 instructions in flight), fixed-order shuffle tree at the end.
+__global__ void __launch_bounds__(256) gemv_kfast_kernel(const __grid_constant__ GemvDev d) {
+    const int lane = threadIdx.x & 31;
+    const long long x = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (x >= d.X) return;
+    long long bo, oo;
+    gemv_x_offsets(d, x, bo, oo);
+    const double *b = d.B + bo;
+    double acc = 0.0;
+    const long long n0 = d.k_ext[0];
+    for (long long k3 = 0; k3 < d.k_ext[3]; ++k3)
+        for (long long k2 = 0; k2 < d.k_ext[2]; ++k2)
+            for (long long k1 = 0; k1 < d.k_ext[1]; ++k1) {
+                const double *bb = b + k3 * d.b_kstr[3] + k2 * d.b_kstr[2] + k1 * d.b_kstr[1];
+                const double *vv = d.vec + k3 * d.v_kstr[3] + k2 * d.v_kstr[2] + k1 * d.v_kstr[1];
+                long long k0 = lane;
+                for (; k0 + 96 < n0; k0 += 128) {
+                    const double b0 = bb[k0 * d.b_kstr[0]], b1 = bb[(k0 + 32) * d.b_kstr[0]],
+                                 b2 = bb[(k0 + 64) * d.b_kstr[0]], b3 = bb[(k0 + 96) * d.b_kstr[0]];
+                    acc += __ldg(vv + k0 * d.v_kstr[0]) * b0;
+                    acc += __ldg(vv + (k0 + 32) * d.v_kstr[0]) * b1;
+                    acc += __ldg(vv + (k0 + 64) * d.v_kstr[0]) * b2;
+                    acc += __ldg(vv + (k0 + 96) * d.v_kstr[0]) * b3;
+                }
+                for (; k0 < n0; k0 += 32) acc += __ldg(vv + k0 * d.v_kstr[0]) * bb[k0 * d.b_kstr[0]];
+            }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        acc *= d.alpha;
+        if (d.beta != 0.0) acc += d.beta * d.out[oo];
+        d.out[oo] = acc;
+    }
+}
+
 __global__ void __launch_bounds__(256)
     cdiv_shifted_kernel(size_t n, const double *__restrict__ diag, double zr, double zi, double shift,
                         const double *xr, const double *xi, double *yr, double *yi) {
@@ -595,6 +687,41 @@ extern "C" int pmb_bdot(const pmb_bdot_t *d, pmb_stream_t stream) {
     } else {
         bdot_thread_kernel<<<grid_for((size_t)k.I, 256, 16 * kSmCount), 256, 0, s>>>(k);
     }
+    count_launch();
+    return cuda_status();
+}
+
+extern "C" int pmb_gemv(const pmb_gemv_t *d, pmb_stream_t stream) {
+    if (!d || !d->vec || !d->B || !d->out || d->nk < 1 || d->nk > 4 || d->nx < 0 || d->nx > 4) return PMB_E_BADARG;
+    GemvDev k;
+    k.vec = d->vec;
+    k.B = d->B;
+    k.out = d->out;
+    k.nk = d->nk;
+    k.nx = d->nx;
+    k.alpha = d->alpha;
+    k.beta = d->beta;
+    k.K = k.X = 1;
+    for (int i = 0; i < 4; ++i) {
+        const bool uk = i < d->nk, ux = i < d->nx;
+        if ((uk && d->k_ext[i] <= 0) || (ux && d->x_ext[i] <= 0)) return PMB_E_BADARG;
+        k.k_ext[i] = uk ? d->k_ext[i] : 1;
+        k.v_kstr[i] = uk ? d->v_kstr[i] : 0;
+        k.b_kstr[i] = uk ? d->b_kstr[i] : 0;
+        k.x_ext[i] = ux ? d->x_ext[i] : 1;
+        k.b_xstr[i] = ux ? d->b_xstr[i] : 0;
+        k.o_xstr[i] = ux ? d->o_xstr[i] : 0;
+        k.K *= k.k_ext[i];
+        k.X *= k.x_ext[i];
+    }
+    if (k.X >= (1LL << 31) * 8) return PMB_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long bk0 = k.b_kstr[0] < 0 ? -k.b_kstr[0] : k.b_kstr[0];
+    const long long bx0 = k.nx ? (k.b_xstr[0] < 0 ? -k.b_xstr[0] : k.b_xstr[0]) : (1LL << 62);
+    if (bk0 < bx0 && k.k_ext[0] >= 32)
+        gemv_kfast_kernel<<<(unsigned)((k.X + 7) / 8), 256, 0, s>>>(k);
+    else
+        gemv_xfast_kernel<<<(unsigned)((k.X + 255) / 256), 256, 0, s>>>(k);
     count_launch();
     return cuda_status();
 }

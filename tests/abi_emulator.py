@@ -110,6 +110,22 @@ class FakeLib:
         _window(_val(yi), n)[:] = y.imag
         return 0
 
+    def pmb_gemv(self, dref, stream):
+        d = dref._obj
+        self.launches += 1
+        k_ext = [d.k_ext[i] for i in range(d.nk)]
+        x_ext = [d.x_ext[i] for i in range(d.nx)]
+        vk = _offsets(k_ext, [d.v_kstr[i] for i in range(d.nk)])
+        bk_ = _offsets(k_ext, [d.b_kstr[i] for i in range(d.nk)])
+        bx = _offsets(x_ext, [d.b_xstr[i] for i in range(d.nx)])
+        ox = _offsets(x_ext, [d.o_xstr[i] for i in range(d.nx)])
+        vec, _, _ = _gather(d.vec, vk)
+        B, _, _ = _gather(d.B, (bk_[:, None] + bx[None, :]).reshape(-1))
+        val = d.alpha * (vec @ B.reshape(len(vk), len(bx)))
+        old, win, lo = _gather(d.out, ox)
+        win[ox - lo] = val + (d.beta * old if d.beta != 0.0 else 0.0)
+        return 0
+
     def pmb_bdot(self, dref, stream):
         d = dref._obj
         self.launches += 1

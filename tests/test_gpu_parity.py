@@ -49,6 +49,26 @@ def test_multi_operand_einsum():
     host.test_multi_operand_einsum(None)
 
 
+def test_matrix_vector_contractions_go_to_gemv(monkeypatch):
+    host.test_matrix_vector_contractions_go_to_gemv(None, monkeypatch)
+
+
+def test_gemv_medium_both_mappings():
+    """pmb_gemv at o=9, v=83 (ragged against the 32-lane / 4-row unrolling) vs numpy."""
+    from pymes_b200 import backend as bk
+    rng = np.random.default_rng(8)
+    no, nv = 9, 83
+    t1 = rng.standard_normal((nv, no))
+    V = rng.standard_normal((no, nv, nv, nv))
+    assert V.size >= bk.GEMV_MIN_ELEMENTS
+    before = bk.launch_count()
+    for spec, A, B in (("ci,iabc->ab", t1, V), ("ci,iacb->ab", t1, V), ("jacb,bj->ac", V, t1),
+                       ("jabc,bj->ac", V, t1)):
+        got = bk.contract(spec, host._t(A), host._t(B))
+        assert _rel(got.cpu().numpy(), np.einsum(spec, A, B)) < 1e-13
+    assert bk.launch_count() - before == 4          # one kernel each: no split-K second stage
+
+
 def test_contract_realigns_conflicting_unit_strides(monkeypatch):
     host.test_contract_realigns_conflicting_unit_strides(None, monkeypatch)
 

@@ -320,6 +320,41 @@ def test_contract_realigns_conflicting_unit_strides(cpu_abi, monkeypatch):
     assert bk._align_k("abcd", _t(rng.standard_normal((4, 4, 4, 4))), "cdij", _t(T2[:4, :4]))[0] == "abcd"
 
 
+def test_matrix_vector_contractions_go_to_gemv(cpu_abi, monkeypatch):
+    """The T1 dressing einsums with an o.v^3 block and no output index on T1 (ccsd.py:257-286:
+    ``ci,iabc->ab``, ``ci,iacb->ab``, ``jacb,bj->ac``, ``jabc,bj->ac``; singles ``bj,jaib->ai``)
+    take the pmb_gemv route: both unit-stride cases, views, alpha/beta accumulation."""
+    from pymes_b200 import backend as bk
+    monkeypatch.setattr(bk, "GEMV_MIN_ELEMENTS", 0)
+    rng = np.random.default_rng(5)
+    no, nv = 3, 37
+    t1 = rng.standard_normal((nv, no))
+    Viabc = rng.standard_normal((no, nv, nv, nv))
+    Vfull = rng.standard_normal((no + nv,) * 4)
+    called = []
+    lib = bk._lib.load()
+    orig = lib.pmb_gemv
+    monkeypatch.setattr(lib, "pmb_gemv", lambda d, s: (called.append(1), orig(d, s))[1], raising=False)
+    for spec, A, B in (("ci,iabc->ab", t1, Viabc), ("ci,iacb->ab", t1, Viabc), ("jacb,bj->ac", Viabc, t1),
+                       ("jabc,bj->ac", Viabc, t1), ("bj,jaib->ai", t1, Vfull[:no, no:, :no, no:])):
+        n0 = len(called)
+        got = bk.contract(spec, _t(A), _t(B))
+        assert len(called) == n0 + 1, spec
+        np.testing.assert_allclose(_n(got), np.einsum(spec, A, B), **TOL)
+    out = _t(rng.standard_normal((nv, nv)))
+    want = 0.5 * _n(out) - 2.0 * np.einsum("ci,iabc->ab", t1, Viabc)
+    bk.contract("ci,iabc->ab", _t(t1), _t(Viabc), out=out, alpha=-2.0, beta=0.5)
+    np.testing.assert_allclose(_n(out), want, **TOL)
+    # transposed output view
+    outT = _t(np.zeros((nv, nv)))
+    bk.contract("ci,iabc->ab", _t(t1), _t(Viabc), out=outT.t())
+    np.testing.assert_allclose(_n(outT).T, np.einsum("ci,iabc->ab", t1, Viabc), **TOL)
+    # ordinary matrix products are not diverted
+    n0 = len(called)
+    bk.contract("ab,bc->ac", _t(rng.standard_normal((40, 50))), _t(rng.standard_normal((50, 30))))
+    assert len(called) == n0
+
+
 def test_ueg_virtual_block_descriptor(cpu_abi):
     """Never-materialised V block as the row operand of a contraction (pmb_term_t.a_gen):
     the descriptor's axis assignment for the pp ladder, a permuted o.v^3 pattern and a row
