@@ -239,7 +239,11 @@ __device__ __forceinline__ void gat_issue_batched(const Gat &g, int krem) {
 // dependent read-modify-write chains (k-window launches pay this once per window).
 template <int MT, int NTL>
 __device__ __forceinline__ void store_tile(const Params &p, double (&acc)[MT][NTL][2], const long long *s_cm,
-                                           const long long *s_cn, int row0, int col0, int mrem, int nrem) {
+                                           const long long *s_cn, int row0, int col0, int mrem, int nrem,
+                                           int ncols = NTL) {
+    // only the first `ncols` fragment columns of the warp tile are in use (ragged tiles of
+    // the warp-specialised kernel): the others never reach memory
+    nrem = min(nrem, col0 - (col0 & 7) + ncols * 8);
     const bool rd = p.beta != 0.0;
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
@@ -273,7 +277,8 @@ __device__ __forceinline__ void store_tile(const Params &p, double (&acc)[MT][NT
 // split-K partial sums: plain row-major [split][M][N] workspace
 template <int MT, int NTL>
 __device__ __forceinline__ void store_partial(const Params &p, const double (&acc)[MT][NTL][2], int m0, int n0,
-                                              int row0, int col0, int mrem, int nrem) {
+                                              int row0, int col0, int mrem, int nrem, int ncols = NTL) {
+    nrem = min(nrem, col0 - (col0 & 7) + ncols * 8);
     double *ws = p.ws + (size_t)blockIdx.y * (size_t)p.M * (size_t)p.N;
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
@@ -838,36 +843,33 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
     int st = 0;
     unsigned full_parity = 0;
     const double *a0 = As + warp_m * WM + (lane >> 2) + (lane & 3) * LDA;
-    const double *b0 = Bs + warp_n * WN + (lane >> 2) + (lane & 3) * LDB;
-    // number of 8-row / 8-column fragments of this warp's tile that intersect C
+    // Ragged tiles.  The fragment columns that intersect C are dealt out evenly over the
+    // WARPS_N warps of a row, in compile-time widths of 2, 4, 6 or 8 fragments: the pp ladder's
+    // last tile (89 of 128 columns = 12 fragments) runs 6 + 6 instead of 8 + 4(+4 wasted), so
+    // the two warps that share a scheduler finish together and the CTA takes 6/8 of a full one.
+    // (Per-fragment predication was measured to cost more than the padding it skips:
+    // C[40000,N] = A.B took 75.7 ms at N = 729 against 72.6 ms at N = 768, tools/micro_edge.py.)
+    // Fragments that are computed but lie outside C read offset-0 operand data and are never
+    // stored.  Rows are not subdivided: a warp row is active or not.
+    static_assert(NTL == 8, "column widths 2/4/6/8");
+    const int nfrag = max(0, min(WARPS_N * NTL, (nrem + 7) >> 3));
+    const int ncw = min(NTL, (((nfrag + WARPS_N - 1) / WARPS_N) + 1) & ~1);    // per warp, even
+    const int wn_off = warp_n * ncw * 8;
     const int mact = max(0, min(MT, (mrem - warp_m * WM + 7) >> 3));
-    const int nact = max(0, min(NTL, (nrem - warp_n * WN + 7) >> 3));
-    const bool interior = mact == MT && nact == NTL;
-    auto substep_full = [&](const double *a, const double *b, auto part) {
+    const int wmode = (mact == 0 || nfrag - warp_n * ncw <= 0) ? 0 : ncw;
+    const double *b0 = Bs + wn_off + (lane >> 2) + (lane & 3) * LDB;
+    auto substep = [&](const double *a, const double *b, auto part, auto ncols) {
         constexpr int ks = decltype(part)::value;
-        double af[MT], bf[NTL];
+        constexpr int NC_ = decltype(ncols)::value;
+        double af[MT], bf[NC_];
 #pragma unroll
         for (int i = 0; i < MT; ++i) af[i] = a[ks * 4 * LDA + i * 8];
 #pragma unroll
-        for (int j = 0; j < NTL; ++j) bf[j] = b[ks * 4 * LDB + j * 8];
+        for (int j = 0; j < NC_; ++j) bf[j] = b[ks * 4 * LDB + j * 8];
 #pragma unroll
         for (int i = 0; i < MT; ++i)
 #pragma unroll
-            for (int j = 0; j < NTL; ++j) dmma(acc[i][j], af[i], bf[j]);
-    };
-    // ragged tile: 8x8 fragments that lie entirely outside C are skipped (warp-uniform)
-    auto substep_edge = [&](const double *a, const double *b, auto part) {
-        constexpr int ks = decltype(part)::value;
-        double af[MT], bf[NTL];
-#pragma unroll
-        for (int i = 0; i < MT; ++i) af[i] = i < mact ? a[ks * 4 * LDA + i * 8] : 0.0;
-#pragma unroll
-        for (int j = 0; j < NTL; ++j) bf[j] = j < nact ? b[ks * 4 * LDB + j * 8] : 0.0;
-#pragma unroll
-        for (int i = 0; i < MT; ++i)
-#pragma unroll
-            for (int j = 0; j < NTL; ++j)
-                if (i < mact && j < nact) dmma(acc[i][j], af[i], bf[j]);
+            for (int j = 0; j < NC_; ++j) dmma(acc[i][j], af[i], bf[j]);
     };
     unsigned ready = 0;
     for (int g = kt_lo; g < kt_hi; ++g) {
@@ -895,19 +897,23 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
         // spinning wait at the top of the next iteration.
         const int nst = st + 1 == STAGES ? 0 : st + 1;
         const unsigned npar = nst == 0 ? full_parity ^ 1u : full_parity;
-        if (interior) {
-            substep_full(a, b, IntC<0>{});
-            substep_full(a, b, IntC<1>{});
-            substep_full(a, b, IntC<2>{});
+        auto ktile = [&](auto ncols) {
+            substep(a, b, IntC<0>{}, ncols);
+            substep(a, b, IntC<1>{}, ncols);
+            substep(a, b, IntC<2>{}, ncols);
             ready = mbar_probe(bar_base + nst * 8, npar);
-            substep_full(a, b, IntC<3>{});
-        } else {
-            substep_edge(a, b, IntC<0>{});
-            substep_edge(a, b, IntC<1>{});
-            substep_edge(a, b, IntC<2>{});
+            substep(a, b, IntC<3>{}, ncols);
+        };
+        if (wmode == 8)
+            ktile(IntC<8>{});
+        else if (wmode == 6)
+            ktile(IntC<6>{});
+        else if (wmode == 4)
+            ktile(IntC<4>{});
+        else if (wmode == 2)
+            ktile(IntC<2>{});
+        else
             ready = mbar_probe(bar_base + nst * 8, npar);
-            substep_edge(a, b, IntC<3>{});
-        }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_base + (STAGES + st) * 8);
         if (++st == STAGES) {
@@ -926,11 +932,12 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
     }
 
     // ---- epilogue (consumers only) ----
-    const int row0 = warp_m * WM + (lane >> 2), col0 = warp_n * WN + (lane & 3) * 2;
+    const int row0 = warp_m * WM + (lane >> 2), col0 = wn_off + (lane & 3) * 2;
+    if (wmode == 0) return;
     if (p.nsplit > 1)
-        store_partial<MT, NTL>(p, acc, m0, n0, row0, col0, mrem, nrem);
+        store_partial<MT, NTL>(p, acc, m0, n0, row0, col0, mrem, nrem, ncw);
     else
-        store_tile<MT, NTL>(p, acc, s_cm, s_cn, row0, col0, mrem, nrem);
+        store_tile<MT, NTL>(p, acc, s_cm, s_cn, row0, col0, mrem, nrem, ncw);
 }
 
 // C[m,n] = beta*C[m,n] + sum_s ws[s][m][n]  (split-K second stage, fixed order)

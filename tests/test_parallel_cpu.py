@@ -63,3 +63,65 @@ def test_sharded_ccsd_world2_matches_reference(tag, is_dcsd):
         np.testing.assert_allclose(t1, g[name + "_t1"], rtol=1e-8, atol=1e-11)
         np.testing.assert_allclose(t2, g[name + "_t2"], rtol=1e-8, atol=1e-11)
     assert sorted(r[5] for r in res) == [0, res[0][6] if res[0][5] == 0 else res[1][6]]
+
+
+def _ueg_case():
+    """TC-UEG 14e in 19 plane waves: Fock matrix, model and the integral kinds of the blocks."""
+    from pymes_b200.model import ueg
+    m = ueg.UEG(14, 7, 7, 0.5)
+    m.init_single_basis(2.0)
+    m.gamma, m.k_cutoff = None, 1.0
+    parts = [("only_non_hermi_2b", m.trunc), ("effect_2b", m.trunc)]
+    rng = np.random.default_rng(2)
+    nP = m.n_orb
+    fock = np.diag(m.kinetic()) + 1e-3 * rng.standard_normal((nP, nP))
+    return m, parts, fock
+
+
+def _ueg_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests import abi_emulator
+        abi_emulator.install(_Patch())
+        from pymes_b200 import log, parallel
+        from pymes_b200.model.ueg import VirtualBlock
+        log.set_quiet(True)
+        m, parts, fock = _ueg_case()
+        comm = parallel.Comm()
+        dV = parallel.build_sharded_hamiltonian(m, 7, comm, parts, virtual=("abcd",))
+        assert isinstance(dV["abcd"], VirtualBlock) and dV["abcd"].nz is not None
+        cc = parallel.ShardedCCSD(7, comm)
+        cc.setup(fock, dV)
+        assert dV["abcd"].shape[0] == cc.shard.na
+        es = [sum(cc.sweep()[:3]) for _ in range(3)]
+        q.put((rank, es, cc._st["T1"].numpy().copy(), cc._st["T2"].numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_ccsd_world2_generated_abcd_rows(cpu_abi):
+    """Each rank GENERATES its (ab) row block of V_abcd (pmb_ueg_operand_t, compressed values)
+    instead of holding it: three CCSD sweeps equal the single-process solve on dense blocks."""
+    from pymes_b200.integral.partition import KEYS
+    from pymes_b200.solver import ccsd
+    m, parts, fock = _ueg_case()
+    ref = ccsd.CCSD(7)
+    ref.setup(fock, m.eval_2b_blocks(7, list(KEYS), parts))
+    want = [sum(ref.sweep()[:3]) for _ in range(3)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_ueg_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, es, t1, t2 in res:
+        np.testing.assert_allclose(es, want, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(t1, ref._st["T1"].numpy(), rtol=1e-9, atol=1e-13)
+        np.testing.assert_allclose(t2, ref._st["T2"].numpy(), rtol=1e-9, atol=1e-13)
