@@ -375,6 +375,7 @@ def describe_contraction(out_sub, terms, out=None, beta=0.0, conv=None, alloc=No
 
 
 GEMV_MIN_ELEMENTS = 1 << 22
+GEMV_MIN_OUTPUTS = 1 << 16           # one thread / one warp per output: needs that many to fill the GPU
 
 
 def _try_gemv(out_sub, terms, out, beta):
@@ -395,6 +396,8 @@ def _try_gemv(out_sub, terms, out, beta):
     vsub, vec, bsub, big = (sa, A, sb, B) if not a_out else (sb, B, sa, A)
     if big.numel() < GEMV_MIN_ELEMENTS or vec.dim() != len(vsub) or big.dim() != len(bsub):
         return None
+    if big.numel() < GEMV_MIN_OUTPUTS * vec.numel():
+        return None                      # few outputs, long sums: the split-K contraction does better
     if len(set(vsub)) != len(vsub) or len(set(bsub)) != len(bsub) or len(set(out_sub)) != len(out_sub):
         return None
     xs = [ch for ch in bsub if ch not in vsub]

@@ -436,16 +436,20 @@ __global__ void __launch_bounds__(256) gemv_xfast_kernel(const __grid_constant__
                 const double *bb = b + k3 * d.b_kstr[3] + k2 * d.b_kstr[2] + k1 * d.b_kstr[1];
                 const double *vv = d.vec + k3 * d.v_kstr[3] + k2 * d.v_kstr[2] + k1 * d.v_kstr[1];
                 const long long n0 = d.k_ext[0];
-                long long k0 = 0;
-                for (; k0 + 4 <= n0; k0 += 4) {
-                    const double b0 = bb[k0 * d.b_kstr[0]], b1 = bb[(k0 + 1) * d.b_kstr[0]],
-                                 b2 = bb[(k0 + 2) * d.b_kstr[0]], b3 = bb[(k0 + 3) * d.b_kstr[0]];
-                    acc += __ldg(vv + k0 * d.v_kstr[0]) * b0;
-                    acc += __ldg(vv + (k0 + 1) * d.v_kstr[0]) * b1;
-                    acc += __ldg(vv + (k0 + 2) * d.v_kstr[0]) * b2;
-                    acc += __ldg(vv + (k0 + 3) * d.v_kstr[0]) * b3;
+                // 8 predicated loads issued back to back per pass (bytes in flight, not
+                // instruction count, is what an HBM-bound loop needs)
+                for (long long base = 0; base < n0; base += 8) {
+                    double bv[8], vv8[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const long long k0 = base + u;
+                        const bool in = k0 < n0;
+                        bv[u] = in ? bb[k0 * d.b_kstr[0]] : 0.0;
+                        vv8[u] = in ? __ldg(vv + k0 * d.v_kstr[0]) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc += vv8[u] * bv[u];
                 }
-                for (; k0 < n0; ++k0) acc += __ldg(vv + k0 * d.v_kstr[0]) * bb[k0 * d.b_kstr[0]];
             }
     acc *= d.alpha;
     if (d.beta != 0.0) acc += d.beta * d.out[oo];

@@ -84,6 +84,10 @@ class Shard:
     def gather(self, local):
         return self.comm.all_gather_rows(local, self.nv, self.max_rows)
 
+    def all_reduce(self, x):
+        """Sum of a small replicated-size tensor over the ranks (in place)."""
+        return self.comm.all_reduce_sum(x)
+
     def gather_dim1(self, local_rows_first):
         """local [na, x, ...] holding block [x, A, ...] transposed -> full view [x, nv, ...]."""
         return self.gather(local_rows_first).transpose(0, 1)
@@ -216,7 +220,8 @@ class ShardedCCSD(ccsd.CCSD):
                 side(lambda: ct("alij", [(1.0, "alcd", dV["aibc"], "cdij", tau)], out=W2))
             W1 = sh.gather_dim1(w1)
             ct("abij", [(-1.0, "ak", T1a, "kbij", W1)], out=R, beta=1.0)
-            W3 = ct("klij", [(1.0, "klcd", dV["ijab"], "cdij", tau)])
+            # o^4 output, contraction over (c,d): each rank sums its c in A, then all-reduce
+            W3 = sh.all_reduce(ct("klij", [(1.0, "klcd", sh.rows(dV["ijab"], 2), "cdij", sh.rows(tau, 0))]))
             ct("alij", [(-1.0, "ak", T1a, "klij", W3)], out=W2, beta=1.0)
             ct("abij", [(-1.0, "bl", T1, "alij", W2)], out=R, beta=1.0)
         return apply

@@ -44,6 +44,9 @@ class _Whole:
     def gather(self, local):
         return local
 
+    def all_reduce(self, x):
+        return x
+
 
 def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abcd,
                      is_dcd=False, is_bruekner=False, pp_ladder=None, shard=None):
@@ -66,9 +69,13 @@ def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abc
     T2b = sh.rows(T2, 1)            # T2[., a in A, ., .]
 
     # I_klij = V_klij (+ V_ijab.T)                                   ccd.py:178-180
+    # (sharded: each rank sums over its c in A, the o^4 partial sums are all-reduced)
     I = bk.copy(V_klij)
     if ccd:
-        ct("klij", [(1.0, "klcd", V_ijab, "cdij", T2)], out=I, beta=1.0)
+        if shard is None:
+            ct("klij", [(1.0, "klcd", V_ijab, "cdij", T2)], out=I, beta=1.0)
+        else:
+            bk.axpby(1.0, sh.all_reduce(ct("klij", [(1.0, "klcd", sh.rows(V_ijab, 2), "cdij", T2a)])), 1.0, I)
 
     # R = V_abij + I.T (hh ladder) + V_abcd.T (pp ladder)             ccd.py:185-187
     R = bk.copy(V_abij)
@@ -93,17 +100,19 @@ def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abc
 
     # Fock-like intermediates; the reference adds the same product twice for CCD
     # (ccd.py:213-221): X_ac = f_ab - c.Tt.V, X_ki = f_ij + c.Tt.V, c = 1/2 (DCD) or 1
-    Xac = bk.copy(fock[no:, no:])
+    # Only the local rows a in A of X_ac are ever used; X_ki is summed over the local c in A
+    # and all-reduced (o^2 numbers).
+    Xac = bk.copy(sh.rows(fock[no:, no:], 0))
     Xki = bk.copy(fock[:no, :no])
-    if not is_bruekner:
-        c = 1.0 if ccd else 0.5
-        ct("ac", [(-c, "adkl", Tt, "lkdc", V_ijab)], out=Xac, beta=1.0)
-        ct("ki", [(+c, "cdil", Tt, "lkdc", V_ijab)], out=Xki, beta=1.0)
-    elif ccd:
-        ct("ac", [(-0.5, "adkl", Tt, "lkdc", V_ijab)], out=Xac, beta=1.0)
-        ct("ki", [(+0.5, "cdil", Tt, "lkdc", V_ijab)], out=Xki, beta=1.0)
+    c = (1.0 if ccd else 0.5) if not is_bruekner else (0.5 if ccd else 0.0)
+    if c != 0.0:
+        ct("ac", [(-c, "adkl", Tta, "lkdc", V_ijab)], out=Xac, beta=1.0)
+        if shard is None:
+            ct("ki", [(+c, "cdil", Tt, "lkdc", V_ijab)], out=Xki, beta=1.0)
+        else:
+            bk.axpby(1.0, sh.all_reduce(ct("ki", [(+c, "cdil", Tta, "lkdc", sh.rows(V_ijab, 3))])), 1.0, Xki)
 
-    Ex = ct("abij", [(1.0, "ac", sh.rows(Xac, 0), "cbij", T2)])      # ccd.py:231
+    Ex = ct("abij", [(1.0, "ac", Xac, "cbij", T2)])                  # ccd.py:231
     ct("abij", [(-1.0, "ki", Xki, "abkj", T2a)], out=Ex, beta=1.0)   # ccd.py:232
     ring = [(-1.0, "kaic", sh.rows(V_iajb, 1), "cbkj", T2),          # ccd.py:233
             (+1.0, "acik", Tta, "kbcj", V_iabj)]                     # ccd.py:235
