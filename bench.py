@@ -48,6 +48,29 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version
+    banner at communicator creation, for one), so file descriptor 1 is pointed at stderr for
+    the whole run and the result line is written to the original stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 # ----------------------------------------------------------------------------
 # clocks / throttle reasons during the timed region
 # ----------------------------------------------------------------------------
@@ -151,7 +174,7 @@ def run_reference(args):
             "e2e": {"value": base["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_gpus, no, cutoff=None, dense_abcd=False):
@@ -335,7 +358,7 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_sample(2, 0, budget_s=40.0)
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -351,6 +374,7 @@ def main():
     ap.add_argument("--dense-abcd", action="store_true",
                     help="store V_abcd in HBM instead of generating it in the ladder kernel")
     args = ap.parse_args()
+    claim_stdout()
     if args.gpus not in CUTOFF_FOR_GPUS:
         raise SystemExit("--gpus must be one of %s" % sorted(CUTOFF_FOR_GPUS))
     if args.impl == "reference":
