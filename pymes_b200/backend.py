@@ -52,15 +52,26 @@ class GeneratedOperand:
     def data_ptr(self):
         return 0
 
+    def numel(self):
+        n = 1
+        for e in self.shape:
+            n *= int(e)
+        return n
+
     def gen_descriptor(self, sub, m_ord, k_ord):
         """ctypes ``pmb_ueg_operand_t`` for this operand indexed by ``sub`` with the M / K index
         groups ordered (fastest first) as ``m_ord`` / ``k_ord``."""
         raise NotImplementedError
 
 
+class LinearOperator:
+    """Marker for objects that stand in for a tensor but are only ever APPLIED (e.g. the
+    T1-dressed V_abcd of ``solver.ccsd.DressedLadder``).  ``asdev`` passes them through."""
+
+
 def asdev(x):
     """numpy array / torch tensor -> float64 CUDA tensor (views keep their strides)."""
-    if isinstance(x, GeneratedOperand):
+    if isinstance(x, (GeneratedOperand, LinearOperator)):
         return x
     if isinstance(x, torch.Tensor):
         if x.dtype != F64:
@@ -331,6 +342,14 @@ def describe_contraction(out_sub, terms, out=None, beta=0.0, conv=None, alloc=No
         m_set, n_set = n_set, m_set
         for t in norm:
             t[1], t[2], t[3], t[4] = t[3], t[4], t[1], t[2]
+    # a generated operand can only be produced on the row (A) side of the kernel: that
+    # outranks the epilogue preference above
+    if any(isinstance(t[4], GeneratedOperand) for t in norm):
+        if any(isinstance(t[2], GeneratedOperand) for t in norm):
+            raise ValueError("generated operands on both sides of a contraction")
+        m_set, n_set = n_set, m_set
+        for t in norm:
+            t[1], t[2], t[3], t[4] = t[3], t[4], t[1], t[2]
     if len(m_set) > _lib.MAX_DIMS or len(n_set) > _lib.MAX_DIMS:
         raise ValueError("too many indices in one group")
     a0 = dict(zip(norm[0][1], norm[0][2].stride()))
@@ -356,9 +375,6 @@ def describe_contraction(out_sub, terms, out=None, beta=0.0, conv=None, alloc=No
         else:
             k_ord = sorted(ks, key=lambda ch: (bstr[ch], ch))
         t = d.terms[i]
-        if isinstance(B, GeneratedOperand):
-            raise ValueError("a generated operand must end up as the A (row) operand of the "
-                             "contraction; here the output layout puts it on the column side")
         t.A, t.B, t.nk, t.alpha = A.data_ptr(), B.data_ptr(), len(k_ord), alpha
         if isinstance(A, GeneratedOperand):
             gen = A.gen_descriptor(sa, m_ord, k_ord)

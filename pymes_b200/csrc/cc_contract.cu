@@ -10,17 +10,21 @@
 // sm_100a has no tcgen05 kind for f64, so FP64 tensor work is issued as
 // warp-level mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).  One DMMA per SM
 // sub-partition every 16 cycles is the hardware peak (64 FMA/clk/SM), which
-// leaves ample issue slots for the gather loads; the kernel is organised so
-// that the DMMA pipe is the only thing that can be busy:
-//   * CTA tile 128x128x16 (8 warps, warp tile 32x64 -> 32 independent
-//     accumulator fragments per warp, no dependent-issue stalls),
-//   * global -> register -> shared double buffering (one __syncthreads per
-//     k-tile), loads for tile t+1 are in flight while tile t is multiplied,
-//   * shared tiles stored [k][x] with a +4 pad so that both the stores (either
-//     thread mapping) and the DMMA fragment loads are bank-conflict free,
-//   * thread->element mapping of the loads follows the operand's unit-stride
-//     direction (x-fast or k-fast) so global accesses stay coalesced to full
-//     32 B sectors for any permutation.
+// leaves ample issue slots for everything else; the kernels are organised so
+// that the DMMA pipe is the only thing that can be busy.  Two kernels:
+//   * contract_ws_kernel (large shapes): one 128x128x16 CTA per SM, four
+//     producer warps (offset tables, cp.async gathers -- or, for a generated
+//     operand, the expansion of compressed UEG integrals into the tile) and
+//     eight consumer warps (fragment LDS + DMMA only) coupled by mbarriers over
+//     a 4-stage shared-memory ring; ragged tiles use compile-time widths;
+//   * contract_kernel (small / skinny shapes): single-role CTAs, 3-4-stage
+//     cp.async pipeline, one __syncthreads per k-tile, split-K when the output
+//     has fewer tiles than the machine has CTA slots.
+// Common to both: shared tiles stored [k][x] with a +4 pad (stores of either
+// thread mapping and the fragment loads are bank-conflict free), and a
+// thread->element mapping of the gathers that follows each operand's
+// unit-stride direction (x-fast or k-fast) so global accesses stay coalesced
+// to full 32 B sectors for any permutation.
 #include <cstdlib>
 #include <cstring>
 

@@ -412,6 +412,17 @@ class VirtualBlock(bk.GeneratedOperand):
         new_ext[dim] = int(n)
         return VirtualBlock(self.model, new_lo, new_ext, *self.tables, compressed=self.compressed, _packed=True)
 
+    def diag_pqpq(self):
+        """D[p,q] = V[p,q,p,q] (the ``einsum("abab->ab")`` of eom_ccsd.py:262) without the dense
+        block: for r = p the momentum-conserving s is q itself, so the element is the stored
+        candidate ``nz[p,q,p]``.  Needs equal p/r and q/s ranges and the compressed values."""
+        if self.nz is None:
+            raise ValueError("diag_pqpq needs the compressed values (compressed=True)")
+        if self.lo[0] != self.lo[2] or self.shape[0] != self.shape[2] or \
+                self.lo[1] != self.lo[3] or self.shape[1] != self.shape[3]:
+            raise ValueError("diag_pqpq needs a block with equal (p, r) and (q, s) ranges")
+        return torch.diagonal(self.nz, dim1=0, dim2=2).t()          # [q,p] view -> [p,q]
+
     def materialise(self):
         """The dense tensor (tests / small systems)."""
         W0a, W1a, W0s = self.tables

@@ -147,6 +147,59 @@ def tau_ladder(T1, dV):
     return apply
 
 
+class DressedLadder(bk.LinearOperator):
+    """The T1-dressed V_abcd (ccsd.py:405-419)
+
+        Vd[a,b,c,d] = V[a,b,c,d] - t[a,k] V_iabc[k,b,c,d] - t[b,l] V_aibc[a,l,c,d]
+                                 + t[a,k] t[b,l] V_ijab[k,l,c,d]
+
+    as an operator: it is never formed (a v^4 array), only applied to amplitude-shaped
+    vectors and asked for its (abab) diagonal -- the two things EOM-CCSD does with it
+    (eom_ccsd.py:262,383).  ``V_abcd`` may be a dense tensor or a never-materialised
+    ``model.ueg.VirtualBlock``; the blocks are the UNDRESSED ones."""
+
+    def __init__(self, V_abcd, V_iabc, V_aibc, V_ijab, T1):
+        self.V_abcd, self.V_iabc, self.V_aibc, self.V_ijab, self.T1 = V_abcd, V_iabc, V_aibc, V_ijab, T1
+        nv = T1.shape[0]
+        self.shape = (nv, nv, nv, nv)
+
+    def apply(self, U, out, coef=1.0):
+        """out[(r,)a,b,i,j] += coef * sum_cd Vd[a,b,c,d] U[(r,)c,d,i,j]; U, out of shape
+        [v,v,o,o] or batched [r,v,v,o,o].  Same factorisation as ``tau_ladder``."""
+        ct, T1 = bk.contract_terms, self.T1
+        r = "r" if U.dim() == 5 else ""
+        ct(r + "abij", [(coef, "abcd", self.V_abcd, r + "cdij", U)], out=out, beta=1.0)
+        W1 = ct(r + "kbij", [(1.0, "kbcd", self.V_iabc, r + "cdij", U)])
+        ct(r + "abij", [(-coef, "ak", T1, r + "kbij", W1)], out=out, beta=1.0)
+        del W1
+        W2 = ct(r + "alij", [(1.0, "alcd", self.V_aibc, r + "cdij", U)])
+        W3 = ct(r + "klij", [(1.0, "klcd", self.V_ijab, r + "cdij", U)])
+        ct(r + "alij", [(-1.0, "ak", T1, r + "klij", W3)], out=W2, beta=1.0)
+        ct(r + "abij", [(-coef, "bl", T1, r + "alij", W2)], out=out, beta=1.0)
+        return out
+
+    def diag_abab(self):
+        """D[a,b] = Vd[a,b,a,b] as a [v,v] tensor."""
+        T1, V = self.T1, self.V_abcd
+        if isinstance(V, bk.GeneratedOperand):
+            D = bk.copy(V.diag_pqpq())
+        else:
+            D = bk.copy(bk.diag_view(V, "abab", "ab"))
+        X = bk.diag_view(self.V_iabc, "kbab", "kab")
+        bk.bdot("ak,kab->ab", T1, X, out=D, alpha=-1.0, beta=1.0)
+        Y = bk.diag_view(self.V_aibc, "alab", "alb")
+        bk.bdot("bl,alb->ab", T1, Y, out=D, alpha=-1.0, beta=1.0)
+        Z = bk.bdot("ak,klab->lab", T1, self.V_ijab)
+        bk.bdot("bl,lab->ab", T1, Z, out=D, alpha=1.0, beta=1.0)
+        return D
+
+    def dense(self):
+        """The dressed block itself (tests / small systems)."""
+        V = self.V_abcd.materialise() if isinstance(self.V_abcd, bk.GeneratedOperand) else self.V_abcd
+        return dressed_block("abcd", self.T1, {"abcd": V, "iabc": self.V_iabc, "aibc": self.V_aibc,
+                                               "ijab": self.V_ijab})
+
+
 class CCSD(ccd.CCD):
     def __init__(self, no, is_diis=True, delta_e=1.e-8, is_non_canonical=False, is_dcsd=False):
         self.t_T_ai = None
@@ -181,6 +234,10 @@ class CCSD(ccd.CCD):
         dV, T1 = _dev_dict(dict_t_V), bk.asdev(t_T_ai)
         for key in V_TERMS:
             if key in dict_t_V_dressed:
+                if key == "abcd" and isinstance(dV["abcd"], bk.GeneratedOperand):
+                    # V_abcd is never materialised: its dressed form is an operator as well
+                    dict_t_V_dressed[key] = DressedLadder(dV["abcd"], dV["iabc"], dV["aibc"], dV["ijab"], T1)
+                    continue
                 blk = dressed_block(key, T1, dV)
                 dict_t_V_dressed[key] = bk.tonumpy(blk) if want_numpy else blk
         return dict_t_V_dressed

@@ -113,7 +113,7 @@ class SigmaPlan:
 
     # ---- planning ------------------------------------------------------
     def _compile(self, table):
-        direct, twostep = {}, {}
+        direct, twostep, operators = {}, {}, []
         for coef, spec, names in table:
             lhs, out = spec.split("->")
             subs, names = lhs.split(","), names.split()
@@ -130,8 +130,13 @@ class SigmaPlan:
             stat = [(subs[i], names[i]) for i in range(len(subs)) if i != dyn[0]]
             all_idx = set("".join(subs))
             if len(stat) == 1:
-                self._add_direct(direct, coef, [stat[0]], usub, uname, out, ext)
                 self.flops_per_vector += 2.0 * _prod(ext, all_idx)
+                if isinstance(self.static[stat[0][1]], bk.LinearOperator):
+                    # the dressed V_abcd given as an operator (ccsd.DressedLadder): applied, not read
+                    assert (stat[0][0], usub, out) == ("abcd", "cdij", "abij"), spec
+                    operators.append((coef, self.static[stat[0][1]]))
+                    continue
+                self._add_direct(direct, coef, [stat[0]], usub, uname, out, ext)
                 continue
             (s1, n1), (s2, n2) = stat
             options = []
@@ -161,7 +166,7 @@ class SigmaPlan:
                 ysub = "".join(sorted(_rename("".join(yidx), ren)))
                 key = (zn, _rename(zs, ren), ysub, out)
                 twostep.setdefault(key, []).append((coef, _rename(xs, ren), xn, _rename(usub, ren), uname))
-        prog = {"direct": [], "twostep": []}
+        prog = {"direct": [], "twostep": [], "operators": operators}
         for (wsub, usub, uname, out), items in direct.items():
             prog["direct"].append((wsub, usub, uname, out, self._materialise(wsub, items)))
         for (zn, zsub, ysub, out), items in twostep.items():
@@ -219,6 +224,8 @@ class SigmaPlan:
                 else:
                     ct("r" + ysub, term, out=Y, beta=1.0)
             ct("r" + out, [(1.0, "r" + ysub, Y, zsub, Z)], out=out_t, beta=1.0)
+        for coef, op in prog["operators"]:
+            op.apply(U["u2"], out_t, coef)
 
     def apply(self, U1, U2, out=None):
         """sigma for a batch: U1 [r,v,o], U2 [r,v,v,o,o] device tensors (any strides along r,
@@ -307,7 +314,9 @@ def diag_doubles(no, fock, dV, T2):
     bk.add_broadcast(1.0, bk.diag_view(dV["klij"], "ijij", "ij"), "ij", D, "abij")
     for coef, spec, tgt in DIAG2_NP_TERMS:
         bk.add_broadcast(coef, bk.bdot(spec, dV["ijab"], T2), tgt, D, "abij")
-    bk.add_broadcast(1.0, bk.diag_view(dV["abcd"], "abab", "ab"), "ab", D, "abij")
+    vabab = dV["abcd"].diag_abab() if isinstance(dV["abcd"], bk.LinearOperator) \
+        else bk.diag_view(dV["abcd"], "abab", "ab")
+    bk.add_broadcast(1.0, vabab, "ab", D, "abij")
     return D
 
 

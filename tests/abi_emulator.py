@@ -422,7 +422,7 @@ def install(monkeypatch):
     monkeypatch.setattr(bk, "_device_key", lambda: "cpu-emulator")
 
     def asdev(x):
-        if isinstance(x, bk.GeneratedOperand):
+        if isinstance(x, (bk.GeneratedOperand, bk.LinearOperator)):
             return x
         if isinstance(x, torch.Tensor):
             return x.to(torch.float64)
