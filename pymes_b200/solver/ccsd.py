@@ -163,18 +163,26 @@ class DressedLadder(bk.LinearOperator):
         nv = T1.shape[0]
         self.shape = (nv, nv, nv, nv)
 
-    def apply(self, U, out, coef=1.0):
-        """out[(r,)a,b,i,j] += coef * sum_cd Vd[a,b,c,d] U[(r,)c,d,i,j]; U, out of shape
-        [v,v,o,o] or batched [r,v,v,o,o].  Same factorisation as ``tau_ladder``."""
+    def apply(self, U, out, coef=1.0, shard=None):
+        """out[(r,)a,b,i,j] += coef * sum_cd Vd[a,b,c,d] U[(r,)c,d,i,j]; U of shape [v,v,o,o] or
+        batched [r,v,v,o,o].  Same factorisation as ``tau_ladder``.  With ``shard``, ``out`` holds
+        the rows a in A only: V_abcd and V_aibc are restricted to those rows, W1 / W3 (no index
+        a) are replicated."""
         ct, T1 = bk.contract_terms, self.T1
         r = "r" if U.dim() == 5 else ""
-        ct(r + "abij", [(coef, "abcd", self.V_abcd, r + "cdij", U)], out=out, beta=1.0)
+        if shard is None:
+            Va, Vaibc, T1a = self.V_abcd, self.V_aibc, T1
+        else:
+            V = self.V_abcd
+            Va = V.rows(0, shard.lo, shard.na) if isinstance(V, bk.GeneratedOperand) else shard.rows(V, 0)
+            Vaibc, T1a = shard.rows(self.V_aibc, 0), shard.rows(T1, 0)
+        ct(r + "abij", [(coef, "abcd", Va, r + "cdij", U)], out=out, beta=1.0)
         W1 = ct(r + "kbij", [(1.0, "kbcd", self.V_iabc, r + "cdij", U)])
-        ct(r + "abij", [(-coef, "ak", T1, r + "kbij", W1)], out=out, beta=1.0)
+        ct(r + "abij", [(-coef, "ak", T1a, r + "kbij", W1)], out=out, beta=1.0)
         del W1
-        W2 = ct(r + "alij", [(1.0, "alcd", self.V_aibc, r + "cdij", U)])
+        W2 = ct(r + "alij", [(1.0, "alcd", Vaibc, r + "cdij", U)])
         W3 = ct(r + "klij", [(1.0, "klcd", self.V_ijab, r + "cdij", U)])
-        ct(r + "alij", [(-1.0, "ak", T1, r + "klij", W3)], out=W2, beta=1.0)
+        ct(r + "alij", [(-1.0, "ak", T1a, r + "klij", W3)], out=W2, beta=1.0)
         ct(r + "abij", [(-coef, "bl", T1, r + "alij", W2)], out=out, beta=1.0)
         return out
 

@@ -98,8 +98,15 @@ def _rename(sub, table):
 class SigmaPlan:
     """Compiled sigma program for one (fock, V blocks, T2); see the module docstring."""
 
-    def __init__(self, no, fock, dV, T2, hoist_cap=None):
+    def __init__(self, no, fock, dV, T2, hoist_cap=None, shard=None):
+        """``shard`` (``pymes_b200.parallel.Shard``): this rank evaluates the rows a in
+        [lo, lo+na) of sigma1[r,a,i] and sigma2[r,a,b,i,j] -- the output index ``a`` of every
+        contraction is restricted on whichever operand carries it -- and the row blocks are
+        all-gathered at the end of ``apply``; trial vectors and intermediates that do not carry
+        ``a`` stay replicated.  The only other exchange is the all-gather of Ex for the explicit
+        Ex + Ex^{baji} (eom_ccsd.py:377)."""
         self.no = no
+        self.shard = shard
         self.nv = nv = T2.shape[0]
         self.static = {"foo": fock[:no, :no], "fov": fock[:no, no:], "fvv": fock[no:, no:], "T": T2}
         for key in V_KEYS_USED:
@@ -210,28 +217,40 @@ class SigmaPlan:
         return 1.0, W
 
     # ---- execution -----------------------------------------------------
+    def _rows(self, sub, t):
+        """``t`` restricted to this rank's rows of the output index ``a`` (summed indices are
+        renamed to e, f, m, n, w..z or keep k, l, c, d: ``a`` is always the sharded one)."""
+        if self.shard is None or "a" not in sub:
+            return t
+        return self.shard.rows(t, sub.index("a"))
+
     def _run(self, prog, U, out_t):
-        """out_t[r,...] += program applied to the stacked vectors U = {"u1": [r,v,o], "u2": [r,v,v,o,o]}."""
+        """out_t[r,...] += program applied to the stacked vectors U = {"u1": [r,v,o], "u2": [r,v,v,o,o]};
+        with a shard, out_t holds the local rows of ``a`` only."""
         ct = bk.contract_terms
+        rows = self._rows
         for wsub, usub, uname, out, (alpha, W) in prog["direct"]:
-            ct("r" + out, [(alpha, wsub, W, "r" + usub, U[uname])], out=out_t, beta=1.0)
+            ct("r" + out, [(alpha, wsub, rows(wsub, W), "r" + usub, rows("r" + usub, U[uname]))],
+               out=out_t, beta=1.0)
         for Z, zsub, ysub, out, items in prog["twostep"]:
             Y = None
             for coef, xsub, xn, usub, uname in items:
-                term = [(coef, xsub, self.static[xn], "r" + usub, U[uname])]
+                term = [(coef, xsub, rows(xsub, self.static[xn]), "r" + usub, rows("r" + usub, U[uname]))]
                 if Y is None:
                     Y = ct("r" + ysub, term)
                 else:
                     ct("r" + ysub, term, out=Y, beta=1.0)
-            ct("r" + out, [(1.0, "r" + ysub, Y, zsub, Z)], out=out_t, beta=1.0)
+            ct("r" + out, [(1.0, "r" + ysub, Y, zsub, rows(zsub, Z))], out=out_t, beta=1.0)
         for coef, op in prog["operators"]:
-            op.apply(U["u2"], out_t, coef)
+            op.apply(U["u2"], out_t, coef, shard=self.shard)
 
     def apply(self, U1, U2, out=None):
         """sigma for a batch: U1 [r,v,o], U2 [r,v,v,o,o] device tensors (any strides along r,
         each vector contiguous) -> (S1, S2).  eom_ccsd.py:268-385 for every r at once."""
         U = {"u1": U1, "u2": U2}
         r = U2.shape[0]
+        if self.shard is not None:
+            return self._apply_sharded(U, r, out)
         if out is None:
             S1, S2 = bk.zeros(*U1.shape), bk.empty(*U2.shape)
         else:
@@ -246,6 +265,32 @@ class SigmaPlan:
         del Ex
         self._run(self.programs["s2n"], U, S2)
         return S1, S2
+
+    def _apply_sharded(self, U, r, out):
+        """Row-block evaluation (see ``__init__``); returns / fills the FULL sigma vectors."""
+        sh, no, nv = self.shard, self.no, self.nv
+
+        def gather_rows(loc):                  # [r, na, ...] -> [r, nv, ...]
+            return sh.gather(loc.transpose(0, 1).contiguous()).transpose(0, 1)
+
+        S1l = bk.zeros(r, sh.na, no)
+        self._run(self.programs["s1"], U, S1l)
+        Exl = bk.zeros(r, sh.na, nv, no, no)
+        self._run(self.programs["s2p"], U, Exl)
+        Exf = gather_rows(Exl)                 # the (ba) block lives on another rank
+        S2l = bk.empty(r, sh.na, nv, no, no)
+        for k in range(r):                                             # eom_ccsd.py:377
+            bk.axpby(1.0, Exl[k], 0.0, S2l[k])
+            bk.axpby(1.0, sh.rows(Exf[k].permute(1, 0, 3, 2), 0), 1.0, S2l[k])
+        del Exl, Exf
+        self._run(self.programs["s2n"], U, S2l)
+        S1f, S2f = gather_rows(S1l), gather_rows(S2l)
+        if out is None:
+            return S1f.contiguous(), S2f.contiguous()
+        for k in range(r):
+            bk.axpby(1.0, S1f[k], 0.0, out[0][k])
+            bk.axpby(1.0, S2f[k], 0.0, out[1][k])
+        return out
 
     def apply_packed(self, X):
         """Same for vectors packed as rows [singles | doubles] of X [r, v*o + v*v*o*o]."""
@@ -349,8 +394,12 @@ def _as_dict_dev(dict_t_V):
 
 
 class EOM_CCSD:
-    def __init__(self, no, n_excit=3):
+    def __init__(self, no, n_excit=3, comm=None):
+        """``comm`` (extension, ``pymes_b200.parallel.Comm``): the sigma product is evaluated in
+        (ab) row blocks over the ranks of ``comm``; everything else (trial vectors, the
+        projected eigenproblem) is replicated and identical on every rank."""
         self.algo_name = "EOM-CCSD"
+        self.comm = comm
         self.no = no
         self.n_excit = n_excit
         self.u_singles = []
@@ -370,8 +419,12 @@ class EOM_CCSD:
         """Compile (or fetch) the sigma program for these operands."""
         key = (id(t_fock_pq), id(dict_t_V), id(t_T_abij))
         if self._plan is None or self._plan_key != key:
-            self._plan = SigmaPlan(self.no, bk.asdev(t_fock_pq), _as_dict_dev(dict_t_V),
-                                   bk.asdev(t_T_abij).contiguous())
+            T2 = bk.asdev(t_T_abij).contiguous()
+            shard = None
+            if self.comm is not None and self.comm.size > 1:
+                from ..parallel import Shard
+                shard = Shard(self.comm, T2.shape[0])
+            self._plan = SigmaPlan(self.no, bk.asdev(t_fock_pq), _as_dict_dev(dict_t_V), T2, shard=shard)
             self._plan_key = key
             self._keep = (t_fock_pq, dict_t_V, t_T_abij)        # keep ids alive
         return self._plan

@@ -86,7 +86,7 @@ def _caxpy(w, coefs, vs):
 
 class FEAST_EOM_CCSD(EOM_CCSD):
     def __init__(self, no, e_c=0., e_r=1, n_trial=5, max_iter=20, tol=1e-12, **kwargs):
-        super().__init__(no, n_excit=2)
+        super().__init__(no, n_excit=2, comm=kwargs.get("comm"))   # comm: sharded sigma, see EOM_CCSD
         self.e_c = e_c
         self.e_r = e_r
         self.n_trial = n_trial

@@ -125,3 +125,70 @@ def test_sharded_ccsd_world2_generated_abcd_rows(cpu_abi):
         np.testing.assert_allclose(es, want, rtol=0, atol=1e-11)
         np.testing.assert_allclose(t1, ref._st["T1"].numpy(), rtol=1e-9, atol=1e-13)
         np.testing.assert_allclose(t2, ref._st["T2"].numpy(), rtol=1e-9, atol=1e-13)
+
+
+def _eom_inputs():
+    """LiH/3-21G: dressed Fock / integrals from the golden CCSD amplitudes (test_eom_ccsd.py:30-47)."""
+    from pymes_b200.integral.partition import part_2_body_int
+    from pymes_b200.solver import ccsd
+    g = np.load(os.path.join(ROOT, "tests", "golden", "mol_LiH_321g.npz"))
+    no = int(g["n_elec"]) // 2
+    dV = part_2_body_int(no, torch.from_numpy(g["V"].copy()))
+    cc = ccsd.CCSD(no)
+    T1, T2 = torch.from_numpy(g["ccsd_t1"].copy()), torch.from_numpy(g["ccsd_t2"].copy())
+    fock = torch.from_numpy(g["fock"].copy())
+    ft = cc.get_T1_dressed_fock(fock, T1, dV)
+    dVd = cc.get_T1_dressed_V(T1, dV)
+    return g, no, ft, dVd, T2
+
+
+def _eom_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests import abi_emulator
+        abi_emulator.install(_Patch())
+        from pymes_b200 import log, parallel
+        from pymes_b200.solver import eom_ccsd
+        log.set_quiet(True)
+        g, no, ft, dVd, T2 = _eom_inputs()
+        comm = parallel.Comm()
+        eom = eom_ccsd.EOM_CCSD(no, n_excit=len(g["eom_e"]), comm=comm)
+        rng = np.random.default_rng(9)
+        nv = T2.shape[0]
+        U1 = torch.from_numpy(rng.standard_normal((3, nv, no)))
+        U2 = torch.from_numpy(rng.standard_normal((3, nv, nv, no, no)))
+        S1, S2 = eom.sigma_batched(ft, dVd, U1, U2, T2)
+        assert eom._plan.shard is not None and eom._plan.shard.na < nv
+        roots = eom.solve(ft, dVd, T2)
+        q.put((rank, S1.numpy().copy(), S2.numpy().copy(), np.asarray(roots).copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_eom_sigma_and_davidson_world2(cpu_abi):
+    """Batched EOM-CCSD sigma evaluated in (ab) row blocks over two ranks (all-gather of Ex and
+    of the sigma rows) == the single-process sigma; the Davidson roots are the golden ones."""
+    from pymes_b200.solver import eom_ccsd
+    g, no, ft, dVd, T2 = _eom_inputs()
+    rng = np.random.default_rng(9)
+    nv = T2.shape[0]
+    U1 = torch.from_numpy(rng.standard_normal((3, nv, no)))
+    U2 = torch.from_numpy(rng.standard_normal((3, nv, nv, no, no)))
+    S1, S2 = eom_ccsd.EOM_CCSD(no, n_excit=3).sigma_batched(ft, dVd, U1, U2, T2)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30100 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_eom_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=900) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, s1, s2, roots in res:
+        np.testing.assert_allclose(s1, S1.numpy(), rtol=0, atol=1e-12)
+        np.testing.assert_allclose(s2, S2.numpy(), rtol=0, atol=1e-12)
+        np.testing.assert_allclose(np.sort(roots), np.sort(g["eom_e"]), rtol=0, atol=1e-8)
