@@ -13,6 +13,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
     config.addinivalue_line("markers", "slow: CPU test that takes more than a few seconds")
+    config.addinivalue_line("markers", "gpu_next: CUDA cases written after the round's last GPU session; "
+                                       "not part of -m gpu until they have run on a B200 once")
 
 
 def golden(name):

@@ -2,7 +2,9 @@
 (BASELINE.json configs[3]/[4] at a basis whose dressed V_abcd fits one B200).
 Prints ms per batch, ms per right-hand side and FP64 TFLOP/s from the plan's own per-vector
 flop count, for batch sizes r = 1, 4, 16, 32(, 64).  Diagnostic, not the bench line.
-usage: bench_eom.py [cutoff=13] [ccsd_sweeps=3] [max_batch=32]"""
+usage: bench_eom.py [cutoff=13] [ccsd_sweeps=3] [max_batch=32] [virtual]
+virtual: V_abcd is never materialised; its dressed form is the operator ccsd.DressedLadder (not
+yet run on a GPU in round 1) and only the dressed blocks sigma reads are built."""
 import json
 import os
 import sys
@@ -17,6 +19,7 @@ from pymes_b200.integral.partition import KEYS
 cutoff = float(sys.argv[1]) if len(sys.argv) > 1 else 13.0
 sweeps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 max_batch = int(sys.argv[3]) if len(sys.argv) > 3 else 32
+virtual = len(sys.argv) > 4 and sys.argv[4] == "virtual"
 torch.cuda.set_device(0)
 plog.set_quiet(True)
 no = bench.N_ELE // 2
@@ -25,15 +28,15 @@ m.init_single_basis(cutoff)
 m.k_cutoff, m.gamma = bench.K_CUTOFF, None
 nv = m.n_orb - no
 fock = bk.asdev(bench.build_fock(m, no))
-dV = m.eval_2b_blocks(no, list(KEYS), bench.tc_parts(m))
+dV = m.eval_2b_blocks(no, list(KEYS), bench.tc_parts(m), virtual=("abcd",) if virtual else ())
 cc = ccsd.CCSD(no)
 cc.setup(fock, dV)
 for _ in range(sweeps):
     e = cc.sweep()
 T1, T2 = cc._st["T1"], cc._st["T2"]
 ft = cc.get_T1_dressed_fock(fock, T1, dV)
-dVd = cc.get_T1_dressed_V(T1, dV)
-del dV
+dVd = cc.get_T1_dressed_V(T1, dV, {k: None for k in eom_ccsd.V_KEYS_USED} if virtual else None)
+del dV, cc
 t0 = torch.cuda.Event(enable_timing=True)
 t1 = torch.cuda.Event(enable_timing=True)
 t0.record()
@@ -42,7 +45,7 @@ t1.record()
 torch.cuda.synchronize()
 n_direct = sum(len(p["direct"]) for p in plan.programs.values())
 n_two = sum(len(p["twostep"]) for p in plan.programs.values())
-out = {"n_orb": m.n_orb, "n_occ": no, "n_virt": nv, "E_ccsd_after_sweeps": sum(e[:3]),
+out = {"n_orb": m.n_orb, "n_occ": no, "n_virt": nv, "E_ccsd_after_sweeps": sum(e[:3]), "virtual_abcd": virtual,
        "plan_ms": t0.elapsed_time(t1), "hoist_flops": plan.hoist_flops,
        "flops_per_vector": plan.flops_per_vector, "direct_groups": n_direct, "twostep_groups": n_two,
        "ladder_flops_per_vector": 2.0 * no**2 * nv**4, "batches": []}
