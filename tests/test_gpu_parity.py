@@ -401,6 +401,12 @@ def test_ueg_virtual_block_host_cases():
     host.test_ueg_virtual_block_descriptor(None)
 
 
+def test_eom_with_never_materialised_abcd():
+    """Dressed V_abcd as an operator (ccsd.DressedLadder) over a generated V_abcd: sigma, batches
+    and diagonals equal the dense path (first passed on a B200 at the end of round 1)."""
+    host.test_eom_with_never_materialised_abcd(None)
+
+
 def _tc_model(n_ele, cutoff, rs=0.5):
     from pymes_b200.model import ueg
     m = ueg.UEG(n_ele, n_ele // 2, n_ele // 2, rs)

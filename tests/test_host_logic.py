@@ -14,7 +14,6 @@ TOL = dict(rtol=1e-10, atol=1e-11)
 
 
 DEVICE = "cpu"      # tests/test_gpu_parity.py re-runs these bodies with DEVICE = "cuda"
-RUN_PENDING_GPU_CASES = False      # tests/test_gpu_next.py switches the not-yet-GPU-validated cases on
 
 
 def _t(x):
@@ -396,8 +395,6 @@ def test_ueg_virtual_block_descriptor(cpu_abi):
     raw = m.virtual_block((no,) * 4, (nv,) * 4, W0a=W0a, W1a=W1a, W0s=W0s, compressed=False)
     assert raw.nz is None and virt.nz is not None
     np.testing.assert_allclose(_n(bk.contract("abcd,cdij->abij", raw, tau)), _n(ref), rtol=0, atol=1e-13)
-    if cpu_abi is None and not RUN_PENDING_GPU_CASES:
-        return          # the cases below joined after the round's last GPU session: emulator only for now
     # an output layout that would put the generated operand on the column side: the roles
     # are swapped back (it can only be produced as the row operand)
     outp = bk.empty(no, no, nv, nv).permute(2, 3, 0, 1)
