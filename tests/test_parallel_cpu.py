@@ -192,3 +192,48 @@ def test_sharded_eom_sigma_and_davidson_world2(cpu_abi):
         np.testing.assert_allclose(s1, S1.numpy(), rtol=0, atol=1e-12)
         np.testing.assert_allclose(s2, S2.numpy(), rtol=0, atol=1e-12)
         np.testing.assert_allclose(np.sort(roots), np.sort(g["eom_e"]), rtol=0, atol=1e-8)
+
+
+def _feast_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests import abi_emulator
+        abi_emulator.install(_Patch())
+        from pymes_b200 import log, parallel
+        from pymes_b200.solver import feast_eom_ccsd
+        log.set_quiet(True)
+        g, no, ft, dVd, T2 = _eom_inputs()
+        gf = np.load(os.path.join(ROOT, "tests", "golden", "feast_LiH.npz"))
+        fe = feast_eom_ccsd.FEAST_EOM_CCSD(no, e_c=float(gf["e_c"]), e_r=float(gf["e_r"]), n_trial=2, max_iter=3,
+                                           comm=parallel.Comm())
+        d1, d2 = fe.get_diag_singles(ft, dVd, T2), fe.get_diag_doubles(ft, dVd, T2)
+        fe.u_singles, fe.u_doubles = [gf["u1"].copy()], [gf["u2"].copy()]
+        q1, q2 = fe._gcrotmk(0, complex(gf["z"]), d1, d2, ft, dVd, T2)
+        assert fe._plan.shard is not None
+        q.put((rank, np.asarray(q1).copy(), np.asarray(q2).copy(), float(fe.ls_residuals[0])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_feast_linear_solve_world2(cpu_abi):
+    """One shifted FEAST linear solve with the sigma product sharded over two ranks reproduces
+    the reference's GCROT iterate (feast_eom_ccsd.py:293-350) like the single-process solve."""
+    gf = np.load(os.path.join(ROOT, "tests", "golden", "feast_LiH.npz"))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30300 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_feast_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=900) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    nrm = np.sqrt(np.sum(abs(gf["q1"]) ** 2) + np.sum(abs(gf["q2"]) ** 2))
+    for rank, q1, q2, resid in res:
+        assert resid < 1e-4
+        err = np.sqrt(np.sum(abs(q1 - gf["q1"]) ** 2) + np.sum(abs(q2 - gf["q2"]) ** 2)) / nrm
+        assert err < 1e-6, err
