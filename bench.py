@@ -169,8 +169,9 @@ def run_reference(args):
             "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(warmup, 1),
             "ms_per_step": base["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args.gpus, no), V_abcd="dense numpy array (sample basis)",
-                           parallelism="host threads", sample=base["sample"]),
+            # the arm's config is OUR arm's config (the driver pairs the two lines by it); what was
+            # actually timed -- a bounded sample of that workload -- is described in cpu_baseline
+            "config": workload_config(args.gpus, no),
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
