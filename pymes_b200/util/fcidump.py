@@ -74,6 +74,76 @@ def read(fcidump_file="FCIDUMP", is_tc=False):
     return n_elec, n_orb, e_core, eps, h, V
 
 
+def read_blocks(fcidump_file="FCIDUMP", is_tc=False, rows=None, sharded_dims=None):
+    """Same file, same symmetry fill as :func:`read`, but the two-body integrals go straight into
+    the 16 partition blocks of ``integral.partition`` -- V_pqrs (nP^4 doubles: 732 GB for the
+    o = 50, v = 500 configuration) never exists.
+
+    ``rows = (lo, n)`` with ``sharded_dims = {key: dim}`` (``parallel.SHARD_DIMS``) keeps, for the
+    listed keys, only the virtual-orbital rows [lo, lo+n) along that dimension: what one rank of
+    a sharded run holds.  -> (n_elec, n_orb, e_core, epsilon_p, h_pq, {key: ndarray})"""
+    from ..integral.partition import KEYS, OCCUPIED
+    print_logging_info("Reading " + fcidump_file + " into partition blocks...", level=1)
+    e_core = 0.0
+    sharded_dims = sharded_dims or {}
+    with open(fcidump_file, "r") as fh:
+        n_orb, n_elec = _header(fh)
+        no = n_elec // 2
+        nv = n_orb - no
+        eps = np.zeros(n_orb)
+        h = np.zeros((n_orb, n_orb))
+        pattern, blocks, window = {}, {}, {}
+        for key in KEYS:
+            pat = tuple(ch in OCCUPIED for ch in key)
+            pattern[pat] = key
+            shape = [no if o else nv for o in pat]
+            window[key] = None
+            if rows is not None and key in sharded_dims:
+                shape[sharded_dims[key]] = int(rows[1])
+                window[key] = (sharded_dims[key], int(rows[0]), int(rows[1]))
+            blocks[key] = np.zeros(shape)
+
+        def put(p, q, r, s, val):
+            idx = (p, q, r, s)
+            pat = tuple(x < no for x in idx)
+            key = pattern[pat]
+            loc = [x if o else x - no for x, o in zip(idx, pat)]
+            w = window[key]
+            if w is not None:
+                loc[w[0]] -= w[1]
+                if not 0 <= loc[w[0]] < w[2]:
+                    return
+            blocks[key][tuple(loc)] = val
+
+        for line in fh:
+            fields = line.split()
+            if len(fields) != 5:
+                if not fields:
+                    continue
+                raise ValueError("malformed FCIDUMP line: %r" % line)
+            val = float(fields[0])
+            p, r, q, s = (int(x) for x in fields[1:])
+            if abs(val) < _TINY:
+                continue
+            if p and q and r and s:
+                p, q, r, s = p - 1, q - 1, r - 1, s - 1
+                put(p, q, r, s, val)
+                if is_tc:
+                    put(q, p, s, r, val)
+                else:
+                    put(r, q, p, s, val)
+                    put(r, s, p, q, val)
+                    put(p, s, r, q, val)
+            elif p == q == r == s == 0:
+                e_core = val
+            elif p and not (q or r or s):
+                eps[p - 1] = val
+            elif p and r and not (q or s):
+                h[r - 1, p - 1] = val
+                h[p - 1, r - 1] = val
+    return n_elec, n_orb, e_core, eps, h, blocks
+
+
 def write(fcidump_file, n_elec, h_pq, V_pqrs, e_core=0.0, is_tc=False, ms2=0, thresh=_TINY):
     """Write integrals so that ``read(file, is_tc)`` reproduces them.
 

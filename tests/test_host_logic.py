@@ -228,6 +228,34 @@ def test_fcidump_roundtrip(tmp_path):
         np.testing.assert_array_equal(V, g["V"])
 
 
+@pytest.mark.parametrize("tag,is_tc", [("LiH_321g", False), ("LiH_tc", True)])
+def test_fcidump_read_blocks_equals_partition_of_dense_read(tmp_path, tag, is_tc):
+    """fcidump.read_blocks fills the 16 partition blocks (optionally only one rank's rows of the
+    v^4 / o.v^3 blocks) exactly as slicing the dense tensor of fcidump.read does."""
+    from pymes_b200.integral.partition import part_2_body_int, KEYS
+    from pymes_b200.parallel import SHARD_DIMS
+    from pymes_b200.util import fcidump
+    g = golden("mol_" + tag)
+    path = str(tmp_path / "FCIDUMP")
+    fcidump.write(path, int(g["n_elec"]), g["h"], g["V"], e_core=float(g["e_core"]), is_tc=is_tc)
+    n_elec, n_orb, e_core, eps, h, V = fcidump.read(path, is_tc=is_tc)
+    np.testing.assert_allclose(V, g["V"], rtol=0, atol=1e-15)
+    no = n_elec // 2
+    dense = part_2_body_int(no, V)
+    got = fcidump.read_blocks(path, is_tc=is_tc)
+    assert got[:3] == (n_elec, n_orb, e_core) and sorted(got[5]) == sorted(KEYS)
+    np.testing.assert_array_equal(got[4], h)
+    for key in KEYS:
+        np.testing.assert_array_equal(got[5][key], dense[key])
+    lo, n = 1, (n_orb - no) // 2
+    part = fcidump.read_blocks(path, is_tc=is_tc, rows=(lo, n), sharded_dims=SHARD_DIMS)[5]
+    for key in KEYS:
+        want = dense[key]
+        if key in SHARD_DIMS:
+            want = np.take(want, range(lo, lo + n), axis=SHARD_DIMS[key])
+        np.testing.assert_array_equal(part[key], want)
+
+
 def test_ueg_basis_matches_reference():
     from pymes_b200.model import ueg
     g = golden("ueg_coulomb")
