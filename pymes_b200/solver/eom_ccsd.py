@@ -197,23 +197,29 @@ class SigmaPlan:
 
     def _materialise(self, wsub, items):
         """(alpha, W): a zero-copy permuted view when the group is one plain operand, otherwise
-        the coefficient-weighted sum of the group's operands / hoisted products."""
+        the coefficient-weighted sum of the group's operands / hoisted products.  In a sharded
+        plan a W that carries the output index ``a`` is built for this rank's rows only (the
+        hoisted products are the big replicated memory otherwise: up to o.v^3 each)."""
+        rows = self._rows
         if len(items) == 1 and len(items[0][1]) == 1:
             coef, [(s, n)] = items[0]
-            return coef, self.static[n].permute(*[s.index(ch) for ch in wsub])
+            return coef, rows(wsub, self.static[n].permute(*[s.index(ch) for ch in wsub]))
         ext = {}
         for _, stat in items:
             for s, n in stat:
                 for ch, e in zip(s, self.static[n].shape):
                     ext[ch] = int(e)
+        if self.shard is not None and "a" in wsub:
+            ext["a"] = self.shard.na
         W = bk.zeros(*[ext[ch] for ch in wsub])
         for coef, stat in items:
             if len(stat) == 1:
                 s, n = stat[0]
-                bk.axpby(coef, self.static[n].permute(*[s.index(ch) for ch in wsub]), 1.0, W)
+                bk.axpby(coef, rows(wsub, self.static[n].permute(*[s.index(ch) for ch in wsub])), 1.0, W)
             else:
                 (s1, n1), (s2, n2) = stat
-                bk.contract_terms(wsub, [(coef, s1, self.static[n1], s2, self.static[n2])], out=W, beta=1.0)
+                bk.contract_terms(wsub, [(coef, s1, rows(s1, self.static[n1]), s2, rows(s2, self.static[n2]))],
+                                  out=W, beta=1.0)
         return 1.0, W
 
     # ---- execution -----------------------------------------------------
@@ -229,9 +235,8 @@ class SigmaPlan:
         with a shard, out_t holds the local rows of ``a`` only."""
         ct = bk.contract_terms
         rows = self._rows
-        for wsub, usub, uname, out, (alpha, W) in prog["direct"]:
-            ct("r" + out, [(alpha, wsub, rows(wsub, W), "r" + usub, rows("r" + usub, U[uname]))],
-               out=out_t, beta=1.0)
+        for wsub, usub, uname, out, (alpha, W) in prog["direct"]:      # W: local rows already
+            ct("r" + out, [(alpha, wsub, W, "r" + usub, rows("r" + usub, U[uname]))], out=out_t, beta=1.0)
         for Z, zsub, ysub, out, items in prog["twostep"]:
             Y = None
             for coef, xsub, xn, usub, uname in items:
