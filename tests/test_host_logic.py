@@ -42,6 +42,37 @@ def test_library_exports_every_declared_symbol():
     assert lib.pmb_version() == 100
 
 
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """Size and field offsets of every struct of include/pymes_b200.h as gcc lays them out ==
+    the ctypes mirrors in pymes_b200/_lib.py (the descriptors cross the C ABI by pointer)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from pymes_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    pairs = {"pmb_term_t": _lib.Term, "pmb_contract_t": _lib.Contract, "pmb_bdot_t": _lib.Bdot,
+             "pmb_gemv_t": _lib.Gemv, "pmb_ueg_t": _lib.Ueg, "pmb_ueg_operand_t": _lib.UegOperand}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "pymes_b200.h"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append('printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["return 0;", "}"]
+    src, exe = tmp_path / "layout.c", tmp_path / "layout"
+    src.write_text("\n".join(lines))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = {}
+    for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines():
+        cname, fname, val = ln.split()
+        got[(cname, fname)] = int(val)
+    for cname, cls in pairs.items():
+        assert got[(cname, "size")] == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+
+
 def test_missing_cuda_fails_loudly():
     from pymes_b200 import backend as bk
     if torch.cuda.is_available():
