@@ -121,15 +121,20 @@ class FEAST_EOM_CCSD(EOM_CCSD):
         self.ls_matvecs += len(vecs)
         return [_CVec(out[2 * k], out[2 * k + 1]) for k in range(len(vecs))]
 
-    def solve_shifted_systems(self, plan, diag, zs, rhs):
-        """Solve (z_s - H-bar) x_s = rhs_s for every s at once (``rhs``: list of real flat
-        device vectors, ``zs``: complex shifts).  Right-preconditioned restarted GMRES advanced in
-        lock-step over the systems; returns the list of complex solutions (_CVec)."""
+    def solve_shifted_systems(self, plan, diag, zs, rhs, hscale=1.0):
+        """Solve (z_s - hscale * H-bar) x_s = rhs_s for every s at once (``rhs``: list of flat
+        device vectors, real tensors or complex ``_CVec``; ``zs``: complex shifts; ``hscale``: a
+        complex scalar, 1 for FEAST, i*dt for the real-time propagator of rt_eom_ccsd.py).
+        Right-preconditioned restarted GMRES advanced in lock-step over the systems; returns the
+        list of complex solutions (_CVec)."""
         nsys = len(zs)
-        zero = torch.zeros_like(rhs[0])
-        bnorm = [np.sqrt(bk.dots([b], b).item()) for b in rhs]
+        hscale = complex(hscale)
+        first = rhs[0].re if isinstance(rhs[0], _CVec) else rhs[0]
+        zero = torch.zeros_like(first)
+        rhs = [b if isinstance(b, _CVec) else _CVec(b, zero) for b in rhs]
+        bnorm = [np.sqrt(bk.dots([b.re], b.re).item() + bk.dots([b.im], b.im).item()) for b in rhs]
         x = [None] * nsys
-        res = [_CVec(b, zero) for b in rhs]                 # x0 = 0 -> r0 = b
+        res = list(rhs)                                     # x0 = 0 -> r0 = b
         rnorm = list(bnorm)
         active = [s for s in range(nsys) if bnorm[s] > 0]
         for _outer in range(self.ls_max_iter):
@@ -148,7 +153,10 @@ class FEAST_EOM_CCSD(EOM_CCSD):
                 HP = self._sigma_c(plan, P)
                 nxt = []
                 for s, p, hp in zip(running, P, HP):
-                    w = _caxpy(_CVec(bk.lincomb([-1.0], [hp.re]), bk.lincomb([-1.0], [hp.im])), [zs[s]], [p])
+                    if hscale == 1.0:
+                        w = _caxpy(_CVec(bk.lincomb([-1.0], [hp.re]), bk.lincomb([-1.0], [hp.im])), [zs[s]], [p])
+                    else:
+                        w = _caxpy(_CVec(zero, zero), [zs[s], -hscale], [p, hp])
                     for _ in range(2):                      # Gram-Schmidt with one refinement
                         h = _cdots(V[s], w)
                         w = _caxpy(w, list(-h), V[s])
@@ -174,7 +182,7 @@ class FEAST_EOM_CCSD(EOM_CCSD):
                 upd.append(s)
             HX = self._sigma_c(plan, [x[s] for s in upd])
             for s, hx in zip(upd, HX):
-                r = _caxpy(_CVec(rhs[s], zero), [-zs[s], 1.0 + 0j], [x[s], hx])
+                r = _caxpy(rhs[s], [-zs[s], hscale], [x[s], hx])
                 res[s] = r
                 rnorm[s] = np.sqrt(bk.dots([r.re], r.re).item() + bk.dots([r.im], r.im).item())
         self.ls_residuals = [rn / bn if bn > 0 else 0.0 for rn, bn in zip(rnorm, bnorm)]

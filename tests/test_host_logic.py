@@ -638,3 +638,59 @@ def test_feast_batched_systems_and_seeded_iteration(cpu_abi):
     assert np.abs(ev.imag).max() < 1e-8
     x, w = feast_eom_ccsd.get_gauss_legendre_quadrature(8)
     assert abs(w.sum() - 2.0) < 1e-14
+
+
+# --------------------------------------------------------------------------
+# RT-EOM-CCSD: one contour-integral propagation step
+# --------------------------------------------------------------------------
+def test_rt_eom_step_matches_reference(cpu_abi):
+    """Two consecutive RT-EOM-CCSD steps (real start state, then the complex result) against the
+    reference run of tests/golden/make_golden.py::sec_rt.  Both sides stop their linear solves at
+    a relative residual of 1e-4 (gcrotmk tol, feast_eom_ccsd.py:346), so the propagated states
+    agree to the solver tolerance, not to round-off."""
+    from pymes_b200.integral.partition import part_2_body_int
+    from pymes_b200.solver import ccsd, rt_eom_ccsd
+    g, m = golden("rt_LiH"), golden("mol_LiH_321g")
+    no = int(m["n_elec"]) // 2
+    cc = ccsd.CCSD(no)
+    dV = part_2_body_int(no, m["V"])
+    ft = cc.get_T1_dressed_fock(m["fock"], g["t1"], dV)
+    dVt = cc.get_T1_dressed_V(g["t1"], dV)
+    rt = rt_eom_ccsd.RT_EOM_CCSD(no, e_c=float(g["e_c"]), e_r=float(g["e_r"]), dt=float(g["dt"]))
+
+    def err(a1, a2, b1, b2):
+        return np.sqrt(np.sum(abs(a1 - b1) ** 2) + np.sum(abs(a2 - b2) ** 2))   # states have norm 1
+
+    q1, q2 = rt.solve(ft, dVt, g["t2"], dt=float(g["dt"]), u_singles=g["u1"].copy(), u_doubles=g["u2"].copy())
+    assert max(rt.ls_residuals) < 1e-4
+    assert abs(np.sum(abs(q1) ** 2) + np.sum(abs(q2) ** 2) - 1.0) < 1e-12
+    assert err(q1, q2, g["q1"], g["q2"]) < 5e-4
+    p1, p2 = rt.solve(ft, dVt, g["t2"], dt=float(g["dt"]), u_singles=g["q1"].copy(), u_doubles=g["q2"].copy())
+    assert err(p1, p2, g["p1"], g["p2"]) < 5e-4
+    # independent check: the contour integral is exp(i H dt) restricted to the eigenvalues of H-bar
+    # inside |lambda - e_c| < e_r (an 8-node quadrature of the Cauchy formula); with converged linear
+    # solves the step must reproduce the quadrature of the dense resolvent exactly
+    nv = g["t2"].shape[0]
+    n = nv * no + nv * nv * no * no
+    plan = rt.plan(ft, dVt, g["t2"])
+    H = _n(plan.apply_packed(_t(np.eye(n)))).T
+    y = np.concatenate([g["u1"].ravel(), g["u2"].ravel()])
+    dt, e_c, e_r = float(g["dt"]), float(g["e_c"]), float(g["e_r"])
+    x, w = np.polynomial.legendre.leggauss(8)
+    theta = -np.pi * x
+    z = (e_c * 1j + e_r * np.exp(1j * theta)) * dt
+    dense = np.zeros(n, dtype=complex)
+    for e in range(8):
+        dense -= w[e] / 2 * e_r * dt * np.exp(1j * theta[e]) * np.linalg.solve(z[e] * np.eye(n) - 1j * dt * H,
+                                                                               np.exp(z[e]) * y)
+    dense /= np.linalg.norm(dense)
+    got = np.concatenate([q1.ravel(), q2.ravel()])
+    ref = np.concatenate([g["q1"].ravel(), g["q2"].ravel()])
+    print("RT step vs dense resolvent quadrature: ours %.2e, reference %.2e; ours - reference %.2e"
+          % (np.linalg.norm(got - dense), np.linalg.norm(ref - dense), np.linalg.norm(got - ref)))
+    assert np.linalg.norm(got - dense) < 5e-4
+    rt.ls_tol, rt.ls_restart = 1e-11, 200        # (restarted GMRES(20) stagnates on the node nearest an eigenvalue)
+    t1, t2 = rt.solve(ft, dVt, g["t2"], dt=dt, u_singles=g["u1"].copy(), u_doubles=g["u2"].copy())
+    tight = np.concatenate([t1.ravel(), t2.ravel()])
+    print("RT step, converged solves, vs dense resolvent quadrature: %.2e" % np.linalg.norm(tight - dense))
+    assert np.linalg.norm(tight - dense) < 1e-8
