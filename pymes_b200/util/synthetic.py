@@ -1,0 +1,78 @@
+"""Synthetic non-hermitian two-body integrals for BASELINE.json configs[2] ("synthetic FCIDUMP,
+o = 50, v = 500, random permutation-symmetric real integrals, non-hermitian CCSD"; recipe of
+SURVEY 8(d)):  V[p,q,r,s] = eps * N(0,1) drawn from a COUNTER-BASED generator keyed on the
+canonical representative of the only symmetry a transcorrelated Hamiltonian keeps,
+(p,q,r,s) ~ (q,p,s,r) (pymes/util/fcidump.py:147-149), so that any sub-block -- in particular one
+rank's row block of V_abcd, 500 GB / N at full size -- can be generated on its own, on any
+device, without V_pqrs ever existing.
+
+The generator is a pure function of (seed, canonical index): splitmix64 finaliser -> two 53-bit
+uniforms -> Box-Muller.  It is evaluated here with numpy integer arithmetic (host); the same
+few lines are what a device-side generated operand would evaluate (round 2)."""
+import numpy as np
+
+_M1 = np.uint64(0xBF58476D1CE4E5B9)
+_M2 = np.uint64(0x94D049BB133111EB)
+_GOLD = np.uint64(0x9E3779B97F4A7C15)
+
+
+def _mix(x):
+    """splitmix64 finaliser on a uint64 array (wrap-around arithmetic)."""
+    with np.errstate(over="ignore"):
+        x = (x ^ (x >> np.uint64(30))) * _M1
+        x = (x ^ (x >> np.uint64(27))) * _M2
+        return x ^ (x >> np.uint64(31))
+
+
+def normal_from_index(seed, idx):
+    """N(0,1) deviates for an array of uint64 counters ``idx`` (deterministic in (seed, idx))."""
+    idx = np.asarray(idx, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        base = _mix(idx * _GOLD + np.uint64(seed) * _M1 + np.uint64(1))
+        a = _mix(base)
+        b = _mix(base ^ _GOLD)
+    u1 = ((a >> np.uint64(11)).astype(np.float64) + 1.0) / 9007199254740993.0      # (0, 1)
+    u2 = (b >> np.uint64(11)).astype(np.float64) / 9007199254740992.0              # [0, 1)
+    return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+
+
+def tc_block(n_orb, lo, ext, seed=0, eps=None):
+    """Block V[lo0:lo0+ext0, ..., lo3:lo3+ext3] of the synthetic tensor (numpy, C order).
+    ``eps`` defaults to 1e-2 / n_orb (small enough for CC to converge)."""
+    eps = 1e-2 / n_orb if eps is None else eps
+    n = np.uint64(n_orb)
+    p, q, r, s = (np.arange(l, l + e, dtype=np.uint64).reshape([-1 if d == k else 1 for d in range(4)])
+                  for k, (l, e) in enumerate(zip(lo, ext)))
+    with np.errstate(over="ignore"):
+        i1 = ((p * n + q) * n + r) * n + s
+        i2 = ((q * n + p) * n + s) * n + r
+    return eps * normal_from_index(seed, np.minimum(i1, i2))
+
+
+def tc_integrals(n_orb, seed=0, eps=None):
+    """The dense V_pqrs [n_orb]^4 (small systems / tests)."""
+    return tc_block(n_orb, (0, 0, 0, 0), (n_orb,) * 4, seed, eps)
+
+
+def tc_fock(no, nv, seed=0, off_diagonal=1e-3):
+    """diag(-2..-1 | +1..+3) plus small NON-symmetric off-diagonal elements."""
+    n = no + nv
+    f = np.diag(np.concatenate([np.linspace(-2.0, -1.0, no), np.linspace(1.0, 3.0, nv)]))
+    idx = np.arange(n * n, dtype=np.uint64).reshape(n, n) + np.uint64(1) << np.uint64(40)
+    off = off_diagonal * normal_from_index(seed, idx)
+    off[np.diag_indices(n)] = 0.0
+    return f + off
+
+
+def tc_blocks(no, nv, keys, seed=0, eps=None, ranges=None):
+    """Named partition blocks (``integral.partition`` keys) generated directly; ``ranges`` =
+    ``{key: {dim: (lo, n)}}`` restricts a dimension to absolute orbital indices (a rank's rows)."""
+    from ..integral.partition import OCCUPIED
+    out = {}
+    for key in keys:
+        lo = [0 if ch in OCCUPIED else no for ch in key]
+        ext = [no if ch in OCCUPIED else nv for ch in key]
+        for dim, (r_lo, r_n) in (ranges or {}).get(key, {}).items():
+            lo[dim], ext[dim] = int(r_lo), int(r_n)
+        out[key] = tc_block(no + nv, lo, ext, seed, eps)
+    return out
