@@ -242,11 +242,11 @@ def run_ours(args):
     if world > 1:
         from pymes_b200 import parallel
         comm = parallel.Comm(dist.group.WORLD)
-        cc = parallel.ShardedCCSD(no, comm)
+        cc = parallel.ShardedCCSD(no, comm, is_dcsd=args.dcsd)
         dV = parallel.build_sharded_hamiltonian(m, no, comm, tc_parts(m), virtual=virtual)
     else:
         from pymes_b200.integral.partition import KEYS
-        cc = ccsd.CCSD(no)
+        cc = ccsd.CCSD(no, is_dcsd=args.dcsd)
         dV = m.eval_2b_blocks(no, list(KEYS), tc_parts(m), virtual=virtual)
     torch.cuda.synchronize()
     t_build = time.time() - t0
@@ -290,7 +290,7 @@ def run_ours(args):
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    F = flops_ccd(no, nv)
+    F = flops_ccd(no, nv, is_dcd=args.dcsd)
     value = F / (ms * 1e-3) / 1e12
 
     # dominant kernel: the particle-particle ladder contraction (this rank's row block)
@@ -351,6 +351,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(args.gpus, no, cutoff, args.dense_abcd), n_orb=nP, n_virt=nv,
+                           **({"method": "DCSD"} if args.dcsd else {}),
                            flops_per_step=F, energy=e_final, build_seconds=t_build),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof}
     if rank == 0:
@@ -373,6 +374,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cutoff", type=float, default=0.0, help="override the plane-wave cutoff (debug)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--dcsd", action="store_true",
+                    help="time a DCSD iteration (the other method of BASELINE configs[1]) instead of CCSD")
     ap.add_argument("--dense-abcd", action="store_true",
                     help="store V_abcd in HBM instead of generating it in the ladder kernel")
     args = ap.parse_args()
