@@ -228,13 +228,15 @@ class ShardedCCSD(ccsd.CCSD):
 
     # ---- driver ----------------------------------------------------------
     def setup(self, t_fock_pq, dict_blocks, level_shift=0., amps=None):
-        if not isinstance(dict_blocks, dict):
-            raise TypeError("ShardedCCSD takes the dictionary of integral blocks (local row blocks "
-                            "for %s)" % sorted(SHARD_DIMS))
         no = self.no
         fock_host = bk.tonumpy(t_fock_pq)
         nv = fock_host.shape[0] - no
         self.shard = Shard(self.comm, nv)
+        if not isinstance(dict_blocks, dict):
+            # the reference call surface: a dense V_pqrs (numpy / tensor) that every rank holds;
+            # each rank keeps views of its row blocks
+            from .integral.partition import part_2_body_int
+            dict_blocks = shard_blocks(part_2_body_int(no, bk.asdev(dict_blocks)), self.shard)
         self.local_rows = self.shard.na
         st = self._st = {}
         st["want_numpy"] = False

@@ -36,7 +36,10 @@ def _worker(rank, world, port, tag, is_dcsd, q):
         shard = parallel.Shard(comm, nv)
         dV = part_2_body_int(no, torch.from_numpy(g["V"].copy()))
         cc = parallel.ShardedCCSD(no, comm, is_dcsd=is_dcsd)
-        r = cc.solve(g["fock"], parallel.shard_blocks(dV, shard), delta_e=1e-12, max_iter=200)
+        if is_dcsd:      # either the dictionary of local row blocks ...
+            r = cc.solve(g["fock"], parallel.shard_blocks(dV, shard), delta_e=1e-12, max_iter=200)
+        else:            # ... or the reference's dense V_pqrs, sliced per rank inside
+            r = cc.solve(g["fock"], g["V"].copy(), delta_e=1e-12, max_iter=200)
         q.put((rank, float(r["ccsd e"]), r["t1"].numpy().copy(), r["t2"].numpy().copy(), cc.iterations,
                shard.lo, shard.na))
     finally:
