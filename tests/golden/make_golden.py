@@ -9,8 +9,10 @@ The unmodified reference (nickirk/pymes @ 734974a) is imported from
 /root/reference with the three shims SURVEY.md 8(c) lists (none touches
 arithmetic): a dummy ``ctf`` module (pymes/solver/dcd.py:4 imports it and never
 uses it), ``gcrotmk(tol=)`` -> ``rtol=`` for scipy >= 1.14, and a seeded
-``np.random``.  Outputs are small ``.npz`` files; the tests never need the
-reference itself.
+``np.random``.  The ``rt`` section needs two more, also outside the arithmetic
+(see ``sec_rt``): ``RT_EOM_CCSD`` never sets ``ls_max_iter`` and still calls the
+ctf-era ``.to_nparray()`` on numpy arrays.  Outputs are small ``.npz`` files; the
+tests never need the reference itself.
 """
 import io
 import os
