@@ -149,13 +149,24 @@ def cpu_sample(steps, warmup, budget_s=150.0):
     for _ in range(steps):
         T1, T2, e, _dt = oc.ccsd_sweep(no, fock, dV, T1, T2, d1, d2, mixer)
     dt = (time.perf_counter() - t0) / max(steps, 1)
+    # the two pieces SURVEY 8(d) asks for beside the whole iteration: CCD.get_residual alone and the
+    # single particle-particle ladder einsum, both as ccd.py writes them (bare np.einsum)
+    t0 = time.perf_counter()
+    oc.doubles_residual(no, fock, T2, dV["klij"], dV["ijab"], dV["abij"], dV["iajb"], dV["iabj"], dV["abcd"])
+    t_res = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    np.einsum("abcd,cdij->abij", dV["abcd"], T2)
+    t_pp = time.perf_counter() - t0
     oc.set_ccd_einsum_mode("optimized")
     F = flops_ccd(no, nP - no)
     return {"value": F / dt / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "port",
             "sample": "TC-UEG 54e rs=%.1f, %d plane waves (o=27, v=%d): %d CCSD+DIIS sweeps of the numpy "
                       "oracle in the reference's einsum modes (ccd.py rows single-threaded c_einsum, "
                       "ccsd.py rows optimize=True/BLAS), %.2f s per sweep" % (RS, nP, nP - no, steps, dt),
-            "seconds_per_step": dt, "n_orb": nP, "energy": float(sum(e))}
+            "seconds_per_step": dt, "n_orb": nP, "energy": float(sum(e)),
+            "doubles_residual_seconds": t_res,
+            "pp_ladder_einsum_seconds": t_pp,
+            "pp_ladder_einsum_gflops": 2.0 * no ** 2 * float(nP - no) ** 4 / t_pp / 1e9}
 
 
 def run_reference(args):
