@@ -11,6 +11,7 @@ PyTorch is used for device memory and streams only.  Every arithmetic kernel is
 in ``libpymes_b200.so``; there is no CPU path.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -243,6 +244,7 @@ def _fill(arr, vals):
 
 
 ALIGN_K_MIN_ELEMENTS = 1 << 16
+SMALL_SIDE_TO_N = os.environ.get("PYMES_B200_SMALL_SIDE_TO_N", "0") == "1"
 
 
 def _unit_index(sub, t):
@@ -342,6 +344,16 @@ def describe_contraction(out_sub, terms, out=None, beta=0.0, conv=None, alloc=No
         m_set, n_set = n_set, m_set
         for t in norm:
             t[1], t[2], t[3], t[4] = t[3], t[4], t[1], t[2]
+    # Experimental (off by default, A/B it with PYMES_B200_SMALL_SIDE_TO_N=1): when one side of
+    # the output is a single occupied index (27 wide: "ci,abcj->abij", "cj,iacb->iajb") putting it
+    # on the N side lets the 64x32 tile waste 5 of 32 columns instead of 37 of 64 rows.
+    if SMALL_SIDE_TO_N and m_set and n_set:
+        m_tot = int(np.prod([ext[ch] for ch in m_set]))
+        n_tot = int(np.prod([ext[ch] for ch in n_set]))
+        if m_tot <= 32 and n_tot >= 1024:
+            m_set, n_set = n_set, m_set
+            for t in norm:
+                t[1], t[2], t[3], t[4] = t[3], t[4], t[1], t[2]
     # a generated operand can only be produced on the row (A) side of the kernel: that
     # outranks the epilogue preference above
     if any(isinstance(t[4], GeneratedOperand) for t in norm):

@@ -415,6 +415,21 @@ def test_matrix_vector_contractions_go_to_gemv(cpu_abi, monkeypatch):
     assert len(called) == n0
 
 
+def test_small_output_side_can_go_to_the_column_group(cpu_abi, monkeypatch):
+    """Opt-in operand-role swap for contractions whose one output side is a single occupied index."""
+    from pymes_b200 import backend as bk
+    rng = np.random.default_rng(6)
+    t1 = rng.standard_normal((17, 5))
+    V = rng.standard_normal((17, 17, 17, 5))                 # V_abci-like: a, b, c, j
+    want = np.einsum("ci,abcj->abij", t1, V)
+    base, _, _ = bk.describe_contraction("abij", [(1.0, "ci", _t(t1), "abcj", _t(V))])
+    assert (base.nm, base.nn) == (1, 3)                      # default: the unit-stride output index on N
+    monkeypatch.setattr(bk, "SMALL_SIDE_TO_N", True)
+    d, _, _ = bk.describe_contraction("abij", [(1.0, "ci", _t(t1), "abcj", _t(V))])
+    assert (d.nm, d.nn) == (3, 1)
+    np.testing.assert_allclose(_n(bk.contract("ci,abcj->abij", _t(t1), _t(V))), want, **TOL)
+
+
 def test_ueg_virtual_block_descriptor(cpu_abi):
     """Never-materialised V block as the row operand of a contraction (pmb_term_t.a_gen):
     the descriptor's axis assignment for the pp ladder, a permuted o.v^3 pattern and a row
