@@ -320,6 +320,13 @@ def run_ours(args):
             "traffic": None, "launches_timed": len(pp_ms), "ms_per_launch": pp_avg,
             "flops_per_launch": pp_flops}
     roof["frac"] = roof["achieved"] / peak if roof["achieved"] else None
+    cal = os.path.join(ROOT, "profiles", "r1_fp64_calibration.json")
+    if os.path.exists(cal):             # context: a plain library DGEMM measured on this pool
+        try:
+            rec = json.load(open(cal))
+            roof["cublas_dgemm_tflops_measured"] = max(v for k, v in rec.items() if k.startswith("dgemm_"))
+        except Exception:               # noqa: BLE001
+            pass
     if clocks.get("sm_mhz"):
         roof["frac_at_observed_clock"] = (roof["achieved"] / (peak * clocks["sm_mhz"] / (clocks["sm_max_mhz"] or 1965))
                                           if roof["achieved"] else None)
