@@ -142,11 +142,14 @@ int pmb_mp2_amplitudes(int no, int nv, int a_lo, int na, const double *eps_i,
                        const int64_t v_str[4], double *T2, pmb_stream_t stream);
 
 /* dT = R * (1 / (e_i + e_j - e_a - e_b + shift)); T += delta * dT;          */
-/* scal[0] += sum dT^2.   ccd.py:123-124,138 ; ccsd.py:152-156,177-179,197   */
+/* scal[0] = sum dT^2.    ccd.py:123-124,138 ; ccsd.py:152-156,177-179,197   */
+/* denom_mode = 1 replaces the sum by the PRODUCT e_i e_j (-e_a)(-e_b): that  */
+/* is what the reference's Brueckner branch executes (ccd.py:118,             */
+/* einsum('i,j,a,b->abij')), reproduced for bug-compatibility.                */
 int pmb_update_doubles(int no, int nv, int a_lo, int na, const double *eps_i,
-                       const double *eps_a, double shift, double delta, const double *R, double *dT,
-                       double *T2, double *scal, void *ws, size_t ws_bytes,
-                       pmb_stream_t stream);
+                       const double *eps_a, double shift, double delta, int denom_mode,
+                       const double *R, double *dT, double *T2, double *scal, void *ws,
+                       size_t ws_bytes, pmb_stream_t stream);
 /* same for singles: dT1 = R1 / (e_i - e_a + shift); T1 += delta * dT1       */
 int pmb_update_singles(int no, int nv, const double *eps_i, const double *eps_a,
                        double shift, double delta, const double *R1, double *dT1,

@@ -115,13 +115,15 @@ def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj,
                 _es_ccd("klcd,dblj->cbkj", V_ijab, Tt))             # ccd.py:202-204
 
     if is_bruekner:                                             # ccd.py:209-211
-        Xac, Xki = fab.copy(), fij.copy()
+        # the reference binds VIEWS of the caller's Fock matrix here, so the in-place
+        # updates of ccd.py:218-221 below modify t_fock_pq itself, sweep after sweep
+        Xac, Xki = fab, fij
     else:                                                       # ccd.py:213-216
         Xac = fab - 0.5 * _es_ccd("adkl,lkdc->ac", Tt, V_ijab)
         Xki = fij + 0.5 * _es_ccd("cdil,lkdc->ki", Tt, V_ijab)
-    if ccd:                                                     # ccd.py:218-221
-        Xac = Xac - 0.5 * _es_ccd("adkl,lkdc->ac", Tt, V_ijab)
-        Xki = Xki + 0.5 * _es_ccd("cdil,lkdc->ki", Tt, V_ijab)
+    if ccd:                                                     # ccd.py:218-221 (in place: `-=`, `+=`)
+        Xac -= 0.5 * _es_ccd("adkl,lkdc->ac", Tt, V_ijab)
+        Xki += 0.5 * _es_ccd("cdil,lkdc->ki", Tt, V_ijab)
 
     ops = {"Xac": Xac, "Xki": Xki, "T": T2, "Tt": Tt, "iajb": V_iajb,
            "iabj": V_iabj}
@@ -142,6 +144,25 @@ def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj,
             continue
         Ex += coef * _es_ccd(sub, ops[a], ops[b])
     return R + Ex + Ex.transpose(1, 0, 3, 2)                    # ccd.py:249-252
+
+
+def drccd_residual(eps_i, eps_a, T2, V_abij, V_aijb, V_iabj, V_ijab):
+    """What ``drccd.get_residual`` (reference drccd.py:10-39) EXECUTES.  The einsum strings of
+    drccd.py:34-35 are not the direct-ring equations of the comment above them: in
+    ``"kbcj, acij -> abij"`` k is summed over V alone and j is a batch index, and in
+    ``"acij, klcd, dblj -> abij"`` k is again summed over V alone with j a batch index.  The
+    restatement spells those sums out."""
+    R = V_abij + eps_a[:, None, None, None] * T2                # "ad,dbij->abij", diagonal f_ab
+    R = R - eps_i[None, None, :, None] * T2                     # "ik,abkj->abij"
+    Tp = T2.transpose(1, 0, 3, 2)                               # T[b,a,j,i]
+    R = R + eps_a[None, :, None, None] * Tp                     # "bd,daji->abij"
+    R = R - eps_i[None, None, None, :] * Tp                     # "jk,baki->abij"
+    R = R + _es("akic,cbkj->abij", V_aijb, T2)                  # drccd.py:33
+    Vs = V_iabj.sum(axis=0)                                     # [b,c,j]   drccd.py:34
+    R = R + _es("bcj,acij->abij", Vs, T2)
+    Ws = V_ijab.sum(axis=0)                                     # [l,c,d]   drccd.py:35
+    R = R + _es("acij,lcd,dblj->abij", T2, Ws, T2)
+    return R
 
 
 def ccd_energy(T2, V_ijab):
@@ -331,9 +352,14 @@ class DIIS:
 # ground-state drivers -- reference ccd.py:24-162, ccsd.py:47-224
 # --------------------------------------------------------------------------
 def ccd_solve(no, fock, V, level_shift=0.0, is_dcd=False, is_diis=True,
-              delta_e=1e-8, max_iter=50, amps=None, trace=None):
+              delta_e=1e-8, max_iter=50, amps=None, trace=None, is_dr_ccd=False, is_bruekner=False):
+    """ccd.py:24-162.  ``is_dr_ccd`` / ``is_bruekner`` restate what those branches execute
+    (ccd.py:95-98, 104-121), including the two things that make ``is_bruekner`` differ from
+    its own comment: the denominator is the PRODUCT e_i e_j e_a e_b (``einsum('i,j,a,b->abij')``,
+    ccd.py:118) and ``fock`` is modified in place by ``doubles_residual`` (its diagonal is what
+    the first quasi-particle energies start from, because ``t_epsilon_*`` are views of it)."""
     dV = partition(no, V)
-    eps_i, eps_a = fock.diagonal()[:no], fock.diagonal()[no:]
+    eps_i, eps_a = fock.diagonal()[:no], fock.diagonal()[no:]     # views, as in ccd.py:40-41
     e_mp2, T2 = mp2(eps_i, eps_a, dV["ijab"], dV["abij"], level_shift)
     if amps is not None:
         T2 = amps
@@ -342,8 +368,16 @@ def ccd_solve(no, fock, V, level_shift=0.0, is_dcd=False, is_diis=True,
     dE, e_last, e, it = abs(e_mp2), e_mp2, 0.0, 0
     while abs(dE) > delta_e and it <= max_iter:
         it += 1
-        R = doubles_residual(no, fock, T2, dV["klij"], dV["ijab"], dV["abij"],
-                             dV["iajb"], dV["iabj"], dV["abcd"], is_dcd)
+        if is_dr_ccd:
+            R = drccd_residual(eps_i, eps_a, T2, dV["abij"], dV["aijb"], dV["iabj"], dV["ijab"])
+        else:
+            R = doubles_residual(no, fock, T2, dV["klij"], dV["ijab"], dV["abij"],
+                                 dV["iajb"], dV["iabj"], dV["abcd"], is_dcd, is_bruekner)
+        if is_bruekner:                                             # ccd.py:104-119
+            Tt = 2.0 * T2 - T2.transpose(1, 0, 2, 3)
+            eps_i = eps_i + 0.5 * np.einsum("ilcd,cdil->i", dV["ijab"], Tt)
+            eps_a = eps_a - 0.5 * np.einsum("klad,adkl->a", dV["ijab"], Tt)
+            d2 = np.einsum("i,j,a,b->abij", eps_i, eps_i, -eps_a, -eps_a) + level_shift
         dT = R / d2
         T2 += dT
         if mixer is not None:
@@ -354,7 +388,8 @@ def ccd_solve(no, fock, V, level_shift=0.0, is_dcd=False, is_diis=True,
         if trace is not None:
             trace.append(dict(e=e, t2=T2.copy(), dt2_norm=np.linalg.norm(dT),
                               t2_norm=np.linalg.norm(T2)))
-    return {"e": e, "t2": T2, "dE": dE, "iterations": it, "e_mp2": e_mp2}
+    return {"e": e, "t2": T2, "dE": dE, "iterations": it, "e_mp2": e_mp2,
+            "hole e": eps_i, "particle e": eps_a}
 
 
 def ccsd_sweep(no, fock, dV, T1, T2, d1, d2, mixer=None, is_dcsd=False):

@@ -552,16 +552,21 @@ def mp2_amplitudes(eps_i, eps_a, shift, V_abij, rows=None):
     return T2
 
 
-def update_doubles(eps_i, eps_a, shift, delta, R, T2, scal, rows=None):
+def update_doubles(eps_i, eps_a, shift, delta, R, T2, scal, rows=None, product_denominator=False):
     """dT = R/D, T2 += delta*dT (in place); scal[0] = |dT|^2.  Returns dT.
-    ``rows=(a_lo, na)``: R and T2 are local row blocks [na,nv,no,no]."""
+    ``rows=(a_lo, na)``: R and T2 are local row blocks [na,nv,no,no].
+    ``product_denominator``: D = e_i e_j e_a e_b + shift (the reference's Brueckner branch,
+    ccd.py:118) instead of e_i + e_j - e_a - e_b + shift."""
+    if not T2.is_contiguous() or not R.is_contiguous():
+        raise ValueError("update_doubles needs contiguous R and T2 (they are indexed flat)")
     lib = _lib.load()
     no, nv = eps_i.numel(), eps_a.numel()
     a_lo, na = rows if rows is not None else (0, nv)
     dT = torch.empty_like(T2)
     ws = scratch().reduce_ws()
     _lib.check(lib.pmb_update_doubles(no, nv, a_lo, na, _ptr(eps_i), _ptr(eps_a), float(shift), float(delta),
-                                      _ptr(R), _ptr(dT), _ptr(T2), _ptr(scal), _ptr(ws), ws.numel() * 8,
+                                      int(bool(product_denominator)), _ptr(R), _ptr(dT), _ptr(T2), _ptr(scal),
+                                      _ptr(ws), ws.numel() * 8,
                                       _stream()), "pmb_update_doubles")
     return dT
 

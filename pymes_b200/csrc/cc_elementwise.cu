@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256)
 // dT = R * (1/D); T += delta*dT; partial sum of dT^2
 __global__ void __launch_bounds__(kReduceThreads)
     update_doubles_kernel(int no, int nv, int a_lo, int na, const double *__restrict__ ei,
-                          const double *__restrict__ ea, double shift, double delta,
+                          const double *__restrict__ ea, double shift, double delta, int denom_mode,
                           const double *__restrict__ R, double *__restrict__ dT, double *__restrict__ T2,
                           double *ws) {
     const size_t n = (size_t)na * nv * no * no;
@@ -142,7 +142,11 @@ __global__ void __launch_bounds__(kReduceThreads)
             const size_t idx = base + off;
             if (idx < n) {
                 const Abij x = split_abij(ab0, rem0 + off, oo, no, nv);
-                const double dinv = 1.0 / (ei[x.i] + ei[x.j] - ea[a_lo + x.a] - ea[x.b] + shift);
+                // denom_mode 1: the PRODUCT e_i e_j (-e_a)(-e_b) that the reference's Brueckner
+                // branch builds with einsum('i,j,a,b->abij') (ccd.py:118), in its order
+                const double den = denom_mode ? ((ei[x.i] * ei[x.j]) * (-ea[a_lo + x.a])) * (-ea[x.b])
+                                              : ei[x.i] + ei[x.j] - ea[a_lo + x.a] - ea[x.b];
+                const double dinv = 1.0 / (den + shift);
                 const double d = r[u] * dinv;
                 dT[idx] = d;
                 T2[idx] = t[u] + delta * d;
@@ -553,15 +557,16 @@ extern "C" int pmb_mp2_amplitudes(int no, int nv, int a_lo, int na, const double
 }
 
 extern "C" int pmb_update_doubles(int no, int nv, int a_lo, int na, const double *eps_i, const double *eps_a,
-                                  double shift, double delta, const double *R, double *dT, double *T2,
-                                  double *scal, void *ws, size_t ws_bytes, pmb_stream_t stream) {
+                                  double shift, double delta, int denom_mode, const double *R, double *dT,
+                                  double *T2, double *scal, void *ws, size_t ws_bytes, pmb_stream_t stream) {
     if (no <= 0 || nv <= 0 || bad_rows(nv, a_lo, na) || !eps_i || !eps_a || !R || !dT || !T2 || !scal)
         return PMB_E_BADARG;
+    if (denom_mode != 0 && denom_mode != 1) return PMB_E_BADARG;
     if (!ws || ws_bytes < pmb_reduce_workspace()) return PMB_E_WORKSPACE;
     const size_t n = (size_t)na * nv * no * no;
     const int blocks = grid_for(n, kReduceThreads, kReduceBlocks);
     update_doubles_kernel<<<blocks, kReduceThreads, 0, (cudaStream_t)stream>>>(
-        no, nv, a_lo, na, eps_i, eps_a, shift, delta, R, dT, T2, (double *)ws);
+        no, nv, a_lo, na, eps_i, eps_a, shift, delta, denom_mode, R, dT, T2, (double *)ws);
     count_launch();
     int rc = cuda_status();
     if (rc) return rc;

@@ -28,7 +28,7 @@ import torch
 from .. import backend as bk
 from ..log import print_logging_info
 from ..mixer import diis
-from . import mp2
+from . import drccd, mp2
 
 
 class _Whole:
@@ -102,8 +102,16 @@ def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abc
     # (ccd.py:213-221): X_ac = f_ab - c.Tt.V, X_ki = f_ij + c.Tt.V, c = 1/2 (DCD) or 1
     # Only the local rows a in A of X_ac are ever used; X_ki is summed over the local c in A
     # and all-reduced (o^2 numbers).
-    Xac = bk.copy(sh.rows(fock[no:, no:], 0))
-    Xki = bk.copy(fock[:no, :no])
+    if is_bruekner:
+        # ccd.py:209-211 binds t_X_ac / t_X_ki to VIEWS of t_fock_pq, so the in-place updates of
+        # ccd.py:218-221 modify the Fock matrix itself, sweep after sweep.  Reproduced: the
+        # contractions below accumulate into the views of ``fock``.
+        if shard is not None:
+            raise NotImplementedError("is_bruekner is not available in sharded runs")
+        Xac, Xki = fock[no:, no:], fock[:no, :no]
+    else:
+        Xac = bk.copy(sh.rows(fock[no:, no:], 0))
+        Xki = bk.copy(fock[:no, :no])
     c = (1.0 if ccd else 0.5) if not is_bruekner else (0.5 if ccd else 0.0)
     if c != 0.0:
         ct("ac", [(-c, "adkl", Tta, "lkdc", V_ijab)], out=Xac, beta=1.0)
@@ -133,6 +141,15 @@ def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abc
     return R
 
 
+def _write_back(target, dev):
+    """Copy a device tensor into the caller's array / tensor unless it already IS that tensor."""
+    if isinstance(target, torch.Tensor):
+        if target.data_ptr() != dev.data_ptr():
+            target.copy_(dev)
+    elif isinstance(target, np.ndarray) and target.flags.writeable:
+        target[...] = bk.tonumpy(dev)
+
+
 class CCD:
     def __init__(self, no, delta_e=1.e-8, is_dcd=False, is_diis=True, is_dr_ccd=False,
                  is_bruekner=False):
@@ -145,18 +162,18 @@ class CCD:
         self.max_iter = 50
         if self.is_diis:
             self.mixer = diis.DIIS(dim_space=6)
-        if is_dr_ccd:
-            raise NotImplementedError("direct-ring CCD is outside the accelerated hot path "
-                                      "(SURVEY.md 8f)")
 
     # ------------------------------------------------------------------
     def get_residual(self, t_fock_pq, t_T_abij, t_V_klij, t_V_ijab, t_V_abij, t_V_iajb, t_V_iabj,
                      t_V_abcd):
         want_numpy = not isinstance(t_T_abij, torch.Tensor)
-        R = doubles_residual(self.no, bk.asdev(t_fock_pq), bk.asdev(t_T_abij).contiguous(),
+        fock = bk.asdev(t_fock_pq)
+        R = doubles_residual(self.no, fock, bk.asdev(t_T_abij).contiguous(),
                              bk.asdev(t_V_klij), bk.asdev(t_V_ijab), bk.asdev(t_V_abij),
                              bk.asdev(t_V_iajb), bk.asdev(t_V_iabj), bk.asdev(t_V_abcd),
                              is_dcd=self.is_dcd, is_bruekner=self.is_bruekner)
+        if self.is_bruekner:
+            _write_back(t_fock_pq, fock)             # ccd.py:209-221 updates t_fock_pq in place
         return bk.tonumpy(R) if want_numpy else R
 
     def get_energy(self, t_T_abij, t_V_ijab):
@@ -183,6 +200,7 @@ class CCD:
         eps_i, eps_a = bk.asdev(eps_i_host), bk.asdev(eps_a_host)
         V = bk.asdev(t_V_pqrs)
         V_iabj = V[:no, no:, no:, :no]
+        V_aijb = V[no:, :no, :no, no:]
         V_ijab = V[:no, :no, no:, no:]
         V_klij = V[:no, :no, :no, :no]
         V_iajb = V[:no, no:, :no, no:]
@@ -203,6 +221,8 @@ class CCD:
         if amps is not None:
             if isinstance(amps, torch.Tensor):
                 T2 = bk.asdev(amps)          # aliased: updated in place like the reference
+                if not T2.is_contiguous():   # the elementwise kernels index the amplitudes flat
+                    raise ValueError("amps given as a tensor must be contiguous [nv,nv,no,no]")
             else:
                 amps_host = amps
                 T2 = bk.asdev(amps).contiguous()
@@ -214,11 +234,21 @@ class CCD:
         e_ccd = e_dir = e_ex = 0.0
         while abs(dE) > delta_e and iteration <= max_iter:
             iteration += 1
-            R = doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abcd,
-                                 is_dcd=self.is_dcd, is_bruekner=self.is_bruekner)
+            if self.is_dr_ccd:                                       # ccd.py:95-98
+                R = drccd.residual_device(eps_i, eps_a, T2, V_abij, V_aijb, V_iabj, V_ijab)
+            else:
+                R = doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abcd,
+                                     is_dcd=self.is_dcd, is_bruekner=self.is_bruekner)
             if self.is_bruekner:
+                if iteration == 1:
+                    # t_epsilon_i / t_epsilon_a are VIEWS of the Fock diagonal in the reference
+                    # (ccd.py:40-41) until the first rebinding at ccd.py:110: they see what
+                    # get_residual has just done to the matrix
+                    eps_i = torch.diagonal(fock)[:no].contiguous()
+                    eps_a = torch.diagonal(fock)[no:].contiguous()
                 eps_i, eps_a = self._bruekner_energies(eps_i, eps_a, T2, V_ijab)
-            dT = bk.update_doubles(eps_i, eps_a, level_shift, delta, R, T2, scal[3:4])
+            dT = bk.update_doubles(eps_i, eps_a, level_shift, delta, R, T2, scal[3:4],
+                                   product_denominator=self.is_bruekner)         # ccd.py:118
             del R
             if amps_host is not None and (iteration == 1 or not self.is_diis):
                 amps_host[...] = bk.tonumpy(T2)      # the reference mutates `amps` in place
@@ -245,14 +275,17 @@ class CCD:
         print_logging_info("CCD correlation energy = {:.12f}".format(e_ccd), level=1)
         print_logging_info("{:.3f} seconds spent on CCD".format(time.time() - t_start), level=1)
         self.iterations = iteration
+        if self.is_bruekner:
+            _write_back(t_fock_pq, fock)             # the reference leaves its caller's matrix modified
         if want_numpy:
             return {"ccd e": e_ccd, "t2 amp": bk.tonumpy(T2), "hole e": bk.tonumpy(eps_i),
                     "particle e": bk.tonumpy(eps_a), "dE": dE}
         return {"ccd e": e_ccd, "t2 amp": T2, "hole e": eps_i, "particle e": eps_a, "dE": dE}
 
     def _bruekner_energies(self, eps_i, eps_a, T2, V_ijab):
-        """Amplitude-dependent quasi-particle energies, ccd.py:104-121."""
+        """Amplitude-dependent quasi-particle energies, ccd.py:104-113.  i / a are batch indices
+        (in both operands and the output): ``pmb_bdot``, not a matrix product."""
         Tt = bk.tilde(T2)
-        di = bk.contract_terms("i", [(0.5, "ilcd", V_ijab, "cdil", Tt)])
-        da = bk.contract_terms("a", [(-0.5, "klad", V_ijab, "adkl", Tt)])
+        di = bk.bdot("ilcd,cdil->i", V_ijab, Tt, alpha=0.5)
+        da = bk.bdot("klad,adkl->a", V_ijab, Tt, alpha=-0.5)
         return eps_i + di, eps_a + da

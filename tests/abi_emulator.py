@@ -168,10 +168,13 @@ class FakeLib:
         _window(_val(T2), na * nv * no * no)[:] = (v.reshape(na, nv, no, no) / D[a_lo:a_lo + na]).reshape(-1)
         return 0
 
-    def pmb_update_doubles(self, no, nv, a_lo, na, ei, ea, shift, delta, R, dT, T2, scal, ws, wsb, stream):
+    def pmb_update_doubles(self, no, nv, a_lo, na, ei, ea, shift, delta, denom_mode, R, dT, T2, scal, ws, wsb,
+                           stream):
         self.launches += 2
         n = na * nv * no * no
-        D, _, _ = self._denoms(no, nv, ei, ea, shift)
+        D, e_i, e_a = self._denoms(no, nv, ei, ea, shift)
+        if denom_mode:
+            D = np.einsum("i,j,a,b->abij", e_i, e_i, -e_a, -e_a) + shift
         d = _window(_val(R), n) * (1.0 / D[a_lo:a_lo + na]).reshape(-1)
         _window(_val(dT), n)[:] = d
         _window(_val(T2), n)[:] += delta * d

@@ -363,11 +363,48 @@ def sec_rt():
     p1, p2 = quiet(rt.solve, ft, dVt, T2, dt=0.1, u_singles=q1.copy(), u_doubles=q2.copy())
     save("rt_LiH", u1=u1, u2=u2, q1=q1, q2=q2, p1=p1, p2=p2, e_c=0.2, e_r=0.6, dt=0.1, t1=r["t1"], t2=T2)
 
+def sec_variants():
+    """The two CCD variants SURVEY 8(f).2 lists, exactly as the reference EXECUTES them:
+    ``is_dr_ccd`` (drccd.py:10-39; its einsum strings sum k over V alone and carry j as a
+    batch index) and ``is_bruekner`` (ccd.py:104-121, 207-221: product denominator, and the
+    Fock matrix is modified in place through the views t_X_ac / t_X_ki)."""
+    from pymes.solver import drccd
+    rng = np.random.default_rng(23)
+    out = {}
+    no, nv = 3, 5
+    eps_i = -1.0 - rng.random(no)
+    eps_a = 1.0 + rng.random(nv)
+    T2 = rng.standard_normal((nv, nv, no, no)) * 0.3
+    blk = dict(abij=rng.standard_normal((nv, nv, no, no)), aijb=rng.standard_normal((nv, no, no, nv)),
+               iabj=rng.standard_normal((no, nv, nv, no)), ijab=rng.standard_normal((no, no, nv, nv)))
+    out.update(rnd_no=no, rnd_eps_i=eps_i, rnd_eps_a=eps_a, rnd_T2=T2,
+               **{"rnd_" + k: v for k, v in blk.items()})
+    out["rnd_R_drccd"] = drccd.get_residual(eps_i, eps_a, T2, blk["abij"], blk["aijb"], blk["iabj"], blk["ijab"])
+    for tag, path, is_tc in (("LiH", "test_ccsd/FCIDUMP.LiH.321g", False),
+                             ("LiHtc", "test_tc_ccsd/FCIDUMP.LiH.tc", True)):
+        n_elec, nb, e_core, eps, h, V = quiet(fcidump.read, os.path.join(TESTDIR, path), is_tc)
+        no = n_elec // 2
+        fock = hf.construct_hf_matrix(no, h, V)
+        out.update({tag + "_no": no, tag + "_V": V, tag + "_fock": fock})
+        for name, kw, sweeps in (("drccd", dict(is_dr_ccd=True), 4), ("drccd_nodiis", dict(is_dr_ccd=True, is_diis=False), 4),
+                                 ("bruekner", dict(is_bruekner=True), 2),
+                                 ("bruekner_nodiis", dict(is_bruekner=True, is_diis=False), 2),
+                                 ("bruekner_dcd", dict(is_bruekner=True, is_dcd=True), 2)):
+            cc = ccd.CCD(no, **kw)
+            tr = Tracer(cc)
+            f = fock.copy()
+            r = quiet(cc.solve, f, V, max_iter=sweeps - 1, delta_e=1e-14)
+            key = tag + "_" + name
+            out.update({key + "_e": r["ccd e"], key + "_trace": np.array(tr.e), key + "_t2": r["t2 amp"],
+                        key + "_hole": np.array(r["hole e"]), key + "_particle": np.array(r["particle e"]),
+                        key + "_fock_after": f, key + "_dE": r["dE"]})
+    save("ccd_variants", **out)
+
 
 SECTIONS = dict(molecules=sec_molecules, hf_molecule=sec_hf_molecule,
                 residual_random=sec_residual_random,
                 dressing_random=sec_dressing_random, diis=sec_diis,
-                ueg_coulomb=sec_ueg_coulomb, ueg_tc=sec_ueg_tc, feast=sec_feast, rt=sec_rt)
+                ueg_coulomb=sec_ueg_coulomb, ueg_tc=sec_ueg_tc, feast=sec_feast, rt=sec_rt, variants=sec_variants)
 
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(SECTIONS)):

@@ -581,3 +581,26 @@ def test_eom_sigma_medium_random_vs_oracle():
         assert _rel(S2[r].cpu().numpy(), oc.eom_sigma_doubles(no, f, dV, U1[r], U2[r], T2)) < 1e-12
     assert _rel(eom.get_diag_doubles(f, dV, T2), oc.eom_diag_doubles(no, f, dV, T2)) < 1e-12
     assert _rel(eom.get_diag_singles(f, dV, T2), oc.eom_diag_singles(no, f, dV, T2)) < 1e-12
+
+
+# --------------------------------------------------------------------------
+# SURVEY 8(f).2 / 8(f).3 on the CUDA path
+# --------------------------------------------------------------------------
+def test_drccd_residual_matches_reference():
+    host.test_drccd_residual_matches_reference(None)
+
+
+@pytest.mark.parametrize("tag", ["LiH", "LiHtc"])
+@pytest.mark.parametrize("name,kw,sweeps", host.VARIANTS)
+def test_ccd_variants_match_reference(tag, name, kw, sweeps):
+    host.test_ccd_variants_match_reference(None, tag, name, kw, sweeps)
+
+
+def test_ccd_rejects_non_contiguous_amps():
+    host.test_ccd_rejects_non_contiguous_amps(None)
+
+
+def test_rt_eom_step_matches_reference():
+    """One real-time propagation step through the lock-step GMRES on the CUDA kernels (passed on a
+    B200 in round 2's first GPU session as tests/test_gpu_next.py)."""
+    host.test_rt_eom_step_matches_reference(None)

@@ -747,3 +747,54 @@ def test_synthetic_tc_integrals_blockwise_and_ccsd(cpu_abi):
             e = cc.sweep()
         assert abs(sum(e[:3]) - ref["e"]) < 1e-12
         np.testing.assert_allclose(_n(cc._st["T2"]), ref["t2"], rtol=1e-9, atol=1e-14)
+
+
+# --------------------------------------------------------------------------
+# the is_dr_ccd / is_bruekner branches, reproduced as the reference executes them
+# (fixtures: tests/golden/ccd_variants.npz, made by running the reference)
+# --------------------------------------------------------------------------
+VARIANTS = [("drccd", dict(is_dr_ccd=True), 4), ("drccd_nodiis", dict(is_dr_ccd=True, is_diis=False), 4),
+            ("bruekner", dict(is_bruekner=True), 2), ("bruekner_nodiis", dict(is_bruekner=True, is_diis=False), 2),
+            ("bruekner_dcd", dict(is_bruekner=True, is_dcd=True), 2)]
+
+
+def test_drccd_residual_matches_reference(cpu_abi):
+    from pymes_b200.solver import drccd
+    g = golden("ccd_variants")
+    R = drccd.get_residual(g["rnd_eps_i"], g["rnd_eps_a"], g["rnd_T2"], g["rnd_abij"], g["rnd_aijb"],
+                           g["rnd_iabj"], g["rnd_ijab"])
+    np.testing.assert_allclose(R, g["rnd_R_drccd"], rtol=1e-12, atol=1e-12)
+    e = drccd.getEnergy(g["rnd_T2"], g["rnd_ijab"])
+    assert abs(e[0] - 2.0 * np.einsum("abij,ijab->", g["rnd_T2"], g["rnd_ijab"])) < 1e-12 and e[1] == 0.
+
+
+@pytest.mark.parametrize("tag", ["LiH", "LiHtc"])
+@pytest.mark.parametrize("name,kw,sweeps", VARIANTS)
+def test_ccd_variants_match_reference(cpu_abi, tag, name, kw, sweeps):
+    """Energies, amplitudes, quasi-particle energies and -- for is_bruekner -- the Fock matrix the
+    reference leaves modified, after the same number of sweeps (relative: the Brueckner branch
+    diverges to O(10) Eh in the reference itself)."""
+    from pymes_b200.solver import ccd
+    g = golden("ccd_variants")
+    no, V, key = int(g[tag + "_no"]), g[tag + "_V"], tag + "_" + name
+    fock = g[tag + "_fock"].copy()
+    cc = ccd.CCD(no, **kw)
+    r = cc.solve(fock, V, max_iter=sweeps - 1, delta_e=1e-14)
+    assert cc.iterations == sweeps
+    assert abs(r["ccd e"] - g[key + "_e"]) <= 1e-10 * max(1.0, abs(g[key + "_e"]))
+    scale = np.abs(g[key + "_t2"]).max()
+    assert np.abs(r["t2 amp"] - g[key + "_t2"]).max() <= 1e-9 * scale
+    np.testing.assert_allclose(r["hole e"], g[key + "_hole"], rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(r["particle e"], g[key + "_particle"], rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(fock, g[key + "_fock_after"], rtol=1e-10, atol=1e-11)
+    assert abs(r["dE"] - g[key + "_dE"]) <= 1e-10 * max(1.0, abs(g[key + "_dE"]))
+
+
+def test_ccd_rejects_non_contiguous_amps(cpu_abi):
+    from pymes_b200.solver import ccd
+    g = golden("ccd_variants")
+    no, V, fock = int(g["LiH_no"]), g["LiH_V"], g["LiH_fock"]
+    nv = fock.shape[0] - no
+    amps = _t(np.zeros((nv, nv, no, no))).permute(1, 0, 2, 3)[:, :, :, ::1].transpose(2, 3)
+    with pytest.raises(ValueError, match="contiguous"):
+        ccd.CCD(no).solve(_t(fock), _t(V), amps=amps, max_iter=0)
