@@ -116,73 +116,131 @@ class ClockSampler(threading.Thread):
 # ----------------------------------------------------------------------------
 # CPU arm: the oracle's restatement of the reference, in the reference's einsum modes
 # ----------------------------------------------------------------------------
-def cpu_sample(steps, warmup, budget_s=150.0):
-    """Time `steps` CCSD sweeps of the reference algorithm (oracle port) on a bounded sample of
-    the workload: the same TC-UEG 54e Hamiltonian in a smaller plane-wave basis."""
+CPU_SAMPLES = ((5.0, 57), (6.0, 65), (7.0, 81), (8.0, 93), (9.0, 123))    # 54e: cutoff -> plane waves
+CPU_MIN_SAMPLE = 65              # v = 38 > o = 27: the smallest non-degenerate shape
+
+
+class CpuProblem:
+    """TC-UEG 54e in a small plane-wave basis, built by the oracle on the host (the reference's own
+    triple loop restated): the bounded sample of the workload that the CPU legs time."""
+
+    def __init__(self, cutoff):
+        import numpy as np
+        from oracle import cc_oracle as oc, ueg_oracle as uo
+        self.no = N_ELE // 2
+        m = uo.UEG(N_ELE, RS).init_single_basis(cutoff)
+        m.k_cutoff, m.gamma = K_CUTOFF, None
+        self.cutoff, self.n_orb = cutoff, m.n_orb
+        self.fock, self.V = m.tc_hamiltonian(self.no)
+        self.dV = oc.partition(self.no, self.V)
+        self.eps_i = self.fock.diagonal()[:self.no].copy()
+        self.eps_a = self.fock.diagonal()[self.no:].copy()
+        self.np, self.oc = np, oc
+
+    def run(self, sweeps, timed_from=0):
+        """`sweeps` CCSD+DIIS sweeps from the MP2 start in the reference's einsum modes (ccd.py
+        rows bare np.einsum, ccsd.py rows optimize=True); returns (seconds per sweep over the
+        sweeps >= timed_from, energy, T1, T2)."""
+        oc, np = self.oc, self.np
+        oc.set_ccd_einsum_mode("as_written")
+        try:
+            _, T2 = oc.mp2(self.eps_i, self.eps_a, self.dV["ijab"], self.dV["abij"])
+            T1 = np.zeros((self.n_orb - self.no, self.no))
+            d1, d2 = oc.denominators(self.eps_i, self.eps_a)
+            mixer = oc.DIIS(6)
+            e, t0 = (0.0, 0.0, 0.0), None
+            for k in range(sweeps):
+                if k == timed_from:
+                    t0 = time.perf_counter()
+                T1, T2, e, _dt = oc.ccsd_sweep(self.no, self.fock, self.dV, T1, T2, d1, d2, mixer)
+            dt = (time.perf_counter() - t0) / max(sweeps - timed_from, 1) if t0 is not None else None
+        finally:
+            oc.set_ccd_einsum_mode("optimized")
+        return dt, float(sum(e)), T1, T2
+
+
+def pick_cpu_sample(n_sweeps, budget_s):
+    """Largest sample basis whose `n_sweeps` sweeps fit `budget_s`, from a MEASURED rate: one
+    sweep of the 57-plane-wave problem is timed first and scaled by algorithmic flops."""
+    no = N_ELE // 2
+    probe = CpuProblem(CPU_SAMPLES[0][0])
+    t_probe, _, _, _ = probe.run(1)
+    rate = flops_ccd(no, probe.n_orb - no) / t_probe            # flop/s of this host on this code
+    pick = None
+    for cutoff, nP in CPU_SAMPLES:
+        if nP < CPU_MIN_SAMPLE:
+            continue
+        if pick is None or flops_ccd(no, nP - no) / rate * n_sweeps <= budget_s:
+            pick = (cutoff, nP)
+    return pick, rate, t_probe
+
+
+def cpu_sample(steps, warmup, budget_s=150.0, cutoff=None, keep_problem=False):
+    """Time `steps` CCSD sweeps (after `warmup`) of the reference algorithm (oracle port) on a
+    bounded sample of the workload: the same TC-UEG 54e Hamiltonian in a smaller basis."""
     import numpy as np
-    from oracle import cc_oracle as oc, ueg_oracle as uo
     cores = len(os.sched_getaffinity(0))
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     no = N_ELE // 2
-    pick = None
-    for cutoff, nP in ((7.0, 81), (6.0, 65), (5.0, 57), (4.0, 33)):
-        est = flops_ccd(no, nP - no) / 1.5e9 * (steps + warmup)      # ~1.5 GF/s as surveyed
-        pick = (cutoff, nP)
-        if est <= budget_s:
-            break
-    cutoff, nP = pick
-    m = uo.UEG(N_ELE, RS).init_single_basis(cutoff)
-    assert m.n_orb == nP
-    m.k_cutoff, m.gamma = K_CUTOFF, None
-    fock, V = m.tc_hamiltonian(no)
-    oc.set_ccd_einsum_mode("as_written")          # ccd.py uses bare np.einsum
-    dV = oc.partition(no, V)
-    eps_i, eps_a = fock.diagonal()[:no].copy(), fock.diagonal()[no:].copy()
-    _, T2 = oc.mp2(eps_i, eps_a, dV["ijab"], dV["abij"])
-    T1 = np.zeros((nP - no, no))
-    d1, d2 = oc.denominators(eps_i, eps_a)
-    mixer = oc.DIIS(6)
-    e = 0.0
-    for _ in range(warmup):
-        T1, T2, e, _dt = oc.ccsd_sweep(no, fock, dV, T1, T2, d1, d2, mixer)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        T1, T2, e, _dt = oc.ccsd_sweep(no, fock, dV, T1, T2, d1, d2, mixer)
-    dt = (time.perf_counter() - t0) / max(steps, 1)
+    rate = t_probe = None
+    if cutoff is None:
+        (cutoff, _nP), rate, t_probe = pick_cpu_sample(steps + warmup, budget_s)
+    prob = CpuProblem(cutoff)
+    nP = prob.n_orb
+    dt, e, T1, T2 = prob.run(steps + warmup, timed_from=warmup)
+    oc = prob.oc
     # the two pieces SURVEY 8(d) asks for beside the whole iteration: CCD.get_residual alone and the
     # single particle-particle ladder einsum, both as ccd.py writes them (bare np.einsum)
+    oc.set_ccd_einsum_mode("as_written")
+    dV = prob.dV
     t0 = time.perf_counter()
-    oc.doubles_residual(no, fock, T2, dV["klij"], dV["ijab"], dV["abij"], dV["iajb"], dV["iabj"], dV["abcd"])
+    oc.doubles_residual(no, prob.fock, T2, dV["klij"], dV["ijab"], dV["abij"], dV["iajb"], dV["iabj"], dV["abcd"])
     t_res = time.perf_counter() - t0
     t0 = time.perf_counter()
     np.einsum("abcd,cdij->abij", dV["abcd"], T2)
     t_pp = time.perf_counter() - t0
     oc.set_ccd_einsum_mode("optimized")
     F = flops_ccd(no, nP - no)
-    return {"value": F / dt / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "port",
-            "sample": "TC-UEG 54e rs=%.1f, %d plane waves (o=27, v=%d): %d CCSD+DIIS sweeps of the numpy "
-                      "oracle in the reference's einsum modes (ccd.py rows single-threaded c_einsum, "
-                      "ccsd.py rows optimize=True/BLAS), %.2f s per sweep" % (RS, nP, nP - no, steps, dt),
-            "seconds_per_step": dt, "n_orb": nP, "energy": float(sum(e)),
-            "doubles_residual_seconds": t_res,
-            "pp_ladder_einsum_seconds": t_pp,
-            "pp_ladder_einsum_gflops": 2.0 * no ** 2 * float(nP - no) ** 4 / t_pp / 1e9}
+    out = {"value": F / dt / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+           "sample": "TC-UEG 54e rs=%.1f, %d plane waves (o=27, v=%d): %d CCSD+DIIS sweeps (after %d untimed) of "
+                     "the numpy oracle in the reference's einsum modes (ccd.py rows single-threaded c_einsum, "
+                     "ccsd.py rows optimize=True/BLAS), %.2f s per sweep" % (RS, nP, nP - no, steps, warmup, dt),
+           "seconds_per_step": dt, "n_orb": nP, "n_virt": nP - no, "cutoff": cutoff, "sweeps_total": steps + warmup,
+           "energy": e, "flops_per_step": F,
+           "doubles_residual_seconds": t_res,
+           "pp_ladder_einsum_seconds": t_pp,
+           "pp_ladder_einsum_gflops": 2.0 * no ** 2 * float(nP - no) ** 4 / t_pp / 1e9}
+    if keep_problem:
+        out["_problem"] = prob
+    if rate is not None:
+        out["sizing"] = "sample chosen from a measured rate: one 57-plane-wave sweep took %.2f s = %.2f GF/s" \
+                        % (t_probe, rate / 1e9)
+    return out
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's algorithm on the host cores (oracle port), on a bounded
+    sample of the workload.  The line's `config` describes WHAT WAS TIMED (n_orb, n_virt of the
+    sample) and names the workload it samples; `value` is the FP64 rate of that sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = args.steps, args.warmup
-    base = cpu_sample(steps, min(warmup, 1))
+    steps, warmup = args.steps, min(args.warmup, 1)
+    base = cpu_sample(steps, warmup, budget_s=150.0)
     no = N_ELE // 2
+    nP = base["n_orb"]
     line = {"impl": "reference", "metric": "ccsd_iteration_fp64_tflops", "value": base["value"],
-            "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(warmup, 1),
+            "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": base["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            # the arm's config is OUR arm's config (the driver pairs the two lines by it); what was
-            # actually timed -- a bounded sample of that workload -- is described in cpu_baseline
-            "config": workload_config(args.gpus, no),
+            "config": {"workload": "TC-UEG 54e rs=%.1f CCSD+DIIS iteration, plane-wave cutoff %g: BOUNDED SAMPLE of the "
+                                   "cutoff-%g workload (the reference cannot hold that V: 563 GB)"
+                                   % (RS, base["cutoff"], CUTOFF_FOR_GPUS[args.gpus]),
+                       "method": "CCSD", "correlator": "trunc k_c=%g" % K_CUTOFF, "n_occ": no, "n_orb": nP,
+                       "n_virt": nP - no, "flops_per_step": base["flops_per_step"], "energy": base["energy"],
+                       "same_config_as_gpu_arm": False,
+                       "note": "the GPU arm times this same %d-orbital problem in its `same_config` field; "
+                               "that ratio is measured, the one against the 515-orbital line is a rate ratio" % nP},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
@@ -222,6 +280,82 @@ def build_fock(m, no):
     return fock
 
 
+def calibrate(torch):
+    """The two roofline denominators MEASURED_PEAKS.json lacks or that should be re-measured on
+    THIS box, with the driver's own recipe (torch library calls, CUDA events, best of 10):
+    cuBLAS DGEMM 8192^3 (burst) and a device-to-device copy of 2 GiB (read + write bytes)."""
+    out = {}
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    c = torch.empty(n, n, dtype=torch.float64, device="cuda")
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.matmul(a, b, out=c)
+    best = 1e30
+    for _ in range(10):
+        ev0.record()
+        torch.matmul(a, b, out=c)
+        ev1.record()
+        torch.cuda.synchronize()
+        best = min(best, ev0.elapsed_time(ev1))
+    out["dgemm_tflops"] = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    del a, b, c
+    x = torch.empty(1 << 28, dtype=torch.float64, device="cuda")      # 2 GiB
+    y = torch.empty_like(x)
+    x.fill_(1.0)
+    y.copy_(x)
+    best = 1e30
+    for _ in range(10):
+        ev0.record()
+        y.copy_(x)
+        ev1.record()
+        torch.cuda.synchronize()
+        best = min(best, ev0.elapsed_time(ev1))
+    out["d2d_copy_gbs"] = 2.0 * x.numel() * 8 / (best * 1e-3) / 1e9
+    out["how"] = "torch.matmul f64 8192^3 and tensor.copy_ over 2 GiB, best of 10, CUDA events, this run"
+    del x, y
+    torch.cuda.empty_cache()
+    return out
+
+
+def same_config_leg(cpu, steps_total, torch):
+    """The problem the CPU leg timed (TC-UEG 54e in `cpu['n_orb']` plane waves), through the public
+    API with HOST buffers on this GPU: numpy Fock / V_pqrs in, `steps_total` CCSD+DIIS sweeps with the
+    amplitudes crossing pinned host memory every sweep (`CCSD.sweep_host`).  Same start (MP2), same
+    number of sweeps as the CPU leg, so the energies are directly comparable."""
+    from pymes_b200.solver import ccsd
+    prob = cpu.pop("_problem", None) or CpuProblem(cpu["cutoff"])    # oracle-built host arrays: shared inputs
+    no, nP = prob.no, prob.n_orb
+    nv = nP - no
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    cc = ccsd.CCSD(no)
+    cc.setup(prob.fock, prob.V)
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t0
+    t1h = torch.zeros((nv, no), dtype=torch.float64).pin_memory()
+    t2h = torch.empty((nv, nv, no, no), dtype=torch.float64).pin_memory()
+    t1h.copy_(cc._st["T1"])
+    t2h.copy_(cc._st["T2"])
+    times = []
+    e = None
+    for _ in range(steps_total):
+        t0 = time.perf_counter()
+        e = cc.sweep_host(t1h, t2h)
+        times.append(time.perf_counter() - t0)
+    e_gpu = e[0] + e[1] + e[2]
+    n_timed = max(1, steps_total - 1)
+    gpu_s = sum(times[-n_timed:]) / n_timed                # first sweep carries one-time allocations
+    return {"n_orb": nP, "n_virt": nv, "n_occ": no, "sweeps": steps_total,
+            "gpu_seconds_per_step": gpu_s, "gpu_setup_seconds_incl_h2d_of_V": t_setup,
+            "cpu_seconds_per_step": cpu["seconds_per_step"], "cpu_cores": cpu["cores"],
+            "speedup_measured": cpu["seconds_per_step"] / gpu_s,
+            "energy_gpu": e_gpu, "energy_cpu": cpu["energy"], "abs_energy_diff": abs(e_gpu - cpu["energy"]),
+            "h2d_bytes_per_step": (t1h.numel() + t2h.numel()) * 8, "d2h_bytes_per_step": (t1h.numel() + t2h.numel()) * 8 + 64,
+            "what": "same inputs, same start, same sweep count on both sides; GPU side through CCSD.sweep_host "
+                    "with host buffers (launch-latency bound at this size: ~500 kernels per sweep)"}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -242,6 +376,9 @@ def run_ours(args):
     plog.set_quiet(True)
     no = N_ELE // 2
     cutoff = args.cutoff if args.cutoff else CUTOFF_FOR_GPUS[args.gpus]
+    cal = calibrate(torch) if (rank == 0 and not args.no_calibration) else None
+    if world > 1:
+        dist.barrier()
 
     t0 = time.time()
     m = ueg.UEG(N_ELE, no, no, RS)
@@ -320,13 +457,11 @@ def run_ours(args):
             "traffic": None, "launches_timed": len(pp_ms), "ms_per_launch": pp_avg,
             "flops_per_launch": pp_flops}
     roof["frac"] = roof["achieved"] / peak if roof["achieved"] else None
-    cal = os.path.join(ROOT, "profiles", "r1_fp64_calibration.json")
-    if os.path.exists(cal):             # context: a plain library DGEMM measured on this pool
-        try:
-            rec = json.load(open(cal))
-            roof["cublas_dgemm_tflops_measured"] = max(v for k, v in rec.items() if k.startswith("dgemm_"))
-        except Exception:               # noqa: BLE001
-            pass
+    if cal is not None:                 # second denominator: a library DGEMM measured in THIS run
+        roof["peak_measured_dgemm"] = cal["dgemm_tflops"]
+        roof["frac_of_measured_dgemm"] = roof["achieved"] / cal["dgemm_tflops"] if roof["achieved"] else None
+        roof["hbm_copy_gbs_measured"] = cal["d2d_copy_gbs"]
+        roof["calibration"] = cal["how"]
     if clocks.get("sm_mhz"):
         roof["frac_at_observed_clock"] = (roof["achieved"] / (peak * clocks["sm_mhz"] / (clocks["sm_max_mhz"] or 1965))
                                           if roof["achieved"] else None)
@@ -376,11 +511,15 @@ def run_ours(args):
         if args.gpus == 1 and not args.no_cpu:
             cores = len(os.sched_getaffinity(0))
             log("timing the CPU oracle on %d host cores ..." % cores)
-            line["cpu_baseline"] = cpu_sample(2, 0, budget_s=40.0)
+            line["cpu_baseline"] = cpu_sample(2, 1, budget_s=60.0, keep_problem=True)
             # the reference cannot hold this workload's V (563 GB): its time here is EXTRAPOLATED by
             # algorithmic flops from the sample that did run, not measured
             line["cpu_baseline"]["extrapolated_seconds_per_step_at_workload"] = \
                 F / (line["cpu_baseline"]["value"] * 1e12)
+            # ... and the MEASURED same-config ratio: the GPU runs the sample problem itself
+            del cc, dV
+            torch.cuda.empty_cache()
+            line["same_config"] = same_config_leg(line["cpu_baseline"], line["cpu_baseline"]["sweeps_total"], torch)
         else:
             line["cpu_baseline"] = None
         emit(line)
@@ -395,7 +534,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cutoff", type=float, default=0.0, help="override the plane-wave cutoff (debug)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and same_config legs")
+    ap.add_argument("--no-calibration", action="store_true", help="skip the in-run DGEMM / D2D-copy calibration")
     ap.add_argument("--dcsd", action="store_true",
                     help="time a DCSD iteration (the other method of BASELINE configs[1]) instead of CCSD")
     ap.add_argument("--dense-abcd", action="store_true",

@@ -120,7 +120,10 @@ class UEG:
     def _correlator_table(self, correlator, lattice_cutoff):
         """u(n2 (2 pi/L)^2) for every integer n2 = |k|^2 the build can ask for."""
         kmax = int(np.abs(self.k_int()).max())
-        reach = lattice_cutoff + 3 * kmax + 1
+        # largest |component| any kernel asks for: lattice vector +- transfer vectors in the
+        # u_mat sum, and sums of up to four basis vectors in contract_exchange_3_body /
+        # contractP_KWithQ (ueg.py:518-573) -- the latter wins for kmax > lattice_cutoff + 1
+        reach = max(lattice_cutoff + 3 * kmax, 4 * kmax) + 1
         n2 = np.arange(3 * reach * reach + 1, dtype=np.float64)
         vals = np.asarray(correlator(n2 * (2 * np.pi / self.L) ** 2), dtype=np.float64)
         return torch.from_numpy(np.ascontiguousarray(vals)).to(bk.device())
@@ -406,11 +409,17 @@ class VirtualBlock(bk.GeneratedOperand):
         self.lin = st["lin"]
 
     def rows(self, dim, lo, n):
-        """The same block restricted along ``dim`` to LOCAL indices [lo, lo+n)."""
-        new_lo, new_ext = list(self.lo), list(self.shape)
-        new_lo[dim] += int(lo)
-        new_ext[dim] = int(n)
-        return VirtualBlock(self.model, new_lo, new_ext, *self.tables, compressed=self.compressed, _packed=True)
+        """The same block restricted along ``dim`` to LOCAL indices [lo, lo+n) (cached: a sharded
+        sigma asks for the same row block on every application)."""
+        key = (int(dim), int(lo), int(n))
+        cache = self.__dict__.setdefault("_rows_cache", {})
+        if key not in cache:
+            new_lo, new_ext = list(self.lo), list(self.shape)
+            new_lo[dim] += int(lo)
+            new_ext[dim] = int(n)
+            cache[key] = VirtualBlock(self.model, new_lo, new_ext, *self.tables, compressed=self.compressed,
+                                      _packed=True)
+        return cache[key]
 
     def diag_pqpq(self):
         """D[p,q] = V[p,q,p,q] (the ``einsum("abab->ab")`` of eom_ccsd.py:262) without the dense

@@ -399,12 +399,19 @@ def _as_dict_dev(dict_t_V):
 
 
 class EOM_CCSD:
-    def __init__(self, no, n_excit=3, comm=None):
-        """``comm`` (extension, ``pymes_b200.parallel.Comm``): the sigma product is evaluated in
-        (ab) row blocks over the ranks of ``comm``; everything else (trial vectors, the
-        projected eigenproblem) is replicated and identical on every rank."""
+    def __init__(self, no, n_excit=3, comm=None, parallel="rows"):
+        """``comm`` (extension, ``pymes_b200.parallel.Comm``) with ``parallel="rows"``: the sigma
+        product is evaluated in (ab) row blocks over the ranks of ``comm`` (operators too large
+        for one GPU); with ``parallel="vectors"``: every rank holds the full operator and applies
+        it to its share of each batch of new trial vectors, the results are summed over the ranks
+        (no exchange inside sigma).  Everything else (trial vectors, the projected eigenproblem) is
+        replicated and identical on every rank."""
+        if parallel not in ("rows", "vectors"):
+            raise ValueError("parallel must be 'rows' or 'vectors'")
         self.algo_name = "EOM-CCSD"
-        self.comm = comm
+        self.comm = comm if parallel == "rows" else None
+        self.vec_comm = comm if (parallel == "vectors" and comm is not None and comm.size > 1) else None
+        self.max_rhs = 16                 # right-hand sides per batched sigma call (bounds the temporaries)
         self.no = no
         self.n_excit = n_excit
         self.u_singles = []
@@ -420,9 +427,21 @@ class EOM_CCSD:
         return
 
     # ---- sigma ----------------------------------------------------------
+    def invalidate(self):
+        """Forget the compiled sigma program and the cached single-vector sigma (call after
+        modifying the Fock matrix, an integral block or T2 IN PLACE: ``plan`` recognises its
+        operands by identity, and for tensors by their in-place version counter)."""
+        self._plan = self._plan_key = None
+        self._last = None
+
+    @staticmethod
+    def _ident(x):
+        return (id(x), getattr(x, "_version", None))
+
     def plan(self, t_fock_pq, dict_t_V, t_T_abij):
-        """Compile (or fetch) the sigma program for these operands."""
-        key = (id(t_fock_pq), id(dict_t_V), id(t_T_abij))
+        """Compile (or fetch) the sigma program for these operands.  The hoisted H-bar
+        intermediates are built from the operands' CURRENT contents; see :meth:`invalidate`."""
+        key = (self._ident(t_fock_pq), id(dict_t_V), self._ident(t_T_abij))
         if self._plan is None or self._plan_key != key:
             T2 = bk.asdev(t_T_abij).contiguous()
             shard = None
@@ -441,20 +460,24 @@ class EOM_CCSD:
 
     def update_singles(self, t_fock_pq, dict_t_V, t_u_ai, t_u_abij, t_T_abij):
         want_numpy = not isinstance(t_u_abij, torch.Tensor)
-        S1, _ = self._single(t_fock_pq, dict_t_V, t_u_ai, t_u_abij, t_T_abij)
+        S1, _ = self._single(0, t_fock_pq, dict_t_V, t_u_ai, t_u_abij, t_T_abij)
         return bk.tonumpy(S1) if want_numpy else S1
 
     def update_doubles(self, t_fock_pq, dict_t_V, t_u_ai, t_u_abij, t_T_abij):
         want_numpy = not isinstance(t_u_abij, torch.Tensor)
-        _, S2 = self._single(t_fock_pq, dict_t_V, t_u_ai, t_u_abij, t_T_abij)
+        _, S2 = self._single(1, t_fock_pq, dict_t_V, t_u_ai, t_u_abij, t_T_abij)
         return bk.tonumpy(S2) if want_numpy else S2
 
-    def _single(self, t_fock_pq, dict_t_V, t_u_ai, t_u_abij, t_T_abij):
-        """One vector; the (S1, S2) pair is cached so that the reference's
-        update_singles + update_doubles call pair costs one sigma."""
-        key = (id(t_u_ai), id(t_u_abij))
+    def _single(self, half, t_fock_pq, dict_t_V, t_u_ai, t_u_abij, t_T_abij):
+        """One vector; the (S1, S2) pair is kept so that the reference's update_singles +
+        update_doubles call PAIR costs one sigma.  The kept pair serves each half once and only
+        for the very same vector objects (tensors: same in-place version), so a vector that is
+        modified in place between two pairs of calls is never answered from the cache."""
+        key = (self._ident(t_u_ai), self._ident(t_u_abij))
         cache = getattr(self, "_last", None)
-        if cache is not None and cache[0] == key and cache[1] is t_u_ai and cache[2] is t_u_abij:
+        if cache is not None and cache[0] == key and cache[1] is t_u_ai and cache[2] is t_u_abij \
+                and half not in cache[4]:
+            cache[4].add(half)
             return cache[3]
         u1 = bk.asdev(t_u_ai)
         u2 = bk.asdev(t_u_abij)
@@ -462,8 +485,28 @@ class EOM_CCSD:
             raise TypeError("complex vectors: stack real and imaginary parts as two right-hand sides")
         S1, S2 = self.sigma_batched(t_fock_pq, dict_t_V, u1.contiguous()[None], u2.contiguous()[None], t_T_abij)
         res = (S1[0], S2[0])
-        self._last = (key, t_u_ai, t_u_abij, res)
+        self._last = (key, t_u_ai, t_u_abij, res, {half})
         return res
+
+    def sigma_list(self, plan, u1s, u2s):
+        """sigma for lists of device vectors -> lists, in batches of at most ``max_rhs``.  In the
+        "vectors" parallel mode every rank evaluates one contiguous share of the list with its
+        own full operator and the shares are combined by an all-reduce over zero-filled slots."""
+        n, no, nv = len(u1s), self.no, plan.nv
+        vc = self.vec_comm
+        lo, hi = 0, n
+        if vc is not None:
+            per = (n + vc.size - 1) // vc.size
+            lo, hi = min(vc.rank * per, n), min((vc.rank + 1) * per, n)
+        S1 = bk.zeros(n, nv, no) if vc is not None else bk.empty(n, nv, no)
+        S2 = bk.zeros(n, nv, nv, no, no) if vc is not None else bk.empty(n, nv, nv, no, no)
+        for b0 in range(lo, hi, self.max_rhs):
+            b1 = min(b0 + self.max_rhs, hi)
+            plan.apply(torch.stack(u1s[b0:b1]), torch.stack(u2s[b0:b1]), out=(S1[b0:b1], S2[b0:b1]))
+        if vc is not None:
+            vc.all_reduce_sum(S1)
+            vc.all_reduce_sum(S2)
+        return [S1[k] for k in range(n)], [S2[k] for k in range(n)]
 
     def get_diag_singles(self, t_fock_pq, dict_t_V, t_T_abij):
         want_numpy = not isinstance(t_T_abij, torch.Tensor)
@@ -522,9 +565,9 @@ class EOM_CCSD:
             n_done = len(w1s)
             u1s, u2s = orthonormalise(u1s, u2s, start=n_done)
             if n_done < m:
-                S1, S2 = plan.apply(torch.stack(u1s[n_done:]), torch.stack(u2s[n_done:]))
-                w1s += [S1[k] for k in range(m - n_done)]
-                w2s += [S2[k] for k in range(m - n_done)]
+                S1, S2 = self.sigma_list(plan, u1s[n_done:], u2s[n_done:])
+                w1s += S1
+                w2s += S2
             Bn = np.zeros((m, m))
             Bn[:n_done, :n_done] = B
             for l in range(n_done, m):                                 # eom_ccsd.py:103-109

@@ -57,20 +57,42 @@ class _CVec:
         self.re, self.im = re, im
 
 
-def _cdots(vs, w):
-    """<v_k, w> = sum conj(v_k) w for a list of _CVec (numpy complex array)."""
+def _cdots_launch(vs, w):
+    """Launch the dot products <v_k, w> = sum conj(v_k) w for a list of _CVec; returns the device
+    results (no synchronisation) for :func:`_cdots_finish`."""
     flat = []
     for v in vs:
         flat += [v.re, v.im]
-    out = np.zeros(len(vs), dtype=complex)
+    parts = []
     for lo in range(0, len(flat), 16):
         chunk = flat[lo:lo + 16]
-        a = bk.dots(chunk, w.re).cpu().numpy()
-        b = bk.dots(chunk, w.im).cpu().numpy()
-        k0 = lo // 2
-        for k in range(len(chunk) // 2):
+        parts.append((bk.dots(chunk, w.re), bk.dots(chunk, w.im)))
+    return len(vs), parts
+
+
+def _cdots_finish(pending):
+    n, parts = pending
+    out = np.zeros(n, dtype=complex)
+    k0 = 0
+    for a, b in parts:
+        a, b = a.cpu().numpy(), b.cpu().numpy()
+        for k in range(len(a) // 2):
             out[k0 + k] = (a[2 * k] + b[2 * k + 1]) + 1j * (b[2 * k] - a[2 * k + 1])
+        k0 += len(a) // 2
     return out
+
+
+def _cdots(vs, w):
+    """<v_k, w> for a list of _CVec (numpy complex array)."""
+    return _cdots_finish(_cdots_launch(vs, w))
+
+
+def _norms(vecs):
+    """2-norms of a list of _CVec with ONE host synchronisation."""
+    if not vecs:
+        return []
+    sq = torch.stack([bk.dots([v.re], v.re)[0] + bk.dots([v.im], v.im)[0] for v in vecs])
+    return list(np.sqrt(sq.cpu().numpy()))
 
 
 def _caxpy(w, coefs, vs):
@@ -86,7 +108,18 @@ def _caxpy(w, coefs, vs):
 
 class FEAST_EOM_CCSD(EOM_CCSD):
     def __init__(self, no, e_c=0., e_r=1, n_trial=5, max_iter=20, tol=1e-12, **kwargs):
-        super().__init__(no, n_excit=2, comm=kwargs.get("comm"))   # comm: sharded sigma, see EOM_CCSD
+        """Extensions (keywords): ``comm`` (``pymes_b200.parallel.Comm``) and ``parallel``:
+        ``"rows"`` -- every batched sigma is evaluated in (ab) row blocks over the ranks (for
+        operators that do not fit one GPU); ``"systems"`` -- the (quadrature node x trial vector)
+        linear systems of the contour are dealt out over the ranks, every rank applies the full
+        (replicated, never-materialised-V_abcd) operator to its own systems and the only exchanges
+        are the all-reduce of the filtered vectors Q and of H-bar Q (second form)."""
+        self.parallel = kwargs.get("parallel", "rows")
+        if self.parallel not in ("rows", "systems"):
+            raise ValueError("parallel must be 'rows' or 'systems'")
+        comm = kwargs.get("comm")
+        super().__init__(no, n_excit=2, comm=comm if self.parallel == "rows" else None)
+        self.sys_comm = comm if (self.parallel == "systems" and comm is not None and comm.size > 1) else None
         self.e_c = e_c
         self.e_r = e_r
         self.n_trial = n_trial
@@ -99,11 +132,13 @@ class FEAST_EOM_CCSD(EOM_CCSD):
         self.ls_restart = 20         # scipy's default m
         self.n_nodes = 8             # feast:97
         self.max_rhs = 64            # real right-hand sides per batched sigma call
+        self.max_systems = None      # systems advanced together (None: all); bounds the Krylov memory
         self.u_singles = []
         self.u_doubles = []
         self.eigvals = np.array([self.e_c - self.e_r, self.e_c + self.e_r])
         self.eigvecs = None
         self.ls_matvecs = 0
+        self.ls_residuals = []
 
     def dump_log(self):
         pass
@@ -122,17 +157,28 @@ class FEAST_EOM_CCSD(EOM_CCSD):
         return [_CVec(out[2 * k], out[2 * k + 1]) for k in range(len(vecs))]
 
     def solve_shifted_systems(self, plan, diag, zs, rhs, hscale=1.0):
-        """Solve (z_s - hscale * H-bar) x_s = rhs_s for every s at once (``rhs``: list of flat
-        device vectors, real tensors or complex ``_CVec``; ``zs``: complex shifts; ``hscale``: a
-        complex scalar, 1 for FEAST, i*dt for the real-time propagator of rt_eom_ccsd.py).
-        Right-preconditioned restarted GMRES advanced in lock-step over the systems; returns the
-        list of complex solutions (_CVec)."""
+        """Solve (z_s - hscale * H-bar) x_s = rhs_s for every s (``rhs``: list of flat device
+        vectors, real tensors or complex ``_CVec``; ``zs``: complex shifts; ``hscale``: a complex
+        scalar, 1 for FEAST, i*dt for the real-time propagator of rt_eom_ccsd.py).
+        Right-preconditioned restarted GMRES advanced in lock-step over groups of at most
+        ``max_systems`` systems (each system keeps ``ls_restart + 1`` complex Krylov vectors);
+        returns the list of complex solutions (_CVec)."""
+        group = self.max_systems or len(zs)
+        out, res = [], []
+        for lo in range(0, len(zs), group):
+            x, r = self._solve_group(plan, diag, list(zs[lo:lo + group]), list(rhs[lo:lo + group]), hscale)
+            out += x
+            res += r
+        self.ls_residuals = res
+        return out
+
+    def _solve_group(self, plan, diag, zs, rhs, hscale):
         nsys = len(zs)
         hscale = complex(hscale)
         first = rhs[0].re if isinstance(rhs[0], _CVec) else rhs[0]
         zero = torch.zeros_like(first)
         rhs = [b if isinstance(b, _CVec) else _CVec(b, zero) for b in rhs]
-        bnorm = [np.sqrt(bk.dots([b.re], b.re).item() + bk.dots([b.im], b.im).item()) for b in rhs]
+        bnorm = _norms(rhs)
         x = [None] * nsys
         res = list(rhs)                                     # x0 = 0 -> r0 = b
         rnorm = list(bnorm)
@@ -151,17 +197,25 @@ class FEAST_EOM_CCSD(EOM_CCSD):
                     break
                 P = [_CVec(*bk.cdiv_shifted(diag, zs[s], 0.01, V[s][j].re, V[s][j].im)) for s in running]
                 HP = self._sigma_c(plan, P)
-                nxt = []
+                W = []
                 for s, p, hp in zip(running, P, HP):
                     if hscale == 1.0:
-                        w = _caxpy(_CVec(bk.lincomb([-1.0], [hp.re]), bk.lincomb([-1.0], [hp.im])), [zs[s]], [p])
+                        W.append(_caxpy(_CVec(bk.lincomb([-1.0], [hp.re]), bk.lincomb([-1.0], [hp.im])), [zs[s]], [p]))
                     else:
-                        w = _caxpy(_CVec(zero, zero), [zs[s], -hscale], [p, hp])
-                    for _ in range(2):                      # Gram-Schmidt with one refinement
-                        h = _cdots(V[s], w)
-                        w = _caxpy(w, list(-h), V[s])
+                        W.append(_caxpy(_CVec(zero, zero), [zs[s], -hscale], [p, hp]))
+                del P, HP
+                # Gram-Schmidt with one refinement.  Every pass launches the dot products of ALL
+                # running systems, reads them back together, then launches all the updates: the
+                # host waits for the device three times per Krylov step, not per system and dot.
+                for _ in range(2):
+                    pend = [_cdots_launch(V[s], w) for s, w in zip(running, W)]
+                    hs = [_cdots_finish(pd) for pd in pend]
+                    for n, (s, h) in enumerate(zip(running, hs)):
+                        W[n] = _caxpy(W[n], list(-h), V[s])
                         H[s][:j + 1, j] += h
-                    hn = np.sqrt(bk.dots([w.re], w.re).item() + bk.dots([w.im], w.im).item())
+                hns = _norms(W)
+                nxt = []
+                for s, w, hn in zip(running, W, hns):
                     H[s][j + 1, j] = hn
                     e1 = np.zeros(j + 2, dtype=complex)
                     e1[0] = rnorm[s]
@@ -171,6 +225,7 @@ class FEAST_EOM_CCSD(EOM_CCSD):
                     if est > self.ls_tol * bnorm[s] and hn > 1e-14 * rnorm[s] and j + 1 < self.ls_restart:
                         V[s].append(_CVec(bk.lincomb([1.0 / hn], [w.re]), bk.lincomb([1.0 / hn], [w.im])))
                         nxt.append(s)
+                del W
                 running = nxt
             # x += M (V y); true residual for the next cycle
             upd = []
@@ -180,13 +235,15 @@ class FEAST_EOM_CCSD(EOM_CCSD):
                 d = _CVec(*bk.cdiv_shifted(diag, zs[s], 0.01, vy.re, vy.im))
                 x[s] = d if x[s] is None else _caxpy(x[s], [1.0 + 0j], [d])
                 upd.append(s)
+            del V
             HX = self._sigma_c(plan, [x[s] for s in upd])
             for s, hx in zip(upd, HX):
-                r = _caxpy(rhs[s], [-zs[s], hscale], [x[s], hx])
-                res[s] = r
-                rnorm[s] = np.sqrt(bk.dots([r.re], r.re).item() + bk.dots([r.im], r.im).item())
-        self.ls_residuals = [rn / bn if bn > 0 else 0.0 for rn, bn in zip(rnorm, bnorm)]
-        return [xs if xs is not None else _CVec(zero, zero) for xs in x]
+                res[s] = _caxpy(rhs[s], [-zs[s], hscale], [x[s], hx])
+            del HX
+            for s, rn in zip(upd, _norms([res[s] for s in upd])):
+                rnorm[s] = rn
+        return ([xs if xs is not None else _CVec(zero, zero) for xs in x],
+                [rn / bn if bn > 0 else 0.0 for rn, bn in zip(rnorm, bnorm)])
 
     # ---- reference-shaped single solve (used by the parity tests) ---------
     def _gcrotmk(self, l, ze, diag_ai, diag_abij, t_fock_dressed_pq, dict_t_V_dressed, t_T_abij, **kwargs):
@@ -201,6 +258,17 @@ class FEAST_EOM_CCSD(EOM_CCSD):
         return qc[:n1].reshape(tuple(d1.shape)), qc[n1:].reshape(tuple(d2.shape))
 
     # ---- FEAST -----------------------------------------------------------
+    def _share(self, n):
+        """Indices 0..n-1 dealt out round-robin over the ranks of the system-parallel mode."""
+        if self.sys_comm is None:
+            return list(range(n))
+        return list(range(self.sys_comm.rank, n, self.sys_comm.size))
+
+    def _sum_over_ranks(self, t):
+        if self.sys_comm is not None:
+            self.sys_comm.all_reduce_sum(t)
+        return t
+
     def solve(self, t_fock_dressed_pq, dict_t_V_dressed, t_T_abij):
         print_title("FEAST-EOM-CCSD Solver")
         time_init = time.time()
@@ -219,35 +287,58 @@ class FEAST_EOM_CCSD(EOM_CCSD):
             a = 0.5 - np.random.rand(nv, no)
             b = (0.5 - np.random.rand(nv, nv, no, no)) * 0.01
             U.append(bk.asdev(np.concatenate([a.ravel(), b.ravel()])))
+        if self.sys_comm is not None:                       # one start for all ranks: rank 0's
+            for u in U:
+                if self.sys_comm.rank != 0:
+                    u.zero_()
+                self.sys_comm.all_reduce_sum(u)
         x, w = get_gauss_legendre_quadrature(self.n_nodes)
         theta = -np.pi / 2 * (x - 1)
         z = self.e_c + self.e_r * np.exp(1j * theta)
+        self.timings = []
 
         e_norm_prev = 1e10
         for it in range(self.max_iter):
-            U = [bk.lincomb([1.0 / np.sqrt(bk.dots([u], u).item())], [u]) for u in U]
+            t_it = time.time()
+            nrm = np.sqrt(torch.stack([bk.dots([u], u)[0] for u in U]).cpu().numpy())
+            U = [bk.lincomb([1.0 / n], [u]) for u, n in zip(U, nrm)]
             m = len(U)
-            # all (node, trial vector) systems in one lock-step batch            feast:113-121
-            zs = [z[e] for e in range(len(z)) for _ in range(m)]
-            rhs = [U[l] for _ in range(len(z)) for l in range(m)]
+            # all (node, trial vector) systems in lock-step batches                 feast:113-121
+            # (system-parallel mode: this rank's share of them)
+            mine = self._share(len(z) * m)
+            zs = [z[g // m] for g in mine]
+            rhs = [U[g % m] for g in mine]
+            mv0 = self.ls_matvecs
             sol = self.solve_shifted_systems(plan, diag, zs, rhs)
-            Q = []
+            Q = [None] * m
+            per_l = {}
+            for g, s_ in zip(mine, sol):
+                per_l.setdefault(g % m, []).append((g // m, s_))
             for l in range(m):
                 coefs, vecs = [], []
-                for e in range(len(z)):
+                for e, s_ in per_l.get(l, []):
                     f = -w[e] / 2 * self.e_r * np.exp(1j * theta[e])
-                    s = sol[e * m + l]
                     coefs += [f.real, -f.imag]              # Re(f * q) = f_r q_r - f_i q_i
-                    vecs += [s.re, s.im]
-                q = None
+                    vecs += [s_.re, s_.im]
+                q = torch.zeros_like(U[0]) if not vecs else None
                 for lo in range(0, len(vecs), 16):
                     q = bk.lincomb(coefs[lo:lo + 16], vecs[lo:lo + 16], out=q, beta=0.0 if q is None else 1.0)
-                Q.append(q)
-            Wq = plan.apply_packed(torch.stack(Q))          # H-bar Q                 feast:128-134
+                Q[l] = q
+            del sol, per_l
+            Qs = self._sum_over_ranks(torch.stack(Q))       # contour sum over every rank's nodes
+            Q = [Qs[l] for l in range(m)]
+            # H-bar Q, each rank its share of the columns                             feast:128-134
+            Wq = torch.zeros_like(Qs)
+            cols = self._share(m)
+            for lo in range(0, len(cols), self.max_rhs):
+                sel = cols[lo:lo + self.max_rhs]
+                Wq[sel] = plan.apply_packed(Qs[sel])
+            self._sum_over_ranks(Wq)
             H_proj, B = np.zeros((m, m)), np.zeros((m, m))
-            for i in range(m):
-                H_proj[:, i] = bk.dots(Q, Wq[i]).cpu().numpy()
-                B[:, i] = bk.dots(Q, Q[i]).cpu().numpy()
+            hb = [(bk.dots(Q, Wq[i]), bk.dots(Q, Q[i])) for i in range(m)]
+            for i, (h_, b_) in enumerate(hb):               # one read-back after all launches
+                H_proj[:, i] = h_.cpu().numpy()
+                B[:, i] = b_.cpu().numpy()
             self.eigvals, self.eigvecs = eig(H_proj, B)     # feast:148
             C = np.real(self.eigvecs)
             if m < self.n_trial:                            # feast:151-159
@@ -256,7 +347,12 @@ class FEAST_EOM_CCSD(EOM_CCSD):
             else:                                           # feast:160-164
                 for l in range(len(self.eigvals)):
                     U[l] = bk.lincomb([1.0] + list(C[:, l]), [U[l]] + Q)
+            del Q, Qs, Wq
             e_norm = np.linalg.norm(self.eigvals)
+            self.timings.append({"iteration": it, "trial_vectors": m, "systems_this_rank": len(mine),
+                                 "matvecs_this_rank": self.ls_matvecs - mv0,
+                                 "max_rel_residual": max(self.ls_residuals) if self.ls_residuals else 0.0,
+                                 "seconds": time.time() - t_it})
             if np.abs(e_norm - e_norm_prev) < self.tol:
                 break
             print_logging_info(f"Iter = {it}, Eigenvalues: {self.eigvals}", level=1)

@@ -604,3 +604,45 @@ def test_rt_eom_step_matches_reference():
     """One real-time propagation step through the lock-step GMRES on the CUDA kernels (passed on a
     B200 in round 2's first GPU session as tests/test_gpu_next.py)."""
     host.test_rt_eom_step_matches_reference(None)
+
+
+# --------------------------------------------------------------------------
+# parity AT THE BENCHMARK'S OWN SHAPE: o = 27, the bench's own Hamiltonian path
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("virtual", [(), ("abcd",)], ids=["dense", "generated_abcd"])
+@pytest.mark.parametrize("is_dcsd", [False, True], ids=["ccsd", "dcsd"])
+def test_bench_path_54e_lockstep_with_oracle(virtual, is_dcsd):
+    """TC-UEG 54 electrons / 65 plane waves (o = 27, v = 38) through exactly what bench.py runs --
+    ``bench.build_fock`` + ``UEG.eval_2b_blocks(..., virtual=)`` + ``CCSD.setup / sweep`` -- in
+    lock-step with the oracle's ``ccsd_sweep`` on the oracle-built Hamiltonian (the reference's
+    triple loop restated, ueg_oracle.tc_hamiltonian): energy 1e-10 Eh, amplitudes 1e-9 relative,
+    after every one of 3 sweeps."""
+    import bench
+    from oracle import cc_oracle as oc
+    from pymes_b200.integral.partition import KEYS
+    from pymes_b200.model import ueg
+    from pymes_b200.solver import ccsd
+    no = bench.N_ELE // 2
+    prob = bench.CpuProblem(6.0)
+    assert prob.n_orb == 65
+    m = ueg.UEG(bench.N_ELE, no, no, bench.RS)
+    m.init_single_basis(6.0)
+    m.k_cutoff, m.gamma = bench.K_CUTOFF, None
+    fock = bench.build_fock(m, no)
+    np.testing.assert_allclose(fock, prob.fock, rtol=1e-11, atol=1e-12)
+    dV = m.eval_2b_blocks(no, list(KEYS), bench.tc_parts(m), virtual=virtual)
+    for key in ("ijab", "abij", "iabc", "klij"):
+        assert _rel(dV[key].cpu().numpy(), prob.dV[key]) < 1e-11, key
+    cc = ccsd.CCSD(no, is_dcsd=is_dcsd)
+    e_mp2 = cc.setup(fock, dV)
+    e_ref, T2 = oc.mp2(prob.eps_i, prob.eps_a, prob.dV["ijab"], prob.dV["abij"])
+    assert abs(e_mp2 - e_ref) < 1e-10
+    T1 = np.zeros((prob.n_orb - no, no))
+    d1, d2 = oc.denominators(prob.eps_i, prob.eps_a)
+    mixer = oc.DIIS(6)
+    for sweep in range(3):
+        T1, T2, e, _ = oc.ccsd_sweep(no, prob.fock, prob.dV, T1, T2, d1, d2, mixer, is_dcsd=is_dcsd)
+        got = cc.sweep()
+        assert abs(sum(got[:3]) - sum(e)) < 1e-10, sweep
+        assert _rel(cc._st["T2"].cpu().numpy(), T2) < 1e-9, sweep
+        assert _rel(cc._st["T1"].cpu().numpy(), T1) < 1e-9, sweep

@@ -240,3 +240,67 @@ def test_sharded_feast_linear_solve_world2(cpu_abi):
         assert resid < 1e-4
         err = np.sqrt(np.sum(abs(q1 - gf["q1"]) ** 2) + np.sum(abs(q2 - gf["q2"]) ** 2)) / nrm
         assert err < 1e-6, err
+
+
+# --------------------------------------------------------------------------
+# the "replicated operator, work dealt out" modes (C4 / C5): parallel="vectors" / "systems"
+# --------------------------------------------------------------------------
+def _feast_seeded(no, ft, dVd, T2, comm=None):
+    from pymes_b200.solver import feast_eom_ccsd
+    gf = np.load(os.path.join(ROOT, "tests", "golden", "feast_LiH.npz"))
+    np.random.seed(5)
+    fe = feast_eom_ccsd.FEAST_EOM_CCSD(no, e_c=float(gf["e_c"]), e_r=float(gf["e_r"]), n_trial=4, max_iter=2,
+                                       comm=comm, parallel="systems")
+    fe.n_nodes = 4
+    fe.max_systems = 3              # groups of 3 systems: exercises the grouping as well
+    ev = fe.solve(ft, dVd, T2)
+    return np.sort_complex(np.asarray(ev)), fe
+
+
+def _dealt_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests import abi_emulator
+        abi_emulator.install(_Patch())
+        from pymes_b200 import log, parallel
+        from pymes_b200.solver import eom_ccsd
+        log.set_quiet(True)
+        g, no, ft, dVd, T2 = _eom_inputs()
+        comm = parallel.Comm()
+        eom = eom_ccsd.EOM_CCSD(no, n_excit=len(g["eom_e"]), comm=comm, parallel="vectors")
+        eom.max_rhs = 1
+        roots = eom.solve(ft, dVd, T2)
+        assert eom._plan.shard is None and eom.vec_comm is not None
+        if rank == 1:
+            np.random.seed(12345)   # the start vectors must come from rank 0 alone
+        ev, fe = _feast_seeded(no, ft, dVd, T2, comm)
+        assert fe.sys_comm is not None and fe._plan.shard is None
+        q.put((rank, np.asarray(roots).copy(), ev, [t["systems_this_rank"] for t in fe.timings]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_vector_and_system_parallel_world2(cpu_abi):
+    """Davidson with the new trial vectors dealt out over two ranks gives the golden roots; a
+    seeded FEAST run with the (node x trial vector) systems dealt out over two ranks gives the
+    eigenvalues of the single-process run (same start vectors, sums reordered only)."""
+    g, no, ft, dVd, T2 = _eom_inputs()
+    ev1, fe1 = _feast_seeded(no, ft, dVd, T2)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30500 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_dealt_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=900) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, roots, ev, nsys in res:
+        np.testing.assert_allclose(np.sort(roots), np.sort(g["eom_e"]), rtol=0, atol=1e-8)
+        # the projected generalised eigenproblem (non-orthogonal Q) amplifies the reordering round-off
+        np.testing.assert_allclose(ev, ev1, rtol=0, atol=1e-7)
+        assert nsys == [t["systems_this_rank"] // 2 for t in fe1.timings]
