@@ -627,8 +627,10 @@ def dots(xs, y, out=None):
     if out is None:
         out = empty(len(xs))
     ws = scratch().reduce_ws()
-    _lib.check(lib.pmb_dots(len(xs), _ptr_array(xs), _ptr(y), y.numel(), _ptr(out), _ptr(ws), ws.numel() * 8,
-                            _stream()), "pmb_dots")
+    for lo in range(0, len(xs), 16):                 # the C entry point takes up to 16 vectors per call
+        chunk = list(xs[lo:lo + 16])
+        _lib.check(lib.pmb_dots(len(chunk), _ptr_array(chunk), _ptr(y), y.numel(), _ptr(out[lo:lo + len(chunk)]),
+                                _ptr(ws), ws.numel() * 8, _stream()), "pmb_dots")
     return out
 
 

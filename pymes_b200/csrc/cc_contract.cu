@@ -65,6 +65,9 @@ struct Params {
     int raster_m_fast;       // consecutive CTAs walk m inside one column of tiles (see launch_ws)
     int total_ktiles, ktiles_per_split, nsplit;
     int kt_base, kt_limit;   // k-tile window of this launch (K-panel), [0, total_ktiles) if not panelled
+    // Tail launch (see pmb_contract): this launch covers the output tiles [tile_base, tile_base +
+    // gridDim.x) only, split over k; partial sums go to ws[split][tile - tile_base][BM x BN].
+    int tile_base, tail;
     double *ws;
     TermDev t[PMB_MAX_TERMS];
     // generated A operand (never-materialised UEG integrals): term index or -1
@@ -283,12 +286,16 @@ template <int MT, int NTL>
 __device__ __forceinline__ void store_partial(const Params &p, const double (&acc)[MT][NTL][2], int m0, int n0,
                                               int row0, int col0, int mrem, int nrem, int ncols = NTL) {
     nrem = min(nrem, col0 - (col0 & 7) + ncols * 8);
-    double *ws = p.ws + (size_t)blockIdx.y * (size_t)p.M * (size_t)p.N;
+    constexpr int kTailTile = 128;     // tail launches exist for the 128 x 128 kernels only
+    double *ws = p.tail ? p.ws + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)(kTailTile * kTailTile)
+                        : p.ws + (size_t)blockIdx.y * (size_t)p.M * (size_t)p.N;
+    const size_t ld = p.tail ? (size_t)kTailTile : (size_t)p.N;
+    if (p.tail) m0 = n0 = 0;
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
         const int ml = row0 + i * 8;
         if (ml >= mrem) continue;
-        double *row = ws + (size_t)(m0 + ml) * (size_t)p.N + n0;
+        double *row = ws + (size_t)(m0 + ml) * ld + n0;
 #pragma unroll
         for (int j = 0; j < NTL; ++j) {
             const int nl = col0 + j * 8;
@@ -574,8 +581,9 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
     // ONE column of tiles, whose equal-sized CTAs start and finish together and therefore
     // stream the same k range of B at the same time: B is read from HBM once per wave instead
     // of once per CTA (ncu: 2.64 TB -> see profiles/ for the pp ladder at v = 488).
-    const int tile_n = p.raster_m_fast ? (int)(blockIdx.x / p.tiles_m) : (int)(blockIdx.x % p.tiles_n);
-    const int tile_m = p.raster_m_fast ? (int)(blockIdx.x % p.tiles_m) : (int)(blockIdx.x / p.tiles_n);
+    const int tile = (int)blockIdx.x + p.tile_base;
+    const int tile_n = p.raster_m_fast ? tile / p.tiles_m : tile % p.tiles_n;
+    const int tile_m = p.raster_m_fast ? tile % p.tiles_m : tile / p.tiles_n;
     const int m0 = tile_m * BM, n0 = tile_n * BN;
     const int mrem = p.M - m0, nrem = p.N - n0;
     const int kt_lo = p.kt_base + blockIdx.y * p.ktiles_per_split;
@@ -958,6 +966,28 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constan
     }
 }
 
+// Second stage of a tail launch: C tile = beta*C + sum_s ws[s][tile][.][.], fixed order.  One CTA
+// per tail tile, threads walk the tile row-major (n fastest, like the partial sums were stored).
+__global__ void __launch_bounds__(256) tail_reduce_kernel(const __grid_constant__ Params p) {
+    constexpr int BT = 128;
+    const int tile = (int)blockIdx.x + p.tile_base;
+    const int tile_n = p.raster_m_fast ? tile / p.tiles_m : tile % p.tiles_n;
+    const int tile_m = p.raster_m_fast ? tile % p.tiles_m : tile / p.tiles_n;
+    const int m0 = tile_m * BT, n0 = tile_n * BT;
+    const int mrem = min(BT, p.M - m0), nrem = min(BT, p.N - n0);
+    const size_t stride = (size_t)gridDim.x * BT * BT;
+    const double *src = p.ws + (size_t)blockIdx.x * BT * BT;
+    for (int e = threadIdx.x; e < BT * BT; e += blockDim.x) {
+        const int ml = e / BT, nl = e - ml * BT;
+        if (ml >= mrem || nl >= nrem) continue;
+        double s = 0.0;
+        for (int k = 0; k < p.nsplit; ++k) s += src[(size_t)k * stride + e];
+        double *dst = p.C + decomp(m0 + ml, p.nm, p.m_ext, p.c_mstr) + decomp(n0 + nl, p.nn, p.n_ext, p.c_nstr);
+        if (p.beta != 0.0) s += p.beta * (*dst);
+        *dst = s;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -1272,6 +1302,8 @@ static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
     p.nsplit = (kt + p.ktiles_per_split - 1) / p.ktiles_per_split;
     p.kt_base = 0;
     p.kt_limit = kt;
+    p.tile_base = 0;
+    p.tail = 0;
     p.ws = nullptr;
     return 0;
 }
@@ -1295,6 +1327,32 @@ static int panel_ktiles(const Params &p, int cfg) {
     return (p.total_ktiles + npanel - 1) / npanel;      // equal windows
 }
 
+// Tail wave.  The warp-specialised kernel runs one CTA per SM, so a grid of `tiles` CTAs takes
+// ceil(tiles / 148) waves and the last one may be nearly empty (ring terms of an 8-way sharded
+// 515-orbital sweep: 1339 tiles = 9.05 waves; the pair of o.v^3.tau contractions: 4.18 waves each).
+// When the last wave would fill at most half of the machine, the launch is cut in two: the full
+// waves as they are, and the R remaining tiles as a second launch split floor(148 / R) ways over k
+// (partial sums to the workspace, fixed-order second stage) -- the tail then costs 1/split of a
+// wave.  Only for long k loops (a wave >= ~130 us), without k windows.
+struct TailPlan {
+    int full_tiles, tail_tiles, split;
+};
+static int g_no_tail = 0;          // tuning bit 64: never cut the tail wave off
+static TailPlan tail_plan(const Params &p, int cfg) {
+    TailPlan t = {0, 0, 1};
+    if (cfg < 5 || g_no_tail || p.nsplit != 1 || panel_ktiles(p, cfg) < p.total_ktiles) return t;
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int full = (tiles / kSmCount) * kSmCount, rest = tiles - full;
+    if (full == 0 || rest == 0 || rest > kSmCount / 2 || p.total_ktiles < 64) return t;
+    int split = kSmCount / rest;
+    if (split > p.total_ktiles / 16) split = p.total_ktiles / 16;
+    if (split < 2) return t;
+    t.full_tiles = full;
+    t.tail_tiles = rest;
+    t.split = split;
+    return t;
+}
+
 }  // namespace pmb
 
 using namespace pmb;
@@ -1302,6 +1360,7 @@ using namespace pmb;
 extern "C" void pmb_contract_set_tuning(int tile_config, int split_k) {
     g_gen_no_walk = tile_config >= 0 && (tile_config & 16);
     g_gen_no_mraster = tile_config >= 0 && (tile_config & 32);
+    g_no_tail = tile_config >= 0 && (tile_config & 64);
     g_force_cfg = tile_config >= 0 ? (tile_config & 15) : tile_config;
     g_force_split = split_k;
 }
@@ -1315,7 +1374,10 @@ extern "C" size_t pmb_contract_workspace(const pmb_contract_t *d) {
     Params p;
     int cfg;
     if (build_params(d, p, cfg) != 0) return 0;
-    if (p.nsplit <= 1) return 0;
+    if (p.nsplit <= 1) {
+        const TailPlan t = tail_plan(p, cfg);
+        return sizeof(double) * (size_t)t.tail_tiles * (size_t)t.split * 128 * 128;
+    }
     return sizeof(double) * (size_t)p.nsplit * (size_t)p.M * (size_t)p.N;
 }
 
@@ -1329,6 +1391,28 @@ extern "C" int pmb_contract(const pmb_contract_t *d, void *ws, size_t ws_bytes, 
         const size_t need = sizeof(double) * (size_t)p.nsplit * (size_t)p.M * (size_t)p.N;
         if (!ws || ws_bytes < need) return PMB_E_WORKSPACE;
         p.ws = (double *)ws;
+    }
+    const TailPlan tail = tail_plan(p, cfg);
+    if (tail.split > 1) {
+        const size_t need = sizeof(double) * (size_t)tail.tail_tiles * (size_t)tail.split * 128 * 128;
+        if (!ws || ws_bytes < need) return PMB_E_WORKSPACE;
+        // full waves, unsplit
+        dim3 g1((unsigned)tail.full_tiles, 1, 1);
+        rc = cfg == 5 ? launch_ws<128, 128, 4, 2, 4>(p, g1, s) : launch_ws<128, 128, 4, 2, 6>(p, g1, s);
+        if (rc != 0) return rc;
+        // the rest, split over k
+        Params q = p;
+        q.tile_base = tail.full_tiles;
+        q.tail = 1;
+        q.ws = (double *)ws;
+        q.ktiles_per_split = (p.total_ktiles + tail.split - 1) / tail.split;
+        q.nsplit = (p.total_ktiles + q.ktiles_per_split - 1) / q.ktiles_per_split;
+        dim3 g2((unsigned)tail.tail_tiles, (unsigned)q.nsplit, 1);
+        rc = cfg == 5 ? launch_ws<128, 128, 4, 2, 4>(q, g2, s) : launch_ws<128, 128, 4, 2, 6>(q, g2, s);
+        if (rc != 0) return rc;
+        tail_reduce_kernel<<<(unsigned)tail.tail_tiles, 256, 0, s>>>(q);
+        count_launch();
+        return cuda_status();
     }
     dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)p.nsplit, 1);
     // copies of the next tile interleaved with the DMMA sub-steps: pays off when one CTA

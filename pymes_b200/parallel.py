@@ -25,7 +25,7 @@ import torch.distributed as dist
 
 from . import backend as bk
 from .solver import ccd, ccsd, mp2
-from .solver.ccsd import FOCK_TERMS, V_TERMS, SINGLES_TERMS
+from .solver.ccsd import FOCK_SHARED, FOCK_TERMS, SHARED_PRODUCTS, V_TERMS, SINGLES_TERMS
 
 # integral blocks held as local row blocks: key -> dimension that carries the sharded index
 SHARD_DIMS = {"abcd": 0, "abci": 0, "abic": 0, "aibc": 0, "iabc": 1}
@@ -53,6 +53,28 @@ class Comm:
         dist.all_gather_into_tensor(buf, send, group=self.group)
         return buf[:n_rows]
 
+    def all_gather_rows_async(self, local, n_rows, max_rows):
+        """Same as :meth:`all_gather_rows`, started now and completed by ``.wait_result()``: the
+        collective runs on the communicator's own stream while the caller keeps launching
+        independent kernels on the compute stream."""
+        rest = tuple(local.shape[1:])
+        send = local.contiguous()
+        if send.shape[0] != max_rows:
+            pad = torch.zeros((max_rows,) + rest, dtype=local.dtype, device=local.device)
+            pad[: send.shape[0]] = send
+            send = pad
+        buf = torch.empty((self.size * max_rows,) + rest, dtype=local.dtype, device=local.device)
+        work = dist.all_gather_into_tensor(buf, send, group=self.group, async_op=True)
+        return Pending(work, buf[:n_rows], keep=(send,))
+
+    def exchange_blocks(self, send):
+        """send [size, ...]: block q goes to rank q; returns recv [size, ...] with block q coming
+        from rank q (all-to-all, equal blocks)."""
+        send = send.contiguous()
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        return recv
+
     def all_reduce_sum(self, x):
         """numpy array or tensor, summed over ranks (returned in the same kind)."""
         if isinstance(x, np.ndarray):
@@ -64,6 +86,24 @@ class Comm:
 
     def barrier(self):
         dist.barrier(group=self.group)
+
+
+class Pending:
+    """Result of a collective that is still in flight."""
+
+    def __init__(self, work, result, keep=(), view=None):
+        self.work, self.result, self.keep, self.view = work, result, keep, view
+
+    def wait_result(self):
+        if self.work is not None:
+            self.work.wait()          # the compute stream waits; the host does not
+            self.work, self.keep = None, ()
+        return self.view(self.result) if self.view is not None else self.result
+
+
+def resolved(x):
+    """A tensor, or the tensor a :class:`Pending` collective delivers."""
+    return x.wait_result() if isinstance(x, Pending) else x
 
 
 class Shard:
@@ -83,6 +123,27 @@ class Shard:
 
     def gather(self, local):
         return self.comm.all_gather_rows(local, self.nv, self.max_rows)
+
+    def gather_async(self, local, view=None):
+        p = self.comm.all_gather_rows_async(local, self.nv, self.max_rows)
+        p.view = view
+        return p
+
+    def transposed_rows(self, Ex):
+        """Ex [na, nv, o, o] (this rank's rows a of an [a,b,i,j] tensor) -> the rows a in A of its
+        (ba)(ji) transpose, T[a,b,i,j] = Ex_full[b,a,j,i], as a VIEW [na, nv, o, o].  Rank q owns
+        the rows b in A_q of Ex_full, so it sends its columns a in A_me: an all-to-all of
+        o^2 v^2 / N elements per rank (the all-gather of Ex moves N times as much)."""
+        mr, na, size = self.max_rows, self.na, self.size
+        no = Ex.shape[2]
+        send = torch.zeros((size, mr, mr, no, no), dtype=Ex.dtype, device=Ex.device)
+        for q in range(size):
+            lo = q * mr
+            n = min(lo + mr, self.nv) - lo
+            bk.axpby(1.0, Ex[:, lo:lo + n], 0.0, send[q, :na, :n])
+        recv = self.comm.exchange_blocks(send)      # recv[q, b', a', j, i] = Ex_q[b', a_me + a', j, i]
+        full = recv.reshape(size * mr, mr, no, no)  # [b (global, padded), a', j, i]
+        return full.permute(1, 0, 3, 2)[:na, :self.nv]
 
     def all_reduce(self, x):
         """Sum of a small replicated-size tensor over the ranks (in place)."""
@@ -146,44 +207,53 @@ class ShardedCCSD(ccsd.CCSD):
         ops = [self._narrow(s, n, src[n]) for s, n in zip(subs, names)]
         bk.einsum(spec, *ops, out=out, alpha=coef, beta=1.0)
 
-    def _dressed_fock(self, fock, T1, dV):
-        """ccsd.py:226-288; the four terms that read V_iabc produce local rows and are gathered."""
-        no, sh = self.no, self.shard
-        nv = T1.shape[0]
+    def _dressed_fock(self, fock, T1, dV, shared):
+        """ccsd.py:226-288.  The four rows that read V_iabc (through the shared partial traces G3 /
+        G4, local rows [na, v]) fill this rank's rows; the other rows read replicated o^2v^2 blocks
+        and produce nP^2 numbers or fewer, so they are dealt out over the ranks term by term.  One
+        all-reduce of an nP x nP matrix assembles both."""
+        no, sh, comm = self.no, self.shard, self.comm
         src = dict(dV)
         src.update(t=T1, foo=fock[:no, :no], fvv=fock[no:, no:], fov=fock[:no, no:])
-        out = bk.copy(fock)
-        views = {"ov": out[:no, no:], "vo": out[no:, :no], "oo": out[:no, :no], "vv": out[no:, no:]}
-        loc = {"vo": bk.zeros(sh.na, no), "vv": bk.zeros(sh.na, nv)}
+        src.update(shared)                                       # G3 / G4: [na, v]
+        acc = bk.zeros(*fock.shape)
+        views = {"ov": acc[:no, no:], "vo": acc[no:, :no], "oo": acc[:no, :no], "vv": acc[no:, no:]}
+        a0, a1 = no + sh.lo, no + sh.lo + sh.na
+        mine = {"vo": acc[a0:a1, :no], "vv": acc[a0:a1, no:]}
+        turn = 0
         for blk, rows in FOCK_TERMS.items():
             for coef, spec, names in rows:
                 names = names.split()
-                if "iabc" in names:
-                    self._eval_rows(coef, spec, names, src, loc[blk])
-                else:
+                if any(n in FOCK_SHARED for n in names):          # local rows in, local rows out
+                    bk.einsum(spec, *[src[n] for n in names], out=mine[blk], alpha=coef, beta=1.0)
+                    continue
+                if turn % comm.size == comm.rank:
                     bk.einsum(spec, *[src[n] for n in names], out=views[blk], alpha=coef, beta=1.0)
-        for blk in ("vo", "vv"):
-            bk.axpby(1.0, sh.gather(loc[blk]), 1.0, views[blk])
-        return out
+                turn += 1
+        comm.all_reduce_sum(acc)
+        return bk.lincomb([1.0, 1.0], [fock.contiguous(), acc])
 
     def _singles_residual(self, ft, T1, T2, dV):
-        """ccsd.py:423-438; the V_aibc term is evaluated on local rows and gathered."""
-        no, sh = self.no, self.shard
+        """ccsd.py:423-438; the V_aibc term is evaluated on this rank's rows, the other terms (vo-sized
+        results of reductions over the replicated amplitudes) are dealt out over the ranks."""
+        no, sh, comm = self.no, self.shard, self.comm
         Tt = bk.tilde(T2, swap_ij=True)
         src = dict(dV)
         src.update(t=T1, Tt=Tt, fov=ft[:no, no:])
-        R1 = bk.copy(ft[no:, :no])
-        loc = bk.zeros(sh.na, no)
+        acc = bk.zeros(T1.shape[0], no)
+        turn = 0
         for coef, spec, names in SINGLES_TERMS:
             names = names.split()
             if "aibc" in names:
-                self._eval_rows(coef, spec, names, src, loc)
-            else:
-                bk.einsum(spec, *[src[n] for n in names], out=R1, alpha=coef, beta=1.0)
-        bk.axpby(1.0, sh.gather(loc), 1.0, R1)
-        return R1
+                self._eval_rows(coef, spec, names, src, sh.rows(acc, 0))
+                continue
+            if turn % comm.size == comm.rank:
+                bk.einsum(spec, *[src[n] for n in names], out=acc, alpha=coef, beta=1.0)
+            turn += 1
+        comm.all_reduce_sum(acc)
+        return bk.lincomb([1.0, 1.0], [bk.copy(ft[no:, :no]), acc])
 
-    def _dressed_rows(self, key, T1, dV, a_dim, skip_tau=False):
+    def _dressed_rows(self, key, T1, dV, a_dim, skip_tau=False, shared=None):
         """Local rows (a in A) of a T1-dressed block, returned with the a index FIRST
         ([na, ...other indices in their original order])."""
         sh = self.shard
@@ -198,6 +268,9 @@ class ShardedCCSD(ccsd.CCSD):
             if skip_tau and is_tau:
                 continue
             nt = spec.split("->")[0].count(",")
+            if source in SHARED_PRODUCTS:                        # X3 / X4: local rows already
+                bk.einsum(spec, shared[source], out=view, alpha=coef, beta=1.0)
+                continue
             self._eval_rows(coef, spec, [source] + ["t"] * nt, src, view)
         return buf
 
@@ -267,11 +340,15 @@ class ShardedCCSD(ccsd.CCSD):
         eps_i, eps_a, shift = st["eps_i"], st["eps_a"], st["shift"]
         rows = (sh.lo, sh.na)
         st["iteration"] += 1
-        ft = self._dressed_fock(fock, T1, dV)
+        shared = ccsd.t1_shared(T1, dV)            # X3 / X4 / G3 / G4 on the local rows of V_iabc[:,A]
+        ft = self._dressed_fock(fock, T1, dV, shared)
         R1 = self._singles_residual(ft, T1, T2, dV)
         V_abij = self._dressed_rows("abij", T1, dV, 0, skip_tau=True)                 # [A,b,i,j]
-        V_iajb = sh.gather_dim1(self._dressed_rows("iajb", T1, dV, 1))                # [i,a,j,b] view
-        V_iabj = sh.gather_dim1(self._dressed_rows("iabj", T1, dV, 1))
+        # local rows [A,i,j,b] -> full [i,a,j,b] views; the two all-gathers travel while the ladder runs
+        dim1 = lambda t: t.transpose(0, 1)
+        V_iajb = sh.gather_async(self._dressed_rows("iajb", T1, dV, 1, shared=shared), view=dim1)
+        V_iabj = sh.gather_async(self._dressed_rows("iabj", T1, dV, 1, shared=shared), view=dim1)
+        del shared
         R2 = ccd.doubles_residual(no, ft, T2, ccsd.dressed_block("klij", T1, dV), dV["ijab"], V_abij, V_iajb,
                                   V_iabj, None, is_dcd=self.is_dcd, pp_ladder=self._tau_ladder(T1, dV),
                                   shard=sh)
@@ -282,9 +359,10 @@ class ShardedCCSD(ccsd.CCSD):
         del R1, R2
         if self.is_diis:
             T1, T2l = self.mixer.mix([dT1, dT2], [T1, T2l], sharded=[False, True])
-        T2 = sh.gather(T2l)
-        st["T1"], st["T2"] = T1, T2
+        T2 = sh.gather_async(T2l)                   # ... while the energy of the local rows is summed
         bk.energy_doubles(T2l, dV["ijab"], scal, T1=T1, rows=rows)
+        T2 = T2.wait_result()
+        st["T1"], st["T2"] = T1, T2
         self.comm.all_reduce_sum(scal[0:4])
         bk.contract_terms("", [(2.0, "ia", fock[:no, no:], "ai", T1)], out=scal[4])
         s = scal.cpu().numpy()

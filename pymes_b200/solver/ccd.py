@@ -48,6 +48,11 @@ class _Whole:
         return x
 
 
+def _resolved(x):
+    """A tensor, or the result of a collective still in flight (``parallel.Pending``)."""
+    return x.wait_result() if hasattr(x, "wait_result") else x
+
+
 def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abcd,
                      is_dcd=False, is_bruekner=False, pp_ladder=None, shard=None):
     """R_abij for device tensors (reference ccd.py:164-254).
@@ -57,9 +62,12 @@ def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abc
 
     ``shard`` (``pymes_b200.parallel.Shard``): this rank owns the rows a in [lo, lo+na) of
     every [a,b,i,j] quantity.  T2 and the o^2v^2-sized integral blocks are replicated; V_abij
-    and V_abcd are the LOCAL row blocks; the returned R is the local row block.  The only
-    exchanges are an all-gather of the ring intermediate Xai (built sharded over its row
-    index c) and an all-gather of Ex for the explicit Ex + Ex^{baji} permutation.
+    and V_abcd are the LOCAL row blocks; the returned R is the local row block.  The exchanges
+    are an all-gather of the ring intermediate Xai (built sharded over its row index; started
+    before the ladder and collected after it, so it travels while the ladder runs) and an
+    all-to-all of the column blocks of Ex for the explicit Ex + Ex^{baji} permutation.
+    ``V_iajb`` / ``V_iabj`` may be collectives still in flight (``parallel.Pending``): they are
+    waited for at their first use, after the ladder.
     """
     nv = T2.shape[0]
     ccd = not is_dcd
@@ -67,6 +75,13 @@ def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abc
     sh = shard if shard is not None else _Whole(nv)
     T2a = sh.rows(T2, 0)            # T2[a in A, ., ., .]
     T2b = sh.rows(T2, 1)            # T2[., a in A, ., .]
+
+    Tt = bk.tilde(T2)                                                # ccd.py:199
+    Tta = sh.rows(Tt, 0)
+    # Xai[c,b,k,j]: every rank builds its rows c, then all ranks need all of it   ccd.py:202
+    Xai = ct("cbkj", [(1.0, "klcd", sh.rows(V_ijab, 2), "dblj", Tt)])
+    if shard is not None:
+        Xai = sh.gather_async(Xai)
 
     # I_klij = V_klij (+ V_ijab.T)                                   ccd.py:178-180
     # (sharded: each rank sums over its c in A, the o^4 partial sums are all-reduced)
@@ -91,11 +106,7 @@ def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abc
         ct("abij", [(1.0, "alcj", X1, "cbil", T2)], out=R, beta=1.0)
         del X1
 
-    Tt = bk.tilde(T2)                                                # ccd.py:199
-    Tta = sh.rows(Tt, 0)
-    # Xai[c,b,k,j]: every rank builds its rows c, then all ranks need all of it   ccd.py:202
-    Xai = sh.gather(ct("cbkj", [(1.0, "klcd", sh.rows(V_ijab, 2), "dblj", Tt)]))
-    ct("abij", [(1.0, "acik", Tta, "cbkj", Xai)], out=R, beta=1.0)   # ccd.py:204
+    ct("abij", [(1.0, "acik", Tta, "cbkj", _resolved(Xai))], out=R, beta=1.0)   # ccd.py:204
     del Xai
 
     # Fock-like intermediates; the reference adds the same product twice for CCD
@@ -120,6 +131,7 @@ def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abc
         else:
             bk.axpby(1.0, sh.all_reduce(ct("ki", [(+c, "cdil", Tta, "lkdc", sh.rows(V_ijab, 3))])), 1.0, Xki)
 
+    V_iajb, V_iabj = _resolved(V_iajb), _resolved(V_iabj)
     Ex = ct("abij", [(1.0, "ac", Xac, "cbij", T2)])                  # ccd.py:231
     ct("abij", [(-1.0, "ki", Xki, "abkj", T2a)], out=Ex, beta=1.0)   # ccd.py:232
     ring = [(-1.0, "kaic", sh.rows(V_iajb, 1), "cbkj", T2),          # ccd.py:233
@@ -135,9 +147,8 @@ def doubles_residual(no, fock, T2, V_klij, V_ijab, V_abij, V_iajb, V_iabj, V_abc
     if shard is None:
         bk.sym_baji(Ex, R, accumulate=True)                          # ccd.py:249-252
     else:
-        Exf = sh.gather(Ex)          # the (ba) block lives on another rank
         bk.axpby(1.0, Ex, 1.0, R)
-        bk.axpby(1.0, sh.rows(Exf.permute(1, 0, 3, 2), 0), 1.0, R)
+        bk.axpby(1.0, sh.transposed_rows(Ex), 1.0, R)    # the (ba) blocks live on the other ranks
     return R
 
 

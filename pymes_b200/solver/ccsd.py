@@ -41,16 +41,42 @@ FOCK_TERMS = {
     "vo": [(-1.0, "ji,aj->ai", "foo t"), (+1.0, "ab,bi->ai", "fvv t"),
            (-1.0, "jb,bi,aj->ai", "fov t t"),
            (+2.0, "bj,jabi->ai", "t iabj"), (-2.0, "bj,jkbi,ak->ai", "t ijak t"),
-           (+2.0, "bj,jabc,ci->ai", "t iabc t"), (-2.0, "bj,jkbc,ci,ak->ai", "t ijab t t"),
+           (+2.0, "ac,ci->ai", "G3 t"), (-2.0, "bj,jkbc,ci,ak->ai", "t ijab t t"),      # "bj,jabc,ci->ai"
            (-1.0, "bj,jaib->ai", "t iajb"), (+1.0, "bj,jkib,ak->ai", "t ijka t"),
-           (-1.0, "bj,jacb,ci->ai", "t iabc t"), (+1.0, "bj,jkcb,ci,ak->ai", "t ijab t t")],
+           (-1.0, "ac,ci->ai", "G4 t"), (+1.0, "bj,jkcb,ci,ak->ai", "t ijab t t")],      # "bj,jacb,ci->ai"
     "oo": [(+2.0, "ck,kicj->ij", "t ijak"), (-1.0, "ck,kijc->ij", "t ijka"),
            (+1.0, "ib,bj->ij", "fov t"),
            (+2.0, "ck,kicb,bj->ij", "t ijab t"), (-1.0, "ck,kibc,bj->ij", "t ijab t")],
-    "vv": [(+2.0, "ci,iacb->ab", "t iabc"), (-1.0, "ci,iabc->ab", "t iabc"),
+    "vv": [(+2.0, "ab->ab", "G3"), (-1.0, "ab->ab", "G4"),                                 # "ci,iacb->ab", "ci,iabc->ab"
            (-1.0, "ib,ai->ab", "fov t"),
            (-2.0, "ck,klcb,al->ab", "t ijab t"), (+1.0, "ck,kibc,ai->ab", "t ijab t")],
 }
+
+# Products of the o.v^3 block V_iabc with T1 that several rows share (each is one HBM pass over the
+# block, 25 GB at v = 488, so each is evaluated ONCE per sweep, `t1_shared`):
+#   X3[i,a,j,b] = sum_c V_iabc[i,a,c,b] t[c,j]      the row "iacb,cj->iajb" of the dressed V_iajb (ccsd.py:379)
+#   X4[i,a,b,j] = sum_c V_iabc[i,a,b,c] t[c,j]      the row "iabc,cj->iabj" of the dressed V_iabj (ccsd.py:387)
+# and the four Fock rows that read V_iabc (ccsd.py:266,270,282,283) are partial traces of them:
+#   G3[a,b] = sum_i X3[i,a,i,b]:  "bj,jabc,ci->ai" = (G3.t)_ai,  "ci,iacb->ab" = G3_ab
+#   G4[a,b] = sum_i X4[i,a,b,i]:  "bj,jacb,ci->ai" = (G4.t)_ai,  "ci,iabc->ab" = G4_ab
+SHARED_PRODUCTS = {"X3": ("iacb,cj->iajb", "iabc t"), "X4": ("iabc,cj->iabj", "iabc t")}
+SHARED_TRACES = {"G3": ("X3", "iaib", "iab"), "G4": ("X4", "iabi", "iab")}
+FOCK_SHARED = ("G3", "G4")
+
+
+def t1_shared(T1, dV):
+    """{"X3", "X4", "G3", "G4"} for these amplitudes (device tensors; with a row-sharded V_iabc
+    [i, a in A, b, c] every entry holds the local rows a in A)."""
+    src = dict(dV)
+    src["t"] = T1
+    out = {}
+    for name, (spec, names) in SHARED_PRODUCTS.items():
+        out[name] = bk.einsum(spec, *[src[n] for n in names.split()])
+    ones = torch.ones(T1.shape[1], dtype=bk.F64, device=T1.device)
+    for name, (source, sub, view_sub) in SHARED_TRACES.items():
+        out[name] = bk.einsum(view_sub + ",i->ab", bk.diag_view(out[source], sub, view_sub), ones)
+    return out
+
 
 # rows marked True are the tau-type terms folded into the pp ladder by `solve`
 V_TERMS = {
@@ -67,9 +93,9 @@ V_TERMS = {
     "ijab": [],
     "ijka": [(+1.0, "ijba,bk->ijka", "ijab", False)],
     "ijak": [(+1.0, "ijab,bk->ijak", "ijab", False)],
-    "iajb": [(+1.0, "iacb,cj->iajb", "iabc", False), (-1.0, "ikjb,ak->iajb", "ijka", False),
+    "iajb": [(+1.0, "iajb->iajb", "X3", False), (-1.0, "ikjb,ak->iajb", "ijka", False),        # "iacb,cj->iajb"
              (-1.0, "ikcb,cj,ak->iajb", "ijab", False)],
-    "iabj": [(-1.0, "ikbj,ak->iabj", "ijak", False), (+1.0, "iabc,cj->iabj", "iabc", False),
+    "iabj": [(-1.0, "ikbj,ak->iabj", "ijak", False), (+1.0, "iabj->iabj", "X4", False),        # "iabc,cj->iabj"
              (-1.0, "ikbc,ak,cj->iabj", "ijab", False)],
     "iabc": [(-1.0, "ijbc,aj->iabc", "ijab", False)],
     "abic": [(-1.0, "jbic,aj->abic", "iajb", False), (+1.0, "abdc,di->abic", "abcd", False),
@@ -93,10 +119,12 @@ def _dev_dict(dict_t_V):
     return {k: (bk.asdev(v) if v is not None else None) for k, v in dict_t_V.items()}
 
 
-def dressed_fock(no, fock, T1, dV):
-    """Device tensors in, dressed Fock (new tensor) out.  ccsd.py:226-288."""
+def dressed_fock(no, fock, T1, dV, shared=None):
+    """Device tensors in, dressed Fock (new tensor) out.  ccsd.py:226-288.  ``shared``: the
+    result of :func:`t1_shared` for these amplitudes (computed here when not given)."""
     src = dict(dV)
     src.update(t=T1, foo=fock[:no, :no], fvv=fock[no:, no:], fov=fock[:no, no:])
+    src.update(shared if shared is not None else t1_shared(T1, dV))
     out = bk.copy(fock)
     views = {"ov": out[:no, no:], "vo": out[no:, :no], "oo": out[:no, :no], "vv": out[no:, no:]}
     for blk, rows in FOCK_TERMS.items():
@@ -105,13 +133,19 @@ def dressed_fock(no, fock, T1, dV):
     return out
 
 
-def dressed_block(key, T1, dV, skip_tau=False):
-    """One T1-dressed V block from the undressed dictionary.  ccsd.py:322-419."""
+def dressed_block(key, T1, dV, skip_tau=False, shared=None):
+    """One T1-dressed V block from the undressed dictionary.  ccsd.py:322-419.  ``shared``: the
+    result of :func:`t1_shared` (needed by "iajb" / "iabj"; computed here when not given)."""
     blk = bk.copy(dV[key])
     for coef, spec, source, is_tau in V_TERMS[key]:
         if skip_tau and is_tau:
             continue
         nt = spec.split("->")[0].count(",")
+        if source in SHARED_PRODUCTS:
+            if shared is None:
+                shared = t1_shared(T1, dV)
+            bk.einsum(spec, shared[source], out=blk, alpha=coef, beta=1.0)
+            continue
         bk.einsum(spec, dV[source], *([T1] * nt), out=blk, alpha=coef, beta=1.0)
     return blk
 
@@ -240,13 +274,14 @@ class CCSD(ccd.CCD):
         if dict_t_V_dressed is None or len(dict_t_V_dressed) == 0:
             dict_t_V_dressed = {}.fromkeys(dict_t_V, None)
         dV, T1 = _dev_dict(dict_t_V), bk.asdev(t_T_ai)
+        shared = t1_shared(T1, dV) if any(k in dict_t_V_dressed for k in ("iajb", "iabj")) else None
         for key in V_TERMS:
             if key in dict_t_V_dressed:
                 if key == "abcd" and isinstance(dV["abcd"], bk.GeneratedOperand):
                     # V_abcd is never materialised: its dressed form is an operator as well
                     dict_t_V_dressed[key] = DressedLadder(dV["abcd"], dV["iabc"], dV["aibc"], dV["ijab"], T1)
                     continue
-                blk = dressed_block(key, T1, dV)
+                blk = dressed_block(key, T1, dV, shared=shared)
                 dict_t_V_dressed[key] = bk.tonumpy(blk) if want_numpy else blk
         return dict_t_V_dressed
 
@@ -317,13 +352,17 @@ class CCSD(ccd.CCD):
         T1, T2, scal = st["T1"], st["T2"], st["scal"]
         eps_i, eps_a, shift = st["eps_i"], st["eps_a"], st["shift"]
         st["iteration"] += 1
-        ft = dressed_fock(no, fock, T1, dV)
+        shared = t1_shared(T1, dV)              # the V_iabc.T1 products: one pass each per sweep
+        ft = dressed_fock(no, fock, T1, dV, shared=shared)
         R1 = singles_residual(no, ft, T1, T2, dV)
+        V_iajb = dressed_block("iajb", T1, dV, shared=shared)
+        V_iabj = dressed_block("iabj", T1, dV, shared=shared)
+        del shared
         R2 = ccd.doubles_residual(
             no, ft, T2, dressed_block("klij", T1, dV), dV["ijab"],
-            dressed_block("abij", T1, dV, skip_tau=True), dressed_block("iajb", T1, dV),
-            dressed_block("iabj", T1, dV), None, is_dcd=self.is_dcd,
+            dressed_block("abij", T1, dV, skip_tau=True), V_iajb, V_iabj, None, is_dcd=self.is_dcd,
             pp_ladder=tau_ladder(T1, dV))
+        del V_iajb, V_iabj
         dT1 = bk.update_singles(eps_i, eps_a, shift, self.delta, R1, T1)
         dT2 = bk.update_doubles(eps_i, eps_a, shift, self.delta, R2, T2, scal[3:4])
         del R1, R2

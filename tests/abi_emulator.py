@@ -228,6 +228,8 @@ class FakeLib:
         return 0
 
     def pmb_dots(self, nvec, X, Y, n, out, ws, wsb, stream):
+        if not 1 <= nvec <= 16:
+            return -1                     # PMB_E_BADARG, as the library does
         self.launches += 2
         y = _window(_val(Y), n)
         o = _window(_val(out), nvec)
@@ -236,6 +238,8 @@ class FakeLib:
         return 0
 
     def pmb_lincomb(self, nvec, c, X, n, beta, out, stream):
+        if not 1 <= nvec <= 16:
+            return -1
         self.launches += 1
         o = _window(_val(out), n)
         acc = beta * o if beta != 0.0 else np.zeros(n)

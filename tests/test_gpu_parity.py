@@ -415,7 +415,7 @@ def _tc_model(n_ele, cutoff, rs=0.5):
     return m
 
 
-@pytest.mark.parametrize("n_ele,cutoff", [(14, 5.0), (14, 9.0), (54, 7.0)])
+@pytest.mark.parametrize("n_ele,cutoff", [(14, 5.0), (14, 9.0), (54, 7.0), (54, 8.0)])   # 54/8.0: 210 tiles -> tail launch
 def test_ueg_virtual_pp_ladder_bit_identical(n_ele, cutoff):
     """Never-materialised V_abcd: the pp ladder with the operand generated in
     the kernel's producer warps equals the ladder on the block pmb_ueg_build_block wrote --
@@ -671,3 +671,41 @@ def test_two_rank_nccl_parity(tmp_path):
     if os.path.isdir(keep):
         import shutil
         shutil.copy(str(out), os.path.join(keep, "r2_nccl_parity_n2.json"))
+
+
+@pytest.mark.parametrize("M,N,K", [(1280, 1920, 1100), (1250, 1900, 1031), (128 * 149, 128, 2048), (2000, 9500, 1030)])
+def test_tail_wave_split(M, N, K):
+    """Grids of the warp-specialised kernel whose last wave is nearly empty are cut into full
+    waves + a k-split tail launch (cc_contract.cu: tail_plan).  Result == numpy and == the same
+    kernel with the tail left alone (tuning bit 64) to round-off; accumulation into C (beta = 1)
+    and a strided C included."""
+    from pymes_b200 import _lib, backend as bk
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.randn(M, K, dtype=torch.float64, device="cuda", generator=g)
+    B = torch.randn(K, N, dtype=torch.float64, device="cuda", generator=g)
+    C0 = torch.randn(N, M, dtype=torch.float64, device="cuda", generator=g)
+    lib = _lib.load()
+    try:
+        lib.pmb_contract_set_tuning(5, 0)
+        before = bk.launch_count()
+        got = bk.contract("mk,kn->mn", A, B)
+        launches = bk.launch_count() - before
+        acc = C0.clone()
+        bk.contract("mk,kn->mn", A, B, out=acc.t(), alpha=0.5, beta=1.0)          # C stored transposed
+        lib.pmb_contract_set_tuning(5 + 64, 0)
+        before = bk.launch_count()
+        plain = bk.contract("mk,kn->mn", A, B)
+        assert bk.launch_count() - before == 1
+    finally:
+        lib.pmb_contract_set_tuning(-1, 0)
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    rest = tiles % 148
+    assert launches == (3 if (tiles > 148 and 0 < rest <= 74) else 1)
+    want = A.cpu().numpy() @ B.cpu().numpy()
+    assert _rel(got.cpu().numpy(), want) < 1e-13
+    assert _rel(plain.cpu().numpy(), got.cpu().numpy()) < 1e-13
+    assert _rel(acc.t().cpu().numpy(), C0.t().cpu().numpy() + 0.5 * want) < 1e-13
+
+
+def test_dots_and_lincomb_beyond_16_vectors():
+    host.test_dots_and_lincomb_beyond_16_vectors(None)

@@ -798,3 +798,16 @@ def test_ccd_rejects_non_contiguous_amps(cpu_abi):
     amps = _t(np.zeros((nv, nv, no, no))).permute(1, 0, 2, 3)[:, :, :, ::1].transpose(2, 3)
     with pytest.raises(ValueError, match="contiguous"):
         ccd.CCD(no).solve(_t(fock), _t(V), amps=amps, max_iter=0)
+
+
+def test_dots_and_lincomb_beyond_16_vectors(cpu_abi):
+    """The C entry points take at most 16 vectors per call (a 10-root Davidson subspace holds 40):
+    the wrappers split longer lists."""
+    from pymes_b200 import backend as bk
+    rng = np.random.default_rng(2)
+    X = rng.standard_normal((37, 50))
+    y = rng.standard_normal(50)
+    c = rng.standard_normal(37)
+    xs = [_t(x) for x in X]
+    np.testing.assert_allclose(_n(bk.dots(xs, _t(y))), X @ y, rtol=1e-13)
+    np.testing.assert_allclose(_n(bk.lincomb(list(c), xs)), c @ X, rtol=1e-13, atol=1e-13)
