@@ -248,6 +248,17 @@ def run_reference(args):
     emit(line)
 
 
+def synthetic_config(n_gpus, no, nv):
+    return {"workload": "synthetic non-hermitian FCIDUMP-like integrals (BASELINE configs[2]): o=%d, v=%d, "
+                        "V = eps*N(0,1) with only the (pq)(rs)<->(qp)(sr) symmetry, CCSD+DIIS iteration" % (no, nv),
+            "method": "CCSD", "n_occ": no, "n_virt": nv, "n_orb": no + nv,
+            "V_abcd": "dense, STORED in HBM as (ab) row blocks (%.1f GB per GPU), streamed by the ladder kernel"
+                      % (8.0 * ((nv + n_gpus - 1) // n_gpus) * nv ** 3 / 1e9),
+            "generator": "pmb_synth_block: counter-based, each rank writes its own rows on the device",
+            "l2_policy": "inputs_exceed_l2 (every operand >> 126 MB L2)",
+            "parallelism": "ab-block x%d" % n_gpus}
+
+
 def workload_config(n_gpus, no, cutoff=None, dense_abcd=False):
     cutoff = cutoff or CUTOFF_FOR_GPUS[n_gpus]
     return {"workload": "TC-UEG 54e rs=%.1f CCSD+DIIS iteration, plane-wave cutoff %g" % (RS, cutoff),
@@ -381,26 +392,46 @@ def run_ours(args):
         dist.barrier()
 
     t0 = time.time()
-    m = ueg.UEG(N_ELE, no, no, RS)
-    m.init_single_basis(cutoff)
-    m.k_cutoff, m.gamma = K_CUTOFF, None
-    nP, nv = m.n_orb, m.n_orb - no
-    virtual = () if args.dense_abcd else ("abcd",)
-    fock = build_fock(m, no)
-    if world > 1:
+    synthetic_wl = args.workload == "synthetic"
+    if synthetic_wl:
+        # BASELINE configs[2]: V_abcd is genuinely dense here -- stored as row blocks, streamed from HBM
         from pymes_b200 import parallel
-        comm = parallel.Comm(dist.group.WORLD)
-        cc = parallel.ShardedCCSD(no, comm, is_dcsd=args.dcsd)
-        dV = parallel.build_sharded_hamiltonian(m, no, comm, tc_parts(m), virtual=virtual)
-    else:
         from pymes_b200.integral.partition import KEYS
-        cc = ccsd.CCSD(no, is_dcsd=args.dcsd)
-        dV = m.eval_2b_blocks(no, list(KEYS), tc_parts(m), virtual=virtual)
+        from pymes_b200.util import synthetic
+        no, nv = args.occ, args.virt
+        nP = no + nv
+        args.dense_abcd = True
+        fock = synthetic.tc_fock(no, nv, seed=0)
+        if world > 1:
+            comm = parallel.Comm(dist.group.WORLD)
+            shard = parallel.Shard(comm, nv)
+            ranges = {k: {d: (no + shard.lo, shard.na)} for k, d in parallel.SHARD_DIMS.items()}
+            cc = parallel.ShardedCCSD(no, comm, is_dcsd=args.dcsd)
+        else:
+            ranges = None
+            cc = ccsd.CCSD(no, is_dcsd=args.dcsd)
+        dV = synthetic.tc_blocks(no, nv, list(KEYS), seed=0, ranges=ranges, device=True)
+    else:
+        m = ueg.UEG(N_ELE, no, no, RS)
+        m.init_single_basis(cutoff)
+        m.k_cutoff, m.gamma = K_CUTOFF, None
+        nP, nv = m.n_orb, m.n_orb - no
+        virtual = () if args.dense_abcd else ("abcd",)
+        fock = build_fock(m, no)
+        if world > 1:
+            from pymes_b200 import parallel
+            comm = parallel.Comm(dist.group.WORLD)
+            cc = parallel.ShardedCCSD(no, comm, is_dcsd=args.dcsd)
+            dV = parallel.build_sharded_hamiltonian(m, no, comm, tc_parts(m), virtual=virtual)
+        else:
+            from pymes_b200.integral.partition import KEYS
+            cc = ccsd.CCSD(no, is_dcsd=args.dcsd)
+            dV = m.eval_2b_blocks(no, list(KEYS), tc_parts(m), virtual=virtual)
     torch.cuda.synchronize()
     t_build = time.time() - t0
     if rank == 0:
-        log("TC-UEG 54e: nP=%d (o=%d, v=%d), integrals built in %.1f s, %.1f GB allocated"
-            % (nP, no, nv, t_build, torch.cuda.memory_allocated() / 1e9))
+        log("%s: nP=%d (o=%d, v=%d), integrals built in %.1f s, %.1f GB allocated"
+            % ("synthetic" if synthetic_wl else "TC-UEG 54e", nP, no, nv, t_build, torch.cuda.memory_allocated() / 1e9))
     e_mp2 = cc.setup(fock, dV)
     if rank == 0:
         log("E_MP2 = %.10f" % e_mp2)
@@ -503,12 +534,13 @@ def run_ours(args):
     line = {"metric": "ccsd_iteration_fp64_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args.gpus, no, cutoff, args.dense_abcd), n_orb=nP, n_virt=nv,
+            "config": dict(synthetic_config(args.gpus, no, nv) if synthetic_wl
+                           else workload_config(args.gpus, no, cutoff, args.dense_abcd), n_orb=nP, n_virt=nv,
                            **({"method": "DCSD"} if args.dcsd else {}),
                            flops_per_step=F, energy=e_final, build_seconds=t_build),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof}
     if rank == 0:
-        if args.gpus == 1 and not args.no_cpu:
+        if args.gpus == 1 and not args.no_cpu and not synthetic_wl:
             cores = len(os.sched_getaffinity(0))
             log("timing the CPU oracle on %d host cores ..." % cores)
             line["cpu_baseline"] = cpu_sample(2, 1, budget_s=60.0, keep_problem=True)
@@ -538,6 +570,11 @@ def main():
     ap.add_argument("--no-calibration", action="store_true", help="skip the in-run DGEMM / D2D-copy calibration")
     ap.add_argument("--dcsd", action="store_true",
                     help="time a DCSD iteration (the other method of BASELINE configs[1]) instead of CCSD")
+    ap.add_argument("--workload", default="ueg", choices=["ueg", "synthetic"],
+                    help="ueg: TC-UEG 54e (BASELINE configs[1], the headline); synthetic: configs[2], o=50 v=500 "
+                         "random non-hermitian integrals with a STORED dense V_abcd (fits 8 GPUs)")
+    ap.add_argument("--occ", type=int, default=50, help="synthetic workload: occupied orbitals")
+    ap.add_argument("--virt", type=int, default=500, help="synthetic workload: virtual orbitals")
     ap.add_argument("--dense-abcd", action="store_true",
                     help="store V_abcd in HBM instead of generating it in the ladder kernel")
     args = ap.parse_args()

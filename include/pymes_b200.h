@@ -335,6 +335,21 @@ typedef struct pmb_ueg_operand {
     int32_t k_axis[PMB_MAX_DIMS];
 } pmb_ueg_operand_t;
 
+/* ------------------------------------------------------------------------ */
+/* Synthetic non-hermitian integrals (BASELINE.json configs[2]; SURVEY 8(d) C3   */
+/* recipe): out[np][nq][nr][ns] = V[lo[0]+.., lo[1]+.., lo[2]+.., lo[3]+..] with  */
+/*   V[p,q,r,s] = eps * table[ h(seed, c) >> 48 ],                                */
+/*   c = min(((p n + q) n + r) n + s, ((q n + p) n + s) n + r)                    */
+/* -- a counter-based generator keyed on the canonical representative of the      */
+/* one symmetry a transcorrelated V keeps, (pq)(rs) <-> (qp)(sr)                  */
+/* (pymes/util/fcidump.py:147-149); h = two splitmix64 finaliser rounds of         */
+/* c * 0x9E3779B97F4A7C15 + seed * 0xBF58476D1CE4E5B9 + 1; `table` = 65536        */
+/* standard-normal quantiles (device, made by the host).  Bit-identical to        */
+/* pymes_b200/util/synthetic.py on the host.  HBM-bound, 8 B per element.         */
+/* ------------------------------------------------------------------------ */
+int pmb_synth_block(int n_orb, unsigned long long seed, double eps, const double *table,
+                    const int32_t lo[4], const int32_t ext[4], double *out, pmb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,8 @@ _SIGS = {
                                       C.c_void_p]),
     "pmb_ueg_build_nz": (C.c_int, [C.POINTER(Ueg), C.c_void_p, C.c_void_p, C.c_void_p, I32x4, I32x4,
                                    C.c_void_p, C.c_void_p]),
+    "pmb_synth_block": (C.c_int, [C.c_int, C.c_ulonglong, C.c_double, C.c_void_p, I32x4, I32x4, C.c_void_p,
+                                  C.c_void_p]),
     "pmb_ueg_build_block": (C.c_int, [C.POINTER(Ueg), C.c_void_p, C.c_void_p, C.c_void_p, I32x4, I32x4,
                                       C.c_void_p, C.c_void_p]),
 }

@@ -28,7 +28,9 @@ from .solver import ccd, ccsd, mp2
 from .solver.ccsd import FOCK_SHARED, FOCK_TERMS, SHARED_PRODUCTS, V_TERMS, SINGLES_TERMS
 
 # integral blocks held as local row blocks: key -> dimension that carries the sharded index
-SHARD_DIMS = {"abcd": 0, "abci": 0, "abic": 0, "aibc": 0, "iabc": 1}
+# (the o^2v^2 blocks V_aibj / V_aijb are read by two rows of the dressed V_abij only, always with a
+#  as the row index: held as local rows as well -- 5 GB each at o = 50, v = 500)
+SHARD_DIMS = {"abcd": 0, "abci": 0, "abic": 0, "aibc": 0, "iabc": 1, "aibj": 0, "aijb": 0}
 
 
 class Comm:

@@ -6,14 +6,20 @@ canonical representative of the only symmetry a transcorrelated Hamiltonian keep
 rank's row block of V_abcd, 500 GB / N at full size -- can be generated on its own, on any
 device, without V_pqrs ever existing.
 
-The generator is a pure function of (seed, canonical index): splitmix64 finaliser -> two 53-bit
-uniforms -> Box-Muller.  It is evaluated here with numpy integer arithmetic (host); the same
-few lines are what a device-side generated operand would evaluate (round 2)."""
+The generator is a pure function of (seed, canonical index): two rounds of the splitmix64
+finaliser give 64 bits, the top 16 select one of 65536 standard-normal quantiles (a table made
+once with ``scipy.special.ndtri``).  Integer arithmetic, one look-up and one multiply -- no
+transcendental function is evaluated per element, so the numpy code below (host) and the kernel
+``pmb_synth_block`` (device, csrc/synth_build.cu) produce the same doubles BIT FOR BIT."""
+import ctypes as C
+
 import numpy as np
 
 _M1 = np.uint64(0xBF58476D1CE4E5B9)
 _M2 = np.uint64(0x94D049BB133111EB)
 _GOLD = np.uint64(0x9E3779B97F4A7C15)
+TABLE_BITS = 16
+_table = {}
 
 
 def _mix(x):
@@ -24,16 +30,40 @@ def _mix(x):
         return x ^ (x >> np.uint64(31))
 
 
+def normal_table():
+    """The 65536 quantiles z_k = Phi^-1((k + 1/2) / 65536) (mean 0, variance 1 - 3e-4)."""
+    if "host" not in _table:
+        from scipy import special
+        k = np.arange(1 << TABLE_BITS, dtype=np.float64)
+        _table["host"] = np.ascontiguousarray(special.ndtri((k + 0.5) / float(1 << TABLE_BITS)))
+    return _table["host"]
+
+
 def normal_from_index(seed, idx):
     """N(0,1) deviates for an array of uint64 counters ``idx`` (deterministic in (seed, idx))."""
     idx = np.asarray(idx, dtype=np.uint64)
     with np.errstate(over="ignore"):
-        base = _mix(idx * _GOLD + np.uint64(seed) * _M1 + np.uint64(1))
-        a = _mix(base)
-        b = _mix(base ^ _GOLD)
-    u1 = ((a >> np.uint64(11)).astype(np.float64) + 1.0) / 9007199254740993.0      # (0, 1)
-    u2 = (b >> np.uint64(11)).astype(np.float64) / 9007199254740992.0              # [0, 1)
-    return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+        h = _mix(_mix(idx * _GOLD + np.uint64(seed) * _M1 + np.uint64(1)))
+    return normal_table()[(h >> np.uint64(64 - TABLE_BITS)).astype(np.int64)]
+
+
+def tc_block_device(n_orb, lo, ext, seed=0, eps=None, out=None):
+    """The same block as :func:`tc_block`, written by ``pmb_synth_block`` into a CUDA tensor
+    (HBM-bound; one rank's 62.5 GB row block of V_abcd at o = 50, v = 500 takes tens of ms)."""
+    import torch
+    from .. import _lib, backend as bk
+    eps = 1e-2 / n_orb if eps is None else eps
+    key = ("dev", bk._device_key()[0])
+    if key not in _table:
+        _table[key] = torch.from_numpy(normal_table()).to(bk.device())
+    if out is None:
+        out = bk.empty(*[int(e) for e in ext])
+    elif not out.is_contiguous() or tuple(out.shape) != tuple(int(e) for e in ext):
+        raise ValueError("out must be a contiguous tensor of the block's shape")
+    _lib.check(_lib.load().pmb_synth_block(int(n_orb), C.c_ulonglong(int(seed)), float(eps), bk._ptr(_table[key]),
+                                           _lib.I32x4(*[int(x) for x in lo]), _lib.I32x4(*[int(x) for x in ext]),
+                                           bk._ptr(out), bk._stream()), "pmb_synth_block")
+    return out
 
 
 def tc_block(n_orb, lo, ext, seed=0, eps=None):
@@ -64,15 +94,17 @@ def tc_fock(no, nv, seed=0, off_diagonal=1e-3):
     return f + off
 
 
-def tc_blocks(no, nv, keys, seed=0, eps=None, ranges=None):
+def tc_blocks(no, nv, keys, seed=0, eps=None, ranges=None, device=False):
     """Named partition blocks (``integral.partition`` keys) generated directly; ``ranges`` =
-    ``{key: {dim: (lo, n)}}`` restricts a dimension to absolute orbital indices (a rank's rows)."""
+    ``{key: {dim: (lo, n)}}`` restricts a dimension to absolute orbital indices (a rank's rows).
+    ``device=True``: CUDA tensors written by ``pmb_synth_block`` (bit-identical values)."""
     from ..integral.partition import OCCUPIED
+    make = tc_block_device if device else tc_block
     out = {}
     for key in keys:
         lo = [0 if ch in OCCUPIED else no for ch in key]
         ext = [no if ch in OCCUPIED else nv for ch in key]
         for dim, (r_lo, r_n) in (ranges or {}).get(key, {}).items():
             lo[dim], ext[dim] = int(r_lo), int(r_n)
-        out[key] = tc_block(no + nv, lo, ext, seed, eps)
+        out[key] = make(no + nv, lo, ext, seed, eps)
     return out

@@ -371,6 +371,28 @@ class FakeLib:
         M = int(np.prod(m_ext)) if m_ext else 1
         return np.ascontiguousarray(blk.transpose(order)).reshape(M, -1).reshape(-1)
 
+    def pmb_synth_block(self, n_orb, seed, eps, table, lo, ext, out, stream):
+        """csrc/synth_build.cu restated with numpy integer arithmetic (written independently of
+        pymes_b200/util/synthetic.py so that the two check each other)."""
+        self.launches += 1
+        seed = int(seed.value if hasattr(seed, "value") else seed)
+        n = np.uint64(n_orb)
+        tab = _window(_val(table), 65536)
+        idx = [np.arange(lo[d], lo[d] + ext[d], dtype=np.uint64) for d in range(4)]
+        p, q, r, s = np.meshgrid(*idx, indexing="ij")
+        m1, m2, gold = np.uint64(0xBF58476D1CE4E5B9), np.uint64(0x94D049BB133111EB), np.uint64(0x9E3779B97F4A7C15)
+
+        def mix(x):
+            x = (x ^ (x >> np.uint64(30))) * m1
+            x = (x ^ (x >> np.uint64(27))) * m2
+            return x ^ (x >> np.uint64(31))
+        with np.errstate(over="ignore"):
+            c = np.minimum(((p * n + q) * n + r) * n + s, ((q * n + p) * n + s) * n + r)
+            h = mix(mix(c * gold + np.uint64(seed) * m1 + np.uint64(1)))
+        vals = eps * tab[(h >> np.uint64(48)).astype(np.int64)]
+        _window(_val(out), vals.size)[:] = vals.reshape(-1)
+        return 0
+
     def pmb_ueg_build_nz(self, u, W0a, W1a, W0s, lo, ext, out, stream):
         self.launches += 1
         blk = self._block(u, W0a, W1a, W0s, [lo[i] for i in range(4)], [ext[i] for i in range(4)])
