@@ -320,8 +320,13 @@ class UEG:
         """-4 pi gamma / k^4 for k > k_c, else 0 (ueg.py:772-800)."""
         self._defaults(1.0)
         kc2 = (self.k_cutoff * 2 * np.pi / self.L) ** 2
-        k2 = np.array(kSquare, dtype=np.float64, copy=True)
-        k2[k2 <= kc2 * (1 + 0.00001)] = 0.
+        if isinstance(kSquare, np.ndarray):
+            # the reference zeroes the small entries of ITS ARGUMENT in place (ueg.py:797): an
+            # observable side effect on the caller's array, kept
+            kSquare[kSquare <= kc2 * (1 + 0.00001)] = 0.
+            k2 = np.asarray(kSquare, dtype=np.float64)
+        else:
+            k2 = np.array(0. if kSquare <= kc2 * (1 + 0.00001) else kSquare, dtype=np.float64)
         res = np.divide(-4. * np.pi, k2 ** 2, out=np.zeros_like(k2), where=(k2 > 1e-12)) * self.gamma
         return res if isinstance(kSquare, np.ndarray) else float(res)
 

@@ -400,11 +400,74 @@ def sec_variants():
                         key + "_fock_after": f, key + "_dE": r["dE"]})
     save("ccd_variants", **out)
 
+def sec_ueg_modes():
+    """Every branch of eval_2b_integrals that ueg_tc does not cover (ueg.py:416-423, 440-457,
+    478-504) with the `trunc` correlator at 14e / 57 plane waves, and every correlator of
+    ueg.py:740-956 through the `only_2b` (array arguments via sumNablaUSquare, scalar ones via
+    the loop) and `effect_2b` branches at 14e / 19 plane waves.  One shim outside the
+    arithmetic: sumNablaUSquare is MEMOISED on its argument (the reference recomputes the same
+    226 981-term lattice sum for every (p, r) pair: 190 s per build at 57 plane waves)."""
+    out = {}
+
+    def memoised(m):
+        inner, cache = m.sumNablaUSquare, {}
+
+        def wrapped(k, cutoff=30):
+            key = tuple(np.round(np.asarray(k, dtype=float) * m.L / (2 * np.pi)).astype(int))
+            if key not in cache:
+                cache[key] = inner(k, cutoff)
+            return cache[key]
+        m.sumNablaUSquare = wrapped
+
+    m, nP, kint, kin = _ueg_setup(14, 0.5, 5.0)
+    m.gamma, m.k_cutoff = None, 1.0
+    memoised(m)
+    out.update(big_kint=kint, big_L=m.L, big_k_cutoff=1.0)
+    for flag in ("is_rpa_approx", "is_only_hermi_2b", "is_only_non_hermi_2b", "is_exchange_1",
+                 "is_exchange_2", "is_exchange_3"):
+        V = quiet(m.eval_2b_integrals, correlator=m.trunc, sp=0, **{flag: True})
+        idx, val = _sparse(V)
+        out["big_" + flag + "_idx"], out["big_" + flag + "_val"] = idx, val
+        print(flag, len(idx), "non-zeros")
+    # a correlator given without any branch flag: all zeros (the elif chain falls through)
+    V = quiet(m.eval_2b_integrals, correlator=m.trunc, sp=0)
+    out["big_noflag_absmax"] = np.abs(V).max()
+    for name, gamma, k_cutoff in (("trunc", None, 1.0), ("coulomb", None, None), ("smooth", None, 1.0),
+                                  ("yukawa", None, None), ("yukawa", 0.7, 1.0), ("stg", None, None), ("stg", 1.3, 1.0),
+                                  ("yukawa_coulomb", None, None), ("yukawa_coulomb", 1.1, 1.0),
+                                  ("gaskell", None, None), ("gaskell", 0.9, 2.0),
+                                  ("gaskell_modified", None, None), ("gaskell_modified", None, 1.0)):
+        m, nP, kint, kin = _ueg_setup(14, 1.0, 2.0)
+        m.gamma, m.k_cutoff = gamma, k_cutoff
+        memoised(m)
+        corr = getattr(m, name)
+        tag = "%s_g%s_k%s" % (name, gamma, k_cutoff)
+        try:
+            for flag in ("is_only_2b", "is_effect_2b"):
+                V = quiet(m.eval_2b_integrals, correlator=corr, sp=0, **{flag: True})
+                idx, val = _sparse(V)
+                out["c_" + tag + "_" + flag + "_idx"], out["c_" + tag + "_" + flag + "_val"] = idx, val
+            out["c_" + tag + "_gamma_after"] = np.nan if m.gamma is None else m.gamma
+            out["c_" + tag + "_kc_after"] = np.nan if m.k_cutoff is None else m.k_cutoff
+            print(tag, "ok")
+        except Exception as exc:                                  # noqa: BLE001
+            out["c_" + tag + "_raises"] = np.array(type(exc).__name__)
+            print(tag, "raises", type(exc).__name__, exc)
+    out["small_kint"] = kint
+    out["small_L"] = m.L
+    # trunc mutates an ndarray argument in place (ueg.py:797)
+    m, nP, kint, kin = _ueg_setup(14, 1.0, 2.0)
+    m.gamma, m.k_cutoff = None, 1.0
+    arg = np.linspace(0.0, 3.0, 13)
+    res = m.trunc(arg)
+    out["trunc_arg_after"], out["trunc_res"] = arg, res
+    save("ueg_modes", **out)
+
 
 SECTIONS = dict(molecules=sec_molecules, hf_molecule=sec_hf_molecule,
                 residual_random=sec_residual_random,
                 dressing_random=sec_dressing_random, diis=sec_diis,
-                ueg_coulomb=sec_ueg_coulomb, ueg_tc=sec_ueg_tc, feast=sec_feast, rt=sec_rt, variants=sec_variants)
+                ueg_coulomb=sec_ueg_coulomb, ueg_tc=sec_ueg_tc, feast=sec_feast, rt=sec_rt, variants=sec_variants, ueg_modes=sec_ueg_modes)
 
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(SECTIONS)):

@@ -432,31 +432,41 @@ def test_ueg_virtual_pp_ladder_bit_identical(n_ele, cutoff):
     g = torch.Generator(device="cuda").manual_seed(1)
     tau = torch.randn(nv, nv, no, no, dtype=torch.float64, device="cuda", generator=g)
     lib = _lib.load()
+    # +64: the tail wave is left alone.  A generated operand rasters the tiles m-fastest, a stored one
+    # n-fastest, so a tail launch (54e / 93 plane waves: 210 tiles = 148 + 62) would k-split DIFFERENT
+    # tiles in the two runs: equal to round-off then, not bit for bit (checked right below)
+    NT = 64
     try:
         lib.pmb_contract_set_tuning(5, 0)
+        n0 = bk.launch_count()
+        with_tail = bk.contract("abcd,cdij->abij", virt, tau)
+        tiles = ((nv * nv + 127) // 128) * ((no * no + 127) // 128)
+        assert bk.launch_count() - n0 == (3 if (tiles > 148 and 0 < tiles % 148 <= 74) else 1)
+        assert _rel(with_tail.cpu().numpy(), bk.contract("abcd,cdij->abij", dense, tau).cpu().numpy()) < 1e-13
+        lib.pmb_contract_set_tuning(5 + NT, 0)
         ref = bk.contract("abcd,cdij->abij", dense, tau)
         got = bk.contract("abcd,cdij->abij", virt, tau)
         assert torch.equal(got, ref)
-        lib.pmb_contract_set_tuning(6, 0)                 # 6-stage ring
+        lib.pmb_contract_set_tuning(6 + NT, 0)                 # 6-stage ring
         assert torch.equal(bk.contract("abcd,cdij->abij", virt, tau), bk.contract("abcd,cdij->abij", dense, tau))
         # split-K: partial sums of the generated operand
-        lib.pmb_contract_set_tuning(5, 3)
+        lib.pmb_contract_set_tuning(5 + NT, 3)
         assert torch.equal(bk.contract("abcd,cdij->abij", virt, tau), bk.contract("abcd,cdij->abij", dense, tau))
         # +16: the scanning producer instead of the non-zero walker (what patterns whose
         # contracted indices are not (r, s) use), alone and with split-K
         for split in (0, 5):
-            lib.pmb_contract_set_tuning(5 + 16, split)
+            lib.pmb_contract_set_tuning(5 + 16 + NT, split)
             assert torch.equal(bk.contract("abcd,cdij->abij", virt, tau), ref if split == 0 else
                                bk.contract("abcd,cdij->abij", dense, tau))
         # contraction over (p, q): the solved index s sits in the row group -> scanning producer
-        lib.pmb_contract_set_tuning(5, 0)
+        lib.pmb_contract_set_tuning(5 + NT, 0)
         assert torch.equal(bk.contract("abcd,abij->cdij", virt, tau), bk.contract("abcd,abij->cdij", dense, tau))
         # without the compressed value table the producers evaluate the integral formula in
         # place (walker and scanning variants): still the very same doubles
         raw = m.virtual_block(virt.lo, virt.shape, *virt.tables, compressed=False)
         assert virt.nz is not None and raw.nz is None
         for cfg in (5, 5 + 16):
-            lib.pmb_contract_set_tuning(cfg, 0)
+            lib.pmb_contract_set_tuning(cfg + NT, 0)
             assert torch.equal(bk.contract("abcd,cdij->abij", raw, tau), ref)
         assert torch.equal(bk.contract("abcd,abij->cdij", raw, tau), bk.contract("abcd,abij->cdij", dense, tau))
     finally:

@@ -824,3 +824,75 @@ def test_dots_and_lincomb_beyond_16_vectors(cpu_abi):
     xs = [_t(x) for x in X]
     np.testing.assert_allclose(_n(bk.dots(xs, _t(y))), X @ y, rtol=1e-13)
     np.testing.assert_allclose(_n(bk.lincomb(list(c), xs)), c @ X, rtol=1e-13, atol=1e-13)
+
+
+# --------------------------------------------------------------------------
+# eval_2b_integrals: the remaining branches and every correlator (fixtures: ueg_modes.npz)
+# --------------------------------------------------------------------------
+UEG_FLAGS = ["is_rpa_approx", "is_only_hermi_2b", "is_only_non_hermi_2b", "is_exchange_1", "is_exchange_2",
+             "is_exchange_3"]
+UEG_CORRELATORS = [("trunc", None, 1.0), ("coulomb", None, None), ("smooth", None, 1.0), ("yukawa", None, None),
+                   ("yukawa", 0.7, 1.0), ("stg", None, None), ("stg", 1.3, 1.0), ("yukawa_coulomb", None, None),
+                   ("yukawa_coulomb", 1.1, 1.0), ("gaskell", None, None), ("gaskell", 0.9, 2.0),
+                   ("gaskell_modified", None, None), ("gaskell_modified", None, 1.0)]
+
+
+@pytest.mark.parametrize("flag", UEG_FLAGS)
+def test_ueg_remaining_branches_match_reference(cpu_abi, flag):
+    """ueg.py:416-423, 440-457, 478-504 with `trunc` at 14e / 57 plane waves against the reference's
+    triple loop.  On the CPU emulator a slab of rows, on the GPU the whole tensor."""
+    from pymes_b200.model import ueg
+    g = golden("ueg_modes")
+    m = ueg.UEG(14, 7, 7, 0.5)
+    m.init_single_basis(5.0)
+    m.gamma, m.k_cutoff = None, 1.0
+    nP = m.n_orb
+    np.testing.assert_array_equal(m.k_int(), g["big_kint"])
+    ref = _dense(g["big_" + flag + "_idx"], g["big_" + flag + "_val"], nP)
+    scale = np.abs(ref).max()
+    if DEVICE == "cuda":
+        V = m.eval_2b_integrals(correlator=m.trunc, sp=0, **{flag: True})
+        assert np.abs(V - ref).max() <= 1e-11 * scale
+        zero = m.eval_2b_integrals(correlator=m.trunc, sp=0)            # no branch selected: zeros
+        assert np.abs(zero).max() == 0.0 == float(g["big_noflag_absmax"])
+    else:
+        mode = "rpa" if flag == "is_rpa_approx" else flag[3:]
+        W0, W1 = m.pair_tables(mode, m.trunc)
+        blk = m.build_block((2, 0, 11, 0), (3, nP, 4, nP), W0a=W0, W1a=W1)
+        assert np.abs(_n(blk) - ref[2:5, :, 11:15, :]).max() <= 1e-11 * scale
+
+
+@pytest.mark.parametrize("name,gamma,k_cutoff", UEG_CORRELATORS)
+def test_ueg_every_correlator_matches_reference(cpu_abi, name, gamma, k_cutoff):
+    """Each correlator of ueg.py:740-956 (default and explicit gamma / k_cutoff) through the
+    `only_2b` and `effect_2b` branches at 14e / 19 plane waves, whole tensor, and the values the
+    correlator leaves in ``gamma`` / ``k_cutoff``."""
+    from pymes_b200.model import ueg
+    g = golden("ueg_modes")
+    tag = "c_%s_g%s_k%s" % (name, gamma, k_cutoff)
+    for flag in ("is_only_2b", "is_effect_2b"):
+        m = ueg.UEG(14, 7, 7, 1.0)
+        m.init_single_basis(2.0)
+        m.gamma, m.k_cutoff = gamma, k_cutoff
+        nP = m.n_orb
+        np.testing.assert_array_equal(m.k_int(), g["small_kint"])
+        V = m.eval_2b_integrals(correlator=getattr(m, name), sp=0, **{flag: True})
+        ref = _dense(g[tag + "_" + flag + "_idx"], g[tag + "_" + flag + "_val"], nP)
+        assert np.abs(V - ref).max() <= 1e-10 * max(np.abs(ref).max(), 1e-300), flag
+    ga, kc = float(g[tag + "_gamma_after"]), float(g[tag + "_kc_after"])
+    assert (m.gamma is None and np.isnan(ga)) or m.gamma == ga
+    assert (m.k_cutoff is None and np.isnan(kc)) or m.k_cutoff == kc
+
+
+def test_trunc_mutates_its_array_argument_like_the_reference():
+    """ueg.py:797 zeroes the small entries of the caller's array in place."""
+    from pymes_b200.model import ueg
+    g = golden("ueg_modes")
+    m = ueg.UEG(14, 7, 7, 1.0)
+    m.init_single_basis(2.0)
+    m.gamma, m.k_cutoff = None, 1.0
+    arg = np.linspace(0.0, 3.0, 13)
+    res = m.trunc(arg)
+    np.testing.assert_array_equal(arg, g["trunc_arg_after"])
+    np.testing.assert_allclose(res, g["trunc_res"], rtol=1e-15)
+    assert m.trunc(0.2) == 0.0 and m.trunc(2.0) == -4.0 * np.pi / 4.0
