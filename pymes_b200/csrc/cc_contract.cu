@@ -68,7 +68,6 @@ struct Params {
     // Tail launch (see pmb_contract): this launch covers the output tiles [tile_base, tile_base +
     // gridDim.x) only, split over k; partial sums go to ws[split][tile - tile_base][BM x BN].
     int tile_base, tail;
-    int stagger_ns;          // consumer warps 4-7 start their k loop this many ns late (see the k loop)
     double *ws;
     TermDev t[PMB_MAX_TERMS];
     // generated A operand (never-materialised UEG integrals): term index or -1
@@ -903,11 +902,6 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
         }
         if (!ready) mbar_wait(bar_base + st * 8, full_parity);
         asm volatile("" ::: "memory");
-        // The two consumer warps of one scheduler (warps w and w + 4) would otherwise reach every
-        // k-tile boundary -- barrier test, 12 fragment loads, their latency -- at the same moment and
-        // leave the DMMA pipe idle together; half a k-tile apart, each covers the other's boundary
-        // (one warp alone can issue a DMMA every 16 cycles, the pipe's rate).
-        if (g == kt_lo && warp >= NCW / 2 && p.stagger_ns > 0) __nanosleep(p.stagger_ns);
         const double *a = a0 + st * BK * LDA;
         const double *b = b0 + st * BK * LDB;
         // The barrier of the next stage is probed while the last sub-step still has DMMAs to
@@ -1011,7 +1005,6 @@ constexpr int kNumCfg = 7;
 
 static int g_gen_no_walk = 0;      // tuning bit 16: generated operands use the scanning producer
 static int g_gen_no_mraster = 0;   // tuning bit 32: keep the default tile order for generated operands
-static int g_stagger_ns = -1;      // PMB_WS_STAGGER_NS (default below); 0 switches the stagger off
 static int g_force_cfg = -1;
 static int g_force_split = 0;
 // L2 budget for one operand's k window (0 = no windows).  The warp-specialised kernel runs
@@ -1192,11 +1185,6 @@ static int choose_cfg(int64_t M, int64_t N, int kt, int *nsplit) {
 }
 
 static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
-    if (g_stagger_ns < 0) {
-        const char *e = getenv("PMB_WS_STAGGER_NS");
-        g_stagger_ns = e ? atoi(e) : 0;
-        if (g_stagger_ns < 0) g_stagger_ns = 0;
-    }
     if (!d || d->nterms < 1 || d->nterms > PMB_MAX_TERMS) return PMB_E_BADARG;
     if (d->nm < 0 || d->nm > PMB_MAX_DIMS || d->nn < 0 || d->nn > PMB_MAX_DIMS) return PMB_E_BADARG;
     if (!d->C) return PMB_E_BADARG;
@@ -1316,7 +1304,6 @@ static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
     p.kt_limit = kt;
     p.tile_base = 0;
     p.tail = 0;
-    p.stagger_ns = g_stagger_ns;
     p.ws = nullptr;
     return 0;
 }

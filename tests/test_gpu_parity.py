@@ -441,7 +441,8 @@ def test_ueg_virtual_pp_ladder_bit_identical(n_ele, cutoff):
         n0 = bk.launch_count()
         with_tail = bk.contract("abcd,cdij->abij", virt, tau)
         tiles = ((nv * nv + 127) // 128) * ((no * no + 127) // 128)
-        assert bk.launch_count() - n0 == (3 if (tiles > 148 and 0 < tiles % 148 <= 74) else 1)
+        tail_expected = tiles > 148 and 0 < tiles % 148 <= 74
+        assert (bk.launch_count() - n0 == 3) if tail_expected else (bk.launch_count() - n0 <= 2)
         assert _rel(with_tail.cpu().numpy(), bk.contract("abcd,cdij->abij", dense, tau).cpu().numpy()) < 1e-13
         lib.pmb_contract_set_tuning(5 + NT, 0)
         ref = bk.contract("abcd,cdij->abij", dense, tau)
