@@ -1003,6 +1003,7 @@ static const TileCfg kCfg[] = {
     {128, 128, 384, 1.30}, {128, 128, 384, 1.00}};
 constexpr int kNumCfg = 7;
 
+static int g_no_tail = 0;          // tuning bit 64: never cut the tail wave off (see tail_plan)
 static int g_gen_no_walk = 0;      // tuning bit 16: generated operands use the scanning producer
 static int g_gen_no_mraster = 0;   // tuning bit 32: keep the default tile order for generated operands
 static int g_force_cfg = -1;
@@ -1173,7 +1174,17 @@ static int choose_cfg(int64_t M, int64_t N, int kt, int *nsplit) {
         const int per_sm = (kCfg[c].threads == 128) ? 3 : 1;   // co-resident CTAs
         const int64_t slots = (int64_t)kSmCount * per_sm;
         const int split = split_for(tiles, slots, kt);
-        const double waves = (double)((tiles * split + slots - 1) / slots);
+        double waves = (double)((tiles * split + slots - 1) / slots);
+        if (c >= 5 && split == 1 && !g_no_tail && kt >= 64) {
+            // the warp-specialised kernel cuts a sparse last wave off and splits it over k
+            // (tail_plan): it then costs 1 / floor(148 / rest) of a wave
+            const int64_t rest = tiles % slots;
+            if (tiles > slots && rest > 0 && rest <= slots / 2) {
+                int64_t ts = slots / rest;
+                if (ts > kt / 16) ts = kt / 16;
+                if (ts >= 2) waves = (double)(tiles / slots) + 1.0 / (double)ts;
+            }
+        }
         const double cost = waves * per_sm * kCfg[c].bm * kCfg[c].bn / (kCfg[c].eff * split);
         if (cost < best_cost * 0.999) {
             best_cost = cost;
@@ -1337,7 +1348,6 @@ static int panel_ktiles(const Params &p, int cfg) {
 struct TailPlan {
     int full_tiles, tail_tiles, split;
 };
-static int g_no_tail = 0;          // tuning bit 64: never cut the tail wave off
 static TailPlan tail_plan(const Params &p, int cfg) {
     TailPlan t = {0, 0, 1};
     if (cfg < 5 || g_no_tail || p.nsplit != 1 || panel_ktiles(p, cfg) < p.total_ktiles) return t;
