@@ -96,6 +96,40 @@ def zeros(*shape):
     return torch.zeros(shape, dtype=F64, device=device())
 
 
+def empty_stacked(shape_a, shape_b):
+    """Two tensors of equal size carved out of ONE allocation, back to back (see ``stacked_rows``)."""
+    na = int(np.prod(shape_a))
+    if na != int(np.prod(shape_b)):
+        raise ValueError("stacked tensors must have the same number of elements")
+    buf = torch.empty(2 * na, dtype=F64, device=device())
+    return buf[:na].view(*shape_a), buf[na:].view(*shape_b)
+
+
+def stacked_rows(A, B, k_shape):
+    """If the contiguous tensors A and B lie back to back in one allocation (``empty_stacked``) and
+    both end in the index pattern ``k_shape`` (the contracted indices of a common contraction),
+    return the VIEW [2, rows, *k_shape] over both -- one operand, so that two contractions with the
+    same right-hand operand become one launch with twice the rows (two few-wave grids side by side
+    become one grid without a second tail wave).  Otherwise None."""
+    if not (isinstance(A, torch.Tensor) and isinstance(B, torch.Tensor)):
+        return None
+    if not (A.is_contiguous() and B.is_contiguous()) or A.numel() != B.numel() or A.numel() == 0:
+        return None
+    k = int(np.prod(k_shape))
+    if tuple(A.shape[-len(k_shape):]) != tuple(k_shape) or tuple(B.shape[-len(k_shape):]) != tuple(k_shape):
+        return None
+    if A.untyped_storage().data_ptr() != B.untyped_storage().data_ptr() or \
+            B.data_ptr() != A.data_ptr() + 8 * A.numel():
+        return None
+    rows = A.numel() // k
+    strides, acc = [], 1
+    for e in reversed(k_shape):
+        strides.append(acc)
+        acc *= int(e)
+    return torch.as_strided(A, (2, rows) + tuple(int(e) for e in k_shape), (A.numel(), k) + tuple(reversed(strides)),
+                            A.storage_offset())
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -404,7 +438,8 @@ def describe_contraction(out_sub, terms, out=None, beta=0.0, conv=None, alloc=No
 
 
 GEMV_MIN_ELEMENTS = 1 << 22
-GEMV_MIN_OUTPUTS = 1 << 16           # one thread / one warp per output: needs that many to fill the GPU
+GEMV_MIN_OUTPUTS = 1 << 16           # one thread per output: needs that many to fill the GPU
+GEMV_MIN_WARP_OUTPUTS = 1 << 11      # one warp per output
 
 
 def _try_gemv(out_sub, terms, out, beta):
@@ -425,8 +460,6 @@ def _try_gemv(out_sub, terms, out, beta):
     vsub, vec, bsub, big = (sa, A, sb, B) if not a_out else (sb, B, sa, A)
     if big.numel() < GEMV_MIN_ELEMENTS or vec.dim() != len(vsub) or big.dim() != len(bsub):
         return None
-    if big.numel() < GEMV_MIN_OUTPUTS * vec.numel():
-        return None                      # few outputs, long sums: the split-K contraction does better
     if len(set(vsub)) != len(vsub) or len(set(bsub)) != len(bsub) or len(set(out_sub)) != len(out_sub):
         return None
     xs = [ch for ch in bsub if ch not in vsub]
@@ -435,6 +468,16 @@ def _try_gemv(out_sub, terms, out, beta):
     ext = dict(zip(bsub, big.shape))
     if any(ext[ch] != n for ch, n in zip(vsub, vec.shape)):
         raise ValueError("extent mismatch in %s,%s" % (sa, sb))
+    # enough outputs to fill the GPU?  When the big operand is unit-stride along a summed index the
+    # kernel gives a whole WARP to each output (lanes walk that index): a few thousand outputs are
+    # enough ("jb,abij->ai": 13 176 outputs of 13 176-term sums over T2 ran at 0.3 TB/s as a split-K
+    # tensor contraction).  Unit-stride along an output index means one THREAD per output.
+    bs = dict(zip(bsub, big.stride()))
+    k0 = min(vsub, key=lambda ch: (bs[ch], ch))
+    warp_per_output = ext[k0] >= 16 and (not xs or bs[k0] < min(bs[ch] for ch in xs))
+    n_out = big.numel() // max(vec.numel(), 1)
+    if n_out < (GEMV_MIN_WARP_OUTPUTS if warp_per_output else GEMV_MIN_OUTPUTS):
+        return None                      # few outputs, long sums: left to the split-K contraction
     shape = tuple(ext[ch] for ch in out_sub)
     if out is None:
         if beta != 0.0:

@@ -49,21 +49,101 @@ struct Str4 {
     long long so[4];
 };
 
+// One pass of `kEwCopy` independent elements per thread (bytes in flight, not instruction count, is
+// what a strided copy needs); the two slow indices are split off once per CTA pass with 64-bit
+// arithmetic, the two fast ones per element in 32 bits.
+constexpr int kEwCopy = 4;
 __global__ void __launch_bounds__(256) axpby4_kernel(Str4 g, double alpha, const double *__restrict__ in,
                                                      double beta, double *out) {
     const size_t n = (size_t)g.e[0] * g.e[1] * g.e[2] * g.e[3];
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-         idx += (size_t)gridDim.x * blockDim.x) {
-        size_t r = idx;
-        const long long i3 = r % g.e[3];
-        r /= g.e[3];
-        const long long i2 = r % g.e[2];
-        r /= g.e[2];
-        const long long i1 = r % g.e[1];
-        const long long i0 = r / g.e[1];
-        const double v = alpha * in[i0 * g.si[0] + i1 * g.si[1] + i2 * g.si[2] + i3 * g.si[3]];
-        double *d = out + i0 * g.so[0] + i1 * g.so[1] + i2 * g.so[2] + i3 * g.so[3];
-        *d = (beta != 0.0) ? v + beta * (*d) : v;
+    const unsigned e3 = (unsigned)g.e[3], e23 = (unsigned)(g.e[2] * g.e[3]);
+    const bool small_inner = g.e[2] * g.e[3] < (1LL << 31);
+    const size_t pass = (size_t)blockDim.x * kEwCopy;
+    for (size_t base = (size_t)blockIdx.x * pass; base < n; base += (size_t)gridDim.x * pass) {
+        double v[kEwCopy];
+        long long oo[kEwCopy];
+        const size_t r01 = small_inner ? base / e23 : 0;            // CTA-uniform
+        const unsigned rem0 = small_inner ? (unsigned)(base - r01 * e23) : 0;
+#pragma unroll
+        for (int u = 0; u < kEwCopy; ++u) {
+            const size_t idx = base + (size_t)u * blockDim.x + threadIdx.x;
+            v[u] = 0.0;
+            oo[u] = -1;
+            if (idx < n) {
+                long long i0, i1, i2, i3;
+                if (small_inner) {
+                    const unsigned local = rem0 + u * blockDim.x + threadIdx.x;      // < e23 + pass
+                    const unsigned d01 = local / e23, r = local - d01 * e23;
+                    const size_t q = r01 + d01;
+                    i0 = (long long)(q / (size_t)g.e[1]);
+                    i1 = (long long)(q - (size_t)i0 * g.e[1]);
+                    i2 = r / e3;
+                    i3 = r - (unsigned)i2 * e3;
+                } else {
+                    size_t r = idx;
+                    i3 = r % g.e[3];
+                    r /= g.e[3];
+                    i2 = r % g.e[2];
+                    r /= g.e[2];
+                    i1 = r % g.e[1];
+                    i0 = r / g.e[1];
+                }
+                v[u] = alpha * in[i0 * g.si[0] + i1 * g.si[1] + i2 * g.si[2] + i3 * g.si[3]];
+                oo[u] = i0 * g.so[0] + i1 * g.so[1] + i2 * g.so[2] + i3 * g.so[3];
+            }
+        }
+        if (beta != 0.0) {
+            double o[kEwCopy];
+#pragma unroll
+            for (int u = 0; u < kEwCopy; ++u) o[u] = oo[u] >= 0 ? out[oo[u]] : 0.0;
+#pragma unroll
+            for (int u = 0; u < kEwCopy; ++u) v[u] += beta * o[u];
+        }
+#pragma unroll
+        for (int u = 0; u < kEwCopy; ++u)
+            if (oo[u] >= 0) out[oo[u]] = v[u];
+    }
+}
+
+// Transposing form of the same copy: the input is unit-stride along dimension `dt` (one of 0..2),
+// the output along dimension 3.  32 x 32 tiles over (dt, 3) go through shared memory so that both
+// the reads (lanes along dt) and the writes (lanes along 3) are full 256 B row segments; the two
+// remaining dimensions are the batch.  (The element-per-thread kernel reads one 32 B sector per
+// 8 B word here: 0.25 of the HBM rate, tools/bench_hbm.py.)
+__global__ void __launch_bounds__(256) axpby4_transpose_kernel(Str4 g, int dt, double alpha,
+                                                               const double *__restrict__ in, double beta,
+                                                               double *out) {
+    __shared__ double tile[32][33];
+    int ob[2], nb = 0;                         // the two batch dimensions
+    for (int d = 0; d < 3; ++d)
+        if (d != dt) ob[nb++] = d;
+    const long long tt = (g.e[dt] + 31) / 32, t3 = (g.e[3] + 31) / 32;
+    const long long ntile = tt * t3 * g.e[ob[0]] * g.e[ob[1]];
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;        // 32 x 8
+    for (long long t = blockIdx.x; t < ntile; t += gridDim.x) {
+        long long r = t;
+        const long long c3 = (r % t3) * 32;
+        r /= t3;
+        const long long ct = (r % tt) * 32;
+        r /= tt;
+        const long long b1 = r % g.e[ob[1]], b0 = r / g.e[ob[1]];
+        const long long ibase = b0 * g.si[ob[0]] + b1 * g.si[ob[1]], obase = b0 * g.so[ob[0]] + b1 * g.so[ob[1]];
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {          // read: lanes along dt, rows along 3
+            const long long i3 = c3 + ly + 8 * k, it = ct + lx;
+            if (i3 < g.e[3] && it < g.e[dt]) tile[ly + 8 * k][lx] = in[ibase + it * g.si[dt] + i3 * g.si[3]];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {          // write: lanes along 3, rows along dt
+            const long long it = ct + ly + 8 * k, i3 = c3 + lx;
+            if (i3 < g.e[3] && it < g.e[dt]) {
+                double *d = out + obase + it * g.so[dt] + i3 * g.so[3];
+                const double v = alpha * tile[lx][ly + 8 * k];
+                *d = (beta != 0.0) ? v + beta * (*d) : v;
+            }
+        }
     }
 }
 
@@ -258,6 +338,39 @@ __global__ void __launch_bounds__(kReduceThreads)
     block_reduce_store<3>(s, ws);
 }
 
+// The same sums when V_ijab is STORED as [a,b,i,j] (the solvers keep such a copy of this static
+// block: element strides (no, 1, nv o^2, o^2) for the indices (i,j,a,b)): the direct term reads row
+// (a,b) of it, the exchange term row (b,a), both contiguous like the row of T2 -- a pure stream,
+// 24 B per element.  One warp per row, 4 rows per pass and CTA.
+__global__ void __launch_bounds__(kReduceThreads)
+    energy_rows_kernel(int no, int nv, int a_lo, int na, const double *__restrict__ T2,
+                       const double *__restrict__ T1, const double *__restrict__ Vt, double *ws) {
+    const int oo = no * no;
+    const long long rows = (long long)na * nv;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    double s[3] = {0.0, 0.0, 0.0};
+    for (long long r = warp0; r < rows; r += nwarps) {
+        const int al = (int)(r / nv), b = (int)(r - (long long)al * nv), a = a_lo + al;
+        const double *t = T2 + (size_t)r * oo;
+        const double *vd = Vt + ((size_t)a * nv + b) * oo;
+        const double *vx = Vt + ((size_t)b * nv + a) * oo;
+        for (int e = lane; e < oo; e += 32) {
+            const double tv = t[e];
+            double tau = tv;
+            if (T1) {
+                const int i = e / no, j = e - i * no;
+                tau += T1[a * no + i] * T1[b * no + j];
+            }
+            s[0] += tau * vd[e];
+            s[1] += tau * vx[e];
+            s[2] += tv * tv;
+        }
+    }
+    block_reduce_store<3>(s, ws);
+}
+
 __global__ void scale3_kernel(double *scal) {
     if (threadIdx.x == 0) {
         scal[0] *= 2.0;
@@ -265,6 +378,45 @@ __global__ void scale3_kernel(double *scal) {
     }
 }
 
+// Tt[a,b,ij] = 2 T[a,b,ij] - T[b,a,ij].  A CTA owns the PAIR of rows (a,b), (b,a) (each o^2
+// contiguous doubles): both are read once and both outputs written, 16 B per element of HBM
+// traffic -- the element-per-thread form reads every row twice (24 B).  swap_ij = 1 is
+// 2 T[a,b,i,j] - T[a,b,j,i]: a transpose inside one row, turned through shared memory.
+constexpr int kRowMax = 4096;      // o^2 <= 4096 (o <= 64) rows live in shared memory
+__global__ void __launch_bounds__(256)
+    tilde_pair_kernel(int no, int nv, const double *__restrict__ T2, double *__restrict__ Tt, int swap_ij) {
+    extern __shared__ double row_sh[];
+    const int oo = no * no;
+    if (swap_ij) {
+        for (long long ab = blockIdx.x; ab < (long long)nv * nv; ab += gridDim.x) {
+            const double *src = T2 + (size_t)ab * oo;
+            __syncthreads();
+            for (int e = threadIdx.x; e < oo; e += blockDim.x) row_sh[e] = src[e];
+            __syncthreads();
+            for (int e = threadIdx.x; e < oo; e += blockDim.x) {
+                const int i = e / no, j = e - i * no;
+                Tt[(size_t)ab * oo + e] = 2.0 * row_sh[e] - row_sh[j * no + i];
+            }
+        }
+        return;
+    }
+    const long long npair = (long long)nv * (nv + 1) / 2;
+    for (long long pr = blockIdx.x; pr < npair; pr += gridDim.x) {
+        // pair index -> (a <= b): row a of the upper triangle starts at a nv - a (a - 1) / 2
+        long long a = (long long)((2.0 * nv + 1.0 - sqrt((2.0 * nv + 1.0) * (2.0 * nv + 1.0) - 8.0 * (double)pr)) * 0.5);
+        while (a > 0 && a * nv - a * (a - 1) / 2 > pr) --a;
+        while ((a + 1) * nv - (a + 1) * a / 2 <= pr) ++a;
+        const long long b = a + (pr - (a * nv - a * (a - 1) / 2));
+        const size_t r1 = ((size_t)a * nv + b) * oo, r2 = ((size_t)b * nv + a) * oo;
+        for (int e = threadIdx.x; e < oo; e += blockDim.x) {
+            const double x = T2[r1 + e], y = T2[r2 + e];
+            Tt[r1 + e] = 2.0 * x - y;
+            if (a != b) Tt[r2 + e] = 2.0 * y - x;
+        }
+    }
+}
+
+// general-size fallback (o^2 > kRowMax): one element per thread
 __global__ void __launch_bounds__(256)
     tilde_kernel(int no, int nv, const double *__restrict__ T2, double *__restrict__ Tt, int swap_ij) {
     const size_t n = (size_t)nv * nv * no * no;
@@ -282,6 +434,39 @@ __global__ void __launch_bounds__(256)
             src = (b * nv + a) * oo + ij;
         }
         Tt[idx] = 2.0 * T2[idx] - T2[src];
+    }
+}
+
+// R[a,b,i,j] (+)= Ex[a,b,i,j] + Ex[b,a,j,i], again by row pairs: X = Ex[a,b,:], Y = Ex[b,a,:] are
+// staged in shared memory (their (ji) transposes are read from there), each is read from HBM once:
+// 8 B (Ex) + 8/16 B (R written / updated) per element.
+__global__ void __launch_bounds__(256)
+    sym_baji_pair_kernel(int no, int nv, const double *__restrict__ Ex, double *__restrict__ R, int accumulate) {
+    extern __shared__ double row_sh[];
+    const int oo = no * no;
+    double *X = row_sh, *Y = row_sh + oo;
+    const long long npair = (long long)nv * (nv + 1) / 2;
+    for (long long pr = blockIdx.x; pr < npair; pr += gridDim.x) {
+        long long a = (long long)((2.0 * nv + 1.0 - sqrt((2.0 * nv + 1.0) * (2.0 * nv + 1.0) - 8.0 * (double)pr)) * 0.5);
+        while (a > 0 && a * nv - a * (a - 1) / 2 > pr) --a;
+        while ((a + 1) * nv - (a + 1) * a / 2 <= pr) ++a;
+        const long long b = a + (pr - (a * nv - a * (a - 1) / 2));
+        const size_t r1 = ((size_t)a * nv + b) * oo, r2 = ((size_t)b * nv + a) * oo;
+        __syncthreads();
+        for (int e = threadIdx.x; e < oo; e += blockDim.x) {
+            X[e] = Ex[r1 + e];
+            Y[e] = Ex[r2 + e];
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < oo; e += blockDim.x) {
+            const int i = e / no, j = e - i * no, t = j * no + i;
+            const double v1 = X[e] + Y[t];
+            R[r1 + e] = accumulate ? R[r1 + e] + v1 : v1;
+            if (a != b) {
+                const double v2 = Y[e] + X[t];
+                R[r2 + e] = accumulate ? R[r2 + e] + v2 : v2;
+            }
+        }
     }
 }
 
@@ -536,8 +721,19 @@ extern "C" int pmb_axpby4(const int64_t ext[4], double alpha, const double *in, 
         if (ext[d] <= 0) return PMB_E_BADARG;
         n *= (size_t)ext[d];
     }
-    axpby4_kernel<<<grid_for(n, 256, 16 * kSmCount), 256, 0, (cudaStream_t)stream>>>(
-        make_str(ext, in_str, out_str), alpha, in, beta, out);
+    // a transpose (input unit-stride along one of the slow output dimensions): tiled kernel
+    int dt = -1;
+    if (out_str[3] == 1 && in_str[3] != 1 && ext[3] >= 16)
+        for (int d = 0; d < 3; ++d)
+            if (in_str[d] == 1 && ext[d] >= 16) dt = d;
+    if (dt >= 0) {
+        const size_t tiles = n / 1024 + 1;
+        axpby4_transpose_kernel<<<grid_for(tiles, 1, 32 * kSmCount), 256, 0, (cudaStream_t)stream>>>(
+            make_str(ext, in_str, out_str), dt, alpha, in, beta, out);
+    } else {
+        axpby4_kernel<<<grid_for(n, 256, 16 * kSmCount), 256, 0, (cudaStream_t)stream>>>(
+            make_str(ext, in_str, out_str), alpha, in, beta, out);
+    }
     count_launch();
     return cuda_status();
 }
@@ -590,7 +786,12 @@ extern "C" int pmb_energy_doubles(int no, int nv, int a_lo, int na, const double
     if (!ws || ws_bytes < pmb_reduce_workspace()) return PMB_E_WORKSPACE;
     const size_t n = (size_t)na * nv * no * no;
     const int blocks = grid_for(n, kReduceThreads, kReduceBlocks);
-    if (mp2_form)
+    const bool abij_storage = !mp2_form && v_str[1] == 1 && v_str[0] == no && v_str[3] == (int64_t)no * no &&
+                              v_str[2] == (int64_t)nv * no * no;
+    if (abij_storage)
+        energy_rows_kernel<<<blocks, kReduceThreads, 0, (cudaStream_t)stream>>>(no, nv, a_lo, na, T2, T1, V_ijab,
+                                                                                (double *)ws);
+    else if (mp2_form)
         energy_kernel<<<blocks, kReduceThreads, 0, (cudaStream_t)stream>>>(
             no, nv, a_lo, na, T2, T1, V_ijab, make_str(nullptr, v_str, nullptr), mp2_form, (double *)ws);
     else
@@ -609,7 +810,14 @@ extern "C" int pmb_energy_doubles(int no, int nv, int a_lo, int na, const double
 extern "C" int pmb_tilde(int no, int nv, const double *T2, double *Tt, int swap_ij, pmb_stream_t stream) {
     if (no <= 0 || nv <= 0 || !T2 || !Tt || T2 == Tt) return PMB_E_BADARG;
     const size_t n = (size_t)nv * nv * no * no;
-    tilde_kernel<<<grid_for(n, 256, 16 * kSmCount), 256, 0, (cudaStream_t)stream>>>(no, nv, T2, Tt, swap_ij);
+    if (no * no <= kRowMax) {
+        const long long rows = swap_ij ? (long long)nv * nv : (long long)nv * (nv + 1) / 2;
+        const unsigned blocks = (unsigned)(rows < 16LL * kSmCount ? rows : 16LL * kSmCount);
+        tilde_pair_kernel<<<blocks, 256, swap_ij ? sizeof(double) * no * no : 0, (cudaStream_t)stream>>>(
+            no, nv, T2, Tt, swap_ij);
+    } else {
+        tilde_kernel<<<grid_for(n, 256, 16 * kSmCount), 256, 0, (cudaStream_t)stream>>>(no, nv, T2, Tt, swap_ij);
+    }
     count_launch();
     return cuda_status();
 }
@@ -618,7 +826,14 @@ extern "C" int pmb_sym_baji(int no, int nv, const double *Ex, double *R, int acc
                             pmb_stream_t stream) {
     if (no <= 0 || nv <= 0 || !Ex || !R || Ex == R) return PMB_E_BADARG;
     const size_t n = (size_t)nv * nv * no * no;
-    sym_baji_kernel<<<grid_for(n, 256, 16 * kSmCount), 256, 0, (cudaStream_t)stream>>>(no, nv, Ex, R, accumulate);
+    if (2 * sizeof(double) * no * no <= 48 * 1024) {
+        const long long rows = (long long)nv * (nv + 1) / 2;
+        const unsigned blocks = (unsigned)(rows < 16LL * kSmCount ? rows : 16LL * kSmCount);
+        sym_baji_pair_kernel<<<blocks, 256, 2 * sizeof(double) * no * no, (cudaStream_t)stream>>>(no, nv, Ex, R,
+                                                                                               accumulate);
+    } else {
+        sym_baji_kernel<<<grid_for(n, 256, 16 * kSmCount), 256, 0, (cudaStream_t)stream>>>(no, nv, Ex, R, accumulate);
+    }
     count_launch();
     return cuda_status();
 }
@@ -727,7 +942,7 @@ extern "C" int pmb_gemv(const pmb_gemv_t *d, pmb_stream_t stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const long long bk0 = k.b_kstr[0] < 0 ? -k.b_kstr[0] : k.b_kstr[0];
     const long long bx0 = k.nx ? (k.b_xstr[0] < 0 ? -k.b_xstr[0] : k.b_xstr[0]) : (1LL << 62);
-    if (bk0 < bx0 && k.k_ext[0] >= 32)
+    if (bk0 < bx0 && k.k_ext[0] >= 16)
         gemv_kfast_kernel<<<(unsigned)((k.X + 7) / 8), 256, 0, s>>>(k);
     else
         gemv_xfast_kernel<<<(unsigned)((k.X + 255) / 256), 256, 0, s>>>(k);

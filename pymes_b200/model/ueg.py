@@ -268,14 +268,25 @@ class UEG:
             W1a = plain[0][2] if len(plain) == 1 else bk.lincomb([1.0] * len(plain), [t[2] for t in plain])
         if sym:
             W0s = sym[0][1] if len(sym) == 1 else bk.lincomb([1.0] * len(sym), [t[1] for t in sym])
-        out = {}
+        out, geom = {}, {}
         for key in keys:
             lo = [0 if ch in OCCUPIED else no for ch in key]
             ext = [no if ch in OCCUPIED else nP - no for ch in key]
             for dim, (r_lo, r_n) in (ranges or {}).get(key, {}).items():
                 lo[dim], ext[dim] = int(r_lo), int(r_n)
-            make = self.virtual_block if key in virtual else self.build_block
-            out[key] = make(tuple(lo), tuple(ext), W0a=W0a, W1a=W1a, W0s=W0s)
+            geom[key] = (tuple(lo), tuple(ext))
+        # V_iabc and V_aibc meet the same tau in every sweep: allocated back to back they are one
+        # operand of one launch (solver.ccsd.pair_with_tau)
+        pre = {}
+        if "iabc" in geom and "aibc" in geom and not {"iabc", "aibc"} & set(virtual) and \
+                int(np.prod(geom["iabc"][1])) == int(np.prod(geom["aibc"][1])):
+            pre["iabc"], pre["aibc"] = bk.empty_stacked(geom["iabc"][1], geom["aibc"][1])
+        for key in keys:
+            lo, ext = geom[key]
+            if key in virtual:
+                out[key] = self.virtual_block(lo, ext, W0a=W0a, W1a=W1a, W0s=W0s)
+            else:
+                out[key] = self.build_block(lo, ext, W0a=W0a, W1a=W1a, W0s=W0s, out=pre.get(key))
         return out
 
     # ------------------------------------------------- 3-body mean-field parts

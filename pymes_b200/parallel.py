@@ -289,11 +289,8 @@ class ShardedCCSD(ccsd.CCSD):
             T1a = sh.rows(T1, 0)
             # W1[k,b,i,j] for b in A from the local V_iabc[:,A], gathered along b
             no = T1.shape[1]
-            w1, W2 = bk.empty(sh.na, no, no, no), bk.empty(sh.na, no, no, no)
-            with bk.side_by_side() as side:   # two short grids fill each other's last wave
-                ct("kbij", [(1.0, "kbcd", dV["iabc"], "cdij", tau)], out=w1.permute(1, 0, 2, 3))
-                side(lambda: ct("alij", [(1.0, "alcd", dV["aibc"], "cdij", tau)], out=W2))
-            W1 = sh.gather_dim1(w1)
+            W1l, W2 = ccsd.pair_with_tau(dV["iabc"], dV["aibc"], tau, no)     # [k, b in A, i, j], [a in A, l, i, j]
+            W1 = sh.gather_dim1(bk.copy(W1l.permute(1, 0, 2, 3)))             # rows first for the gather (o^3 v / N numbers)
             ct("abij", [(-1.0, "ak", T1a, "kbij", W1)], out=R, beta=1.0)
             # o^4 output, contraction over (c,d): each rank sums its c in A, then all-reduce
             W3 = sh.all_reduce(ct("klij", [(1.0, "klcd", sh.rows(dV["ijab"], 2), "cdij", sh.rows(tau, 0))]))
@@ -333,6 +330,7 @@ class ShardedCCSD(ccsd.CCSD):
         st["scal"] = bk.zeros(8)
         st["e_mp2"] = e_mp2
         st["iteration"] = 0
+        st["V_ijab_e"] = ccsd.energy_layout(st["dV"]["ijab"])
         return e_mp2
 
     def sweep(self):
@@ -362,7 +360,7 @@ class ShardedCCSD(ccsd.CCSD):
         if self.is_diis:
             T1, T2l = self.mixer.mix([dT1, dT2], [T1, T2l], sharded=[False, True])
         T2 = sh.gather_async(T2l)                   # ... while the energy of the local rows is summed
-        bk.energy_doubles(T2l, dV["ijab"], scal, T1=T1, rows=rows)
+        bk.energy_doubles(T2l, st["V_ijab_e"], scal, T1=T1, rows=rows)
         T2 = T2.wait_result()
         st["T1"], st["T2"] = T1, T2
         self.comm.all_reduce_sum(scal[0:4])

@@ -161,6 +161,36 @@ def singles_residual(no, fock_dressed, T1, T2, dV):
     return R1
 
 
+def energy_layout(V_ijab):
+    """V_ijab re-stored as [a,b,i,j] and handed back as an (i,j,a,b)-indexed VIEW of that storage.
+    The block is static, the energy is evaluated every sweep: with this layout ``pmb_energy_doubles``
+    streams row (a,b) for the direct and row (b,a) for the exchange term next to the same row of T2
+    (coalesced, 24 B per amplitude) instead of gathering V[i,j,.,.] at stride v^2."""
+    return bk.copy(V_ijab.permute(2, 3, 0, 1)).permute(2, 3, 0, 1)
+
+
+def pair_with_tau(V_iabc, V_aibc, tau, no):
+    """(W1, W2) = (V_iabc.tau [k,b,i,j], V_aibc.tau [a,l,i,j]) with V_iabc = [o, nb, v, v] and V_aibc =
+    [nb, o, v, v] (nb = v, or the local rows of a sharded run).  When the two blocks were allocated
+    back to back (``UEG.eval_2b_blocks`` / ``synthetic.tc_blocks`` do that) they are ONE operand of
+    2.o.nb rows: a single launch whose sparse last wave is split over k, instead of two grids of
+    4.2 waves each (N = 1) or of 78 tiles on 148 SMs each (N = 8).  Otherwise two launches side by
+    side on two streams."""
+    ct = bk.contract_terms
+    nv = tau.shape[0]
+    nb = V_iabc.shape[1]
+    st = bk.stacked_rows(V_iabc, V_aibc, (nv, nv))
+    if st is not None:
+        W = bk.empty(2, no * nb, no, no)
+        ct("grij", [(1.0, "grcd", st, "cdij", tau)], out=W)
+        return W[0].view(no, nb, no, no), W[1].view(nb, no, no, no)
+    W1, W2 = bk.empty(no, nb, no, no), bk.empty(nb, no, no, no)
+    with bk.side_by_side() as side:
+        ct("kbij", [(1.0, "kbcd", V_iabc, "cdij", tau)], out=W1)
+        side(lambda: ct("alij", [(1.0, "alcd", V_aibc, "cdij", tau)], out=W2))
+    return W1, W2
+
+
 def tau_ladder(T1, dV):
     """Returns the ``pp_ladder(T2, R)`` callback described in the module docstring."""
     def apply(T2, R):
@@ -170,10 +200,7 @@ def tau_ladder(T1, dV):
         with bk.timed("pp_ladder"):
             ct("abij", [(1.0, "abcd", dV["abcd"], "cdij", tau)], out=R, beta=1.0)
         nv, no = T1.shape
-        W1, W2 = bk.empty(no, nv, no, no), bk.empty(nv, no, no, no)
-        with bk.side_by_side() as side:       # two 4-wave grids fill each other's last wave
-            ct("kbij", [(1.0, "kbcd", dV["iabc"], "cdij", tau)], out=W1)
-            side(lambda: ct("alij", [(1.0, "alcd", dV["aibc"], "cdij", tau)], out=W2))
+        W1, W2 = pair_with_tau(dV["iabc"], dV["aibc"], tau, no)
         ct("abij", [(-1.0, "ak", T1, "kbij", W1)], out=R, beta=1.0)
         W3 = ct("klij", [(1.0, "klcd", dV["ijab"], "cdij", tau)])
         ct("alij", [(-1.0, "ak", T1, "klij", W3)], out=W2, beta=1.0)
@@ -341,6 +368,7 @@ class CCSD(ccd.CCD):
         st["scal"] = bk.zeros(8)
         st["e_mp2"] = e_mp2
         st["iteration"] = 0
+        st["V_ijab_e"] = energy_layout(st["dV"]["ijab"])
         return e_mp2
 
     def sweep(self):
@@ -373,7 +401,7 @@ class CCSD(ccd.CCD):
         if self.is_diis:
             T1, T2 = self.mixer.mix([dT1, dT2], [T1, T2])
         st["T1"], st["T2"] = T1, T2
-        bk.energy_doubles(T2, dV["ijab"], scal, T1=T1)
+        bk.energy_doubles(T2, st["V_ijab_e"], scal, T1=T1)
         bk.contract_terms("", [(2.0, "ia", fock[:no, no:], "ai", T1)], out=scal[4])
         s = scal.cpu().numpy()
         return float(s[4]), float(s[0]), float(s[1]), float(np.sqrt(s[2])), float(np.sqrt(s[3]))

@@ -99,12 +99,22 @@ def tc_blocks(no, nv, keys, seed=0, eps=None, ranges=None, device=False):
     ``{key: {dim: (lo, n)}}`` restricts a dimension to absolute orbital indices (a rank's rows).
     ``device=True``: CUDA tensors written by ``pmb_synth_block`` (bit-identical values)."""
     from ..integral.partition import OCCUPIED
-    make = tc_block_device if device else tc_block
-    out = {}
+    out, geom = {}, {}
     for key in keys:
         lo = [0 if ch in OCCUPIED else no for ch in key]
         ext = [no if ch in OCCUPIED else nv for ch in key]
         for dim, (r_lo, r_n) in (ranges or {}).get(key, {}).items():
             lo[dim], ext[dim] = int(r_lo), int(r_n)
-        out[key] = make(no + nv, lo, ext, seed, eps)
+        geom[key] = (lo, ext)
+    pre = {}
+    if device and "iabc" in geom and "aibc" in geom and \
+            int(np.prod(geom["iabc"][1])) == int(np.prod(geom["aibc"][1])):
+        from .. import backend as bk          # back to back: one operand for solver.ccsd.pair_with_tau
+        pre["iabc"], pre["aibc"] = bk.empty_stacked(geom["iabc"][1], geom["aibc"][1])
+    for key in keys:
+        lo, ext = geom[key]
+        if device:
+            out[key] = tc_block_device(no + nv, lo, ext, seed, eps, out=pre.get(key))
+        else:
+            out[key] = tc_block(no + nv, lo, ext, seed, eps)
     return out

@@ -57,6 +57,7 @@ def test_gemv_medium_both_mappings(monkeypatch):
     """pmb_gemv at o=9, v=83 (ragged against the 32-lane / 8-row unrolling) vs numpy."""
     from pymes_b200 import backend as bk
     monkeypatch.setattr(bk, "GEMV_MIN_OUTPUTS", 0)
+    monkeypatch.setattr(bk, "GEMV_MIN_WARP_OUTPUTS", 0)
     rng = np.random.default_rng(8)
     no, nv = 9, 83
     t1 = rng.standard_normal((nv, no))
@@ -775,3 +776,50 @@ def test_synth_block_large_rows_statistics():
     other = synthetic.tc_block_device(n, (no + 100, no + 7, no + 3, no + 20), (5, 1, 7, 6), seed=0, eps=1.0)
     assert torch.equal(other.permute(1, 0, 3, 2), blk[:, 100:105, 20:26, 3:10])
     assert abs(float(blk.mean())) < 1e-3 and abs(float(blk.std()) - 1.0) < 1e-3 and float(blk.abs().max()) < 4.5
+
+
+@pytest.mark.parametrize("no,nv", [(6, 17), (27, 40), (50, 21)])
+def test_elementwise_kernels_pair_rows_and_streams(no, nv):
+    """Round-2 forms of the HBM-bound kernels: T-tilde and Ex + Ex^{baji} by row PAIRS (a,b),(b,a),
+    the energy streaming an [a,b,i,j]-stored V_ijab (whole tensor and a row block), the strided copy
+    with its 32-bit inner index split -- all against numpy, bit for bit where no sum is involved.
+    o = 50 exceeds the shared-memory row buffers of sym_baji: the element-per-thread kernels run."""
+    from pymes_b200 import backend as bk
+    from pymes_b200.solver import ccsd
+    rng = np.random.default_rng(no * 100 + nv)
+    T = rng.standard_normal((nv, nv, no, no))
+    R = rng.standard_normal((nv, nv, no, no))
+    V = rng.standard_normal((no, no, nv, nv))
+    T1 = rng.standard_normal((nv, no))
+    Td = bk.asdev(T)
+    assert _rel(bk.tilde(Td).cpu().numpy(), 2 * T - T.transpose(1, 0, 2, 3)) == 0
+    assert _rel(bk.tilde(Td, swap_ij=True).cpu().numpy(), 2 * T - T.transpose(0, 1, 3, 2)) == 0
+    Rd = bk.asdev(R.copy())
+    bk.sym_baji(Td, Rd, accumulate=True)
+    assert _rel(Rd.cpu().numpy(), R + (T + T.transpose(1, 0, 3, 2))) < 1e-15
+    assert _rel(bk.sym_baji(Td).cpu().numpy(), T + T.transpose(1, 0, 3, 2)) == 0
+    Ve = ccsd.energy_layout(bk.asdev(V))
+    assert tuple(Ve.shape) == (no, no, nv, nv) and Ve.stride(1) == 1 and torch.equal(Ve, bk.asdev(V))
+    tau = T + np.einsum("ai,bj->abij", T1, T1)
+    want = (2 * np.einsum("abij,ijab->", tau, V), -np.einsum("abij,ijba->", tau, V), np.sum(T * T))
+    for Vdev in (Ve, bk.asdev(V)):                       # streamed rows / tiled gather: same sums
+        scal = bk.zeros(8)
+        bk.energy_doubles(Td, Vdev, scal, T1=bk.asdev(T1))
+        s = scal.cpu().numpy()
+        assert np.allclose(s[:3], want, rtol=1e-12, atol=1e-10)
+    lo, na = nv // 3, nv - nv // 3 - 2
+    scal = bk.zeros(8)
+    bk.energy_doubles(bk.asdev(T[lo:lo + na].copy()), Ve, scal, T1=bk.asdev(T1), rows=(lo, na))
+    part = (2 * np.einsum("abij,ijab->", tau[lo:lo + na], V[:, :, lo:lo + na]),
+            -np.einsum("abij,ijba->", tau[lo:lo + na], V[:, :, :, lo:lo + na]), np.sum(T[lo:lo + na] ** 2))
+    assert np.allclose(scal.cpu().numpy()[:3], part, rtol=1e-12, atol=1e-10)
+    # strided copies: permuted source, strided destination, accumulation
+    src = bk.asdev(V)
+    assert _rel(bk.axpby(2.0, src.permute(2, 3, 0, 1)).cpu().numpy(), 2 * V.transpose(2, 3, 0, 1)) == 0
+    big = bk.asdev(rng.standard_normal((nv + 3, no + 2, nv + 1, no + 5)))
+    view = big[2:2 + nv, 1:1 + no, :nv, 3:3 + no]
+    got = bk.axpby(-0.5, view.permute(0, 2, 1, 3), 1.0, Rd.clone())
+    assert _rel(got.cpu().numpy(), Rd.cpu().numpy() - 0.5 * view.permute(0, 2, 1, 3).cpu().numpy()) < 1e-15
+    out = bk.zeros(nv + 3, no + 2, nv + 1, no + 5)
+    bk.axpby(1.0, Td.permute(0, 2, 1, 3), 0.0, out[2:2 + nv, 1:1 + no, :nv, 3:3 + no])
+    assert torch.equal(out[2:2 + nv, 1:1 + no, :nv, 3:3 + no], Td.permute(0, 2, 1, 3)) and float(out[0].abs().max()) == 0

@@ -386,6 +386,7 @@ def test_matrix_vector_contractions_go_to_gemv(cpu_abi, monkeypatch):
     from pymes_b200 import backend as bk
     monkeypatch.setattr(bk, "GEMV_MIN_ELEMENTS", 0)
     monkeypatch.setattr(bk, "GEMV_MIN_OUTPUTS", 0)
+    monkeypatch.setattr(bk, "GEMV_MIN_WARP_OUTPUTS", 0)
     rng = np.random.default_rng(5)
     no, nv = 3, 37
     t1 = rng.standard_normal((nv, no))

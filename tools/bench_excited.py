@@ -202,10 +202,11 @@ def main(argv):
         if rank == 0:
             print(*a, file=sys.stderr, flush=True)
 
+    bench.claim_stdout()          # libraries print to stdout too (NCCL's version banner): keep it for the JSON
     out = (run_feast if mode == "feast" else run_davidson)(argv[1:], comm, log)
     out["n_gpus"] = world
     if rank == 0:
-        print(json.dumps(out))
+        bench.emit(out)
     if world > 1 and dist.is_initialized():
         dist.destroy_process_group()
     return out

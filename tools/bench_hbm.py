@@ -1,8 +1,9 @@
 """Achieved HBM bandwidth of the HBM-bound kernels (CUDA events, inputs >> L2).
 Writes gpurun_out/hbm_kernels.json.  ALGORITHMIC bytes per element:
-update 32 B (read R, read T, write T, write dT), energy 16 B (T2 + V_ijab; the exchange read
-hits the same lines), DIIS dots 8(m+1) B, DIIS combine 8(m+1) B, UEG build 8 B per stored element,
-tilde 16 B (+ the permuted re-read), sym_baji 24 B."""
+update 32 B (read R, read T, write T, write dT), energy 24 B (the row of T2 and the rows (a,b), (b,a)
+of the [a,b,i,j]-stored V_ijab; 16 B if the exchange rows were paired), DIIS dots 8(m+1) B, DIIS combine 8(m+1) B, UEG build 8 B per stored element,
+tilde 16 B (row pairs: every row read once), sym_baji 24 B (Ex once, R read + written), strided
+copy / transpose 16 B."""
 import json
 import os
 import sys
@@ -19,7 +20,11 @@ n = nv * nv * no * no
 res = {"shape": "o=27 v=314 (%.2f GB per T2-sized tensor)" % (n * 8 / 1e9), "peak_gbs": PEAK}
 
 
-def timeit(fn, reps=5):
+REPS = int(os.environ.get("HBM_REPS", "5"))       # HBM_REPS=1 under ncu
+
+
+def timeit(fn, reps=None):
+    reps = REPS if reps is None else reps
     fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -45,7 +50,10 @@ ei = torch.linspace(-2, -1, no, dtype=torch.float64, device="cuda")
 ea = torch.linspace(1, 3, nv, dtype=torch.float64, device="cuda")
 scal = bk.zeros(8)
 rec("update_doubles", timeit(lambda: bk.update_doubles(ei, ea, 0.0, 1.0, R, T, scal[3:4])), 32 * n)
-rec("energy_doubles", timeit(lambda: bk.energy_doubles(T, V, scal)), 16 * n)
+from pymes_b200.solver import ccsd
+Ve = ccsd.energy_layout(V)       # what CCSD.sweep hands over: V_ijab stored as [a,b,i,j]
+rec("energy_doubles", timeit(lambda: bk.energy_doubles(T, Ve, scal)), 24 * n)      # T2 row + V rows (a,b) and (b,a)
+rec("energy_doubles_ijab_storage", timeit(lambda: bk.energy_doubles(T, V, scal)), 16 * n)
 rec("tilde", timeit(lambda: bk.tilde(T)), 16 * n)
 rec("sym_baji", timeit(lambda: bk.sym_baji(T, R, accumulate=True)), 24 * n)
 xs = [torch.randn_like(T) for _ in range(6)]
