@@ -145,10 +145,107 @@ class UEG:
         desc = self._descriptor(u_table)
         return self._umat_device(desc, q_int, lattice_cutoff).cpu().numpy()
 
+    # Correlators whose value at every lattice point is insensitive to the last bits of the
+    # argument (continuous there, or switched with a guard band like trunc's 1 + 1e-5): for these
+    # the device kernels may look the correlator up in a table over the integer |k|^2.
+    _TABLE_SAFE = ("trunc", "coulomb", "smooth")
+
+    def _wants_exact_arguments(self, correlator):
+        """Must the correlator be evaluated at the reference's own floating-point arguments?
+        ``self.exact_correlator_arguments`` = True / False forces it; None (default) decides by the
+        correlator: yukawa, stg, yukawa_coulomb, gaskell, gaskell_modified and user callables compare
+        k^2 with a cutoff without a guard band, and when that cutoff is exactly the squared length of
+        a lattice shell the reference's answer depends on the rounding of its k-vector differences
+        (e.g. 3x - 2x against 2x - x), pair by pair and lattice term by lattice term."""
+        flag = getattr(self, "exact_correlator_arguments", None)
+        if flag is not None:
+            return bool(flag)
+        func = getattr(correlator, "__func__", None)
+        return not (getattr(correlator, "__self__", None) is self and func is not None
+                    and func.__name__ in self._TABLE_SAFE)
+
+    def _pair_tables_exact(self, mode, correlator, lattice_cutoff):
+        """W0 / W1 of one branch of ueg.py:411-504 with every correlator argument formed exactly as
+        the reference forms it (same numpy calls, same order, one (p, r) pair at a time) -- O(nP^2 n_occ)
+        host work on the nP x nP tables; the dense block is still written by the device."""
+        from functools import partial
+        einsum = partial(np.einsum, optimize=True)                          # ueg.py:10
+        nP, nocc = self.n_orb, self.n_ele // 2
+        kp, kint = self.k_float(), self.k_int().astype(np.int64)
+        occ = np.array([kp[i] for i in range(nocc)])
+        omega, n_ele = self.Omega, self.n_ele
+        lattice = np.array([[i, j, k] for i in range(-lattice_cutoff, lattice_cutoff + 1)
+                            for j in range(-lattice_cutoff, lattice_cutoff + 1)
+                            for k in range(-lattice_cutoff, lattice_cutoff + 1)])
+        umat_cache = {}
+
+        def u_mat(q_int, k):                                                # ueg.py:581-596
+            key = tuple(int(x) for x in q_int)
+            if key not in umat_cache:
+                k1 = 2 * np.pi * lattice / self.L
+                k2 = k - k1
+                res = einsum("ni,ni->n", k1, k2) * correlator(einsum("ni,ni->n", k1, k1)) \
+                    * correlator(einsum("ni,ni->n", k2, k2))
+                umat_cache[key] = einsum("n->", res) / omega
+            return umat_cache[key]
+
+        def ex3(p_vec, kvec):                                               # ueg.py:518-542
+            pv = p_vec - occ
+            res = einsum("ni,i->n", pv, kvec) * correlator(einsum("i,i->", kvec, kvec)) \
+                * correlator(einsum("ni,ni->n", pv, pv))
+            return einsum("n->", res) / omega
+
+        def pk(p_vec, kvec):                                                # ueg.py:544-573
+            v1, v2 = p_vec - kvec - occ, p_vec - occ
+            res = einsum("ni,ni->n", v1, v2) * correlator(einsum("ni,ni->n", v1, v1)) \
+                * correlator(einsum("ni,ni->n", v2, v2))
+            return einsum("n->", res) / omega
+
+        W0, W1 = np.zeros((nP, nP)), np.zeros((nP, nP))
+        need_umat = mode in ("only_2b", "only_hermi_2b")
+        for p in range(nP):
+            for r in range(nP):
+                d = kp[r] - kp[p]
+                d2 = d.dot(d)
+                nz = np.abs(d2) > 0.
+                um = u_mat(kint[r] - kint[p], d) if need_umat else 0.
+                if mode == "rpa":
+                    if nz:
+                        W0[p, r] = (-n_ele * d2 * correlator(d2) ** 2 / omega) / omega
+                elif mode in ("only_2b", "only_hermi_2b"):
+                    W0[p, r] = (4. * np.pi / d2 + um + d2 * correlator(d2)) / omega if nz else um / omega
+                    if nz and mode == "only_2b":
+                        W1[p, r] = -correlator(d2) / omega
+                elif mode == "only_non_hermi_2b":
+                    if nz:
+                        W0[p, r] = (4. * np.pi / d2) / omega
+                        W1[p, r] = -correlator(d2) / omega
+                elif mode == "effect_2b":
+                    if nz:
+                        w = -n_ele * d2 * correlator(d2) ** 2 / omega + 2. * ex3(kp[r], d) - 2. * ex3(kp[p], d) \
+                            + 2. * pk(kp[r], d)
+                    else:
+                        w = 2. * pk(kp[r], d)
+                    W0[p, r] = w / omega
+                elif mode == "exchange_1":
+                    if nz:
+                        W0[p, r] = 2. * ex3(kp[r], d) / omega
+                elif mode == "exchange_2":
+                    if nz:
+                        W0[p, r] = -2. * ex3(kp[p], d) / omega
+                elif mode == "exchange_3":
+                    W0[p, r] = 2. * pk(kp[r], d) / omega
+                else:
+                    raise ValueError(mode)
+        return bk.asdev(W0.reshape(-1)), bk.asdev(W1.reshape(-1))
+
     def pair_tables(self, mode, correlator=None, lattice_cutoff=30):
-        """(W0, W1, descriptor keep-alives) for one branch of ueg.py:411-504."""
+        """(W0, W1) for one branch of ueg.py:411-504: nP x nP tables of the (p, r)-only factors."""
         lib = _lib.load()
         nP = self.n_orb
+        if mode != "coulomb" and correlator is not None and self._wants_exact_arguments(correlator):
+            self.correlator = correlator
+            return self._pair_tables_exact(mode, correlator, lattice_cutoff)
         u_table = None
         if mode != "coulomb":
             if correlator is None:
@@ -294,30 +391,44 @@ class UEG:
         return self.k_float()[: self.n_ele // 2]
 
     def triple_contractions_in_3_body(self):
-        """Scalar mean-field energy of the 3-body operator (ueg.py:598-630)."""
+        """Scalar mean-field energy of the 3-body operator (ueg.py:598-630).  The correlator (a host
+        callable) is evaluated on the |k_i - k_j|^2 table; the contractions run on the device
+        (``pmb_bdot`` / ``pmb_dots``: batch-index products, not matrix products)."""
         ki = self._occupied_k()
         d = ki[:, None, :] - ki[None, :, :]
         d2 = np.einsum("pqi,pqi->pq", d, d)
-        u = self.correlator(d2.copy())
-        direct = np.sum(u ** 2 * d2) * self.n_ele / 2 / self.Omega ** 2 * 2
-        dots = np.einsum("poi,pqi->pqo", d, d)
-        exch = -2 * 2 * np.einsum("pqo,pq,po->", dots, u, u) / 2. / self.Omega ** 2
+        u = bk.asdev(self.correlator(d2.copy()))
+        dd, d2d = bk.asdev(d), bk.asdev(d2)
+        u2 = bk.bdot("pq,pq->pq", u, u)
+        direct = float(bk.dots([u2.reshape(-1)], d2d.reshape(-1)).item()) * self.n_ele / 2 / self.Omega ** 2 * 2
+        # sum_{pqo} (d_po . d_pq) u_pq u_po = sum_p | sum_q u_pq d_pq |^2
+        Y = bk.bdot("pqi,pq->pi", dd, u)
+        exch = -2 * 2 * float(bk.dots([Y.reshape(-1)], Y.reshape(-1)).item()) / 2. / self.Omega ** 2
         return direct + exch
 
     def double_contractions_in_3_body(self):
-        """One-body energies from doubly contracted 3-body terms (ueg.py:632-733)."""
+        """One-body energies from doubly contracted 3-body terms (ueg.py:632-733), contractions on the
+        device as above; returns a numpy array like the reference."""
         kp, ki = self.k_float(), self._occupied_k()
         dpi = kp[:, None, :] - ki[None, :, :]                    # p - i
         dpi2 = np.einsum("pij,pij->pi", dpi, dpi)
-        upi = self.correlator(dpi2.copy())
-        perl = 2.0 * self.n_ele / self.Omega ** 2 / 2 * np.sum(upi ** 2 * dpi2, axis=1)
-        wave = -np.einsum("pik,pjk,pi,pj->p", dpi, dpi, upi, upi) * 2 / self.Omega ** 2 / 2
+        upi = bk.asdev(self.correlator(dpi2.copy()))
         dij = ki[:, None, :] - ki[None, :, :]
         dij2 = np.einsum("ijk,ijk->ij", dij, dij)
-        uij = self.correlator(dij2.copy())
-        shield = np.ones(len(kp)) * np.sum(uij ** 2 * dij2) * 2 / 2 / self.Omega ** 2
-        frog = -np.einsum("ijk,pik,ij,pi->p", dij, -dpi, uij, upi) * 4 / self.Omega ** 2 / 2
-        return perl + wave + shield + frog
+        uij = bk.asdev(self.correlator(dij2.copy()))
+        dpi_d, dpi2_d, dij_d, dij2_d = bk.asdev(dpi), bk.asdev(dpi2), bk.asdev(dij), bk.asdev(dij2)
+        om2 = self.Omega ** 2
+        upi2 = bk.bdot("pi,pi->pi", upi, upi)
+        perl = bk.bdot("pi,pi->p", upi2, dpi2_d, alpha=2.0 * self.n_ele / om2 / 2)
+        Y = bk.bdot("pik,pi->pk", dpi_d, upi)                    # sum_i u_pi (p - i)
+        wave = bk.bdot("pk,pk->p", Y, Y, alpha=-2.0 / om2 / 2)
+        uij2 = bk.bdot("ij,ij->ij", uij, uij)
+        shield = float(bk.dots([uij2.reshape(-1)], dij2_d.reshape(-1)).item()) * 2 / 2 / om2
+        Z = bk.bdot("ijk,ij->ik", dij_d, uij)                    # sum_j u_ij (i - j)
+        W = bk.bdot("pik,pi->pik", dpi_d, upi)
+        frog = bk.bdot("pik,ik->p", W, Z, alpha=4.0 / om2 / 2)   # -(...)(-dpi) of ueg.py:725-731
+        out = bk.lincomb([1.0, 1.0, 1.0], [perl, wave, frog])
+        return bk.tonumpy(out) + shield
 
     # ------------------------------------------------------------ correlators
     # u(k^2); scalar or array argument.  ueg.py:740-956
@@ -379,18 +490,21 @@ class UEG:
         kf = self.basis_fns[(self.n_ele // 2) * 2].kp
         kf2 = kf.dot(kf)
         kc2 = 4. * kf2 if self.k_cutoff is None else self.k_cutoff ** 2 * kf2
+        # the reference branches on isinstance(kSquare, np.ndarray): a 0-d ARRAY (what
+        # einsum(..., optimize=True) returns for "i,i->") takes the array branch, whose cutoff test
+        # is `>` while the scalar branch's is `<` -- they differ exactly at k^2 == cutoff
+        if not isinstance(kSquare, np.ndarray):
+            return -(mu / kSquare) if (1e-12 < kSquare < kc2) else -0.0
         k2 = np.asarray(kSquare, dtype=np.float64)
         res = np.divide(mu, k2, out=np.zeros_like(k2), where=(k2 > 1e-12))
-        if k2.ndim == 0:
-            return -float(res) if (1e-12 < k2 < kc2) else -0.0
         res[k2 > kc2] = 0.
         return -res
 
     def gaskell_modified(self, kSquare, multiply_by_k_square=False):
         kc2 = 2 if self.k_cutoff is None else (self.k_cutoff * (2 * np.pi / self.L)) ** 2
+        if not isinstance(kSquare, np.ndarray):          # same dispatch as the reference (see gaskell)
+            return -0.0 if (1e-12 < kSquare < kc2) else -(4 * np.pi / kSquare ** 2)
         k2 = np.asarray(kSquare, dtype=np.float64)
-        if k2.ndim == 0:
-            return -0.0 if (1e-12 < k2 < kc2) else -(4 * np.pi / float(k2) ** 2)
         return -np.divide(4 * np.pi, k2 ** 2, out=np.zeros_like(k2), where=(k2 >= kc2))
 
 

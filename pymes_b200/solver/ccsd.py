@@ -5,7 +5,8 @@ constructor, ``solve``, ``get_T1_dressed_fock``, ``get_T1_dressed_V``,
 ``get_singles_residual``, ``get_doubles_residual``, ``get_energy``, the returned
 dict keys, ``self.t_T_ai`` / ``self.t_T_abij`` and the log lines.
 
-Design differences (results agree to round-off, see tests/test_ccsd_gpu.py):
+Design differences (results agree to round-off: tests/test_gpu_parity.py, lock-step with the oracle
+sweep by sweep on LiH, LiH-TC, HF/aug-cc-pVDZ, TC-UEG 14e and 54e, synthetic o=10 v=60):
 
 * Every dressing product (ccsd.py:257-286, 322-419) is a row of a term table that
   is evaluated pairwise on the DMMA engine (``backend.einsum``); sources are always

@@ -823,3 +823,16 @@ def test_elementwise_kernels_pair_rows_and_streams(no, nv):
     out = bk.zeros(nv + 3, no + 2, nv + 1, no + 5)
     bk.axpby(1.0, Td.permute(0, 2, 1, 3), 0.0, out[2:2 + nv, 1:1 + no, :nv, 3:3 + no])
     assert torch.equal(out[2:2 + nv, 1:1 + no, :nv, 3:3 + no], Td.permute(0, 2, 1, 3)) and float(out[0].abs().max()) == 0
+
+
+# --------------------------------------------------------------------------
+# eval_2b_integrals: every branch and every correlator against the reference's triple loop
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("flag", host.UEG_FLAGS)
+def test_ueg_remaining_branches_match_reference(flag):
+    host.test_ueg_remaining_branches_match_reference(None, flag)
+
+
+@pytest.mark.parametrize("name,gamma,k_cutoff", host.UEG_CORRELATORS)
+def test_ueg_every_correlator_matches_reference(name, gamma, k_cutoff):
+    host.test_ueg_every_correlator_matches_reference(None, name, gamma, k_cutoff)

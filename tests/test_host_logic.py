@@ -866,18 +866,13 @@ def test_ueg_remaining_branches_match_reference(cpu_abi, flag):
         assert np.abs(_n(blk) - ref[2:5, :, 11:15, :]).max() <= 1e-11 * scale
 
 
-# KNOWN DEVIATION ("correlators with a hard cutoff on a lattice shell").  These
-# correlators switch on/off at k^2 == threshold with a strict comparison and NO guard band, and with
-# these parameters the threshold is exactly the squared length of a lattice shell ((2 pi/L)^2 for
-# k_cutoff = 1; 4 k_F^2 = 8 (2 pi/L)^2 for gaskell at 14 electrons).  Which side the reference takes
-# is decided by the rounding noise of ITS floating-point k-vector differences (e.g. 3x - 2x vs
-# 2x - x), pair by pair and lattice term by lattice term; the device build evaluates the correlator
-# once per integer |k|^2, so every point of the shell falls on one side.  Affected: u_mat(q) of
-# `only_2b` for yukawa / stg (a few lattice terms flip: 1e-3 relative), the pair factor of
-# `effect_2b` for gaskell (12 elements with |k_r - k_p|^2 on the shell).  `trunc` -- the correlator of
-# every TC workload here -- carries a guard band (ueg.py:793: 1 + 1e-5) and is exact.
-KNIFE_EDGE = {("yukawa", 0.7, 1.0, "is_only_2b"): 2e-3, ("stg", 1.3, 1.0, "is_only_2b"): 5e-4,
-              ("gaskell", None, None, "is_effect_2b"): 0.2, ("gaskell", 0.9, 2.0, "is_effect_2b"): 0.2}
+# Correlators that compare k^2 with a cutoff WITHOUT a guard band (yukawa / stg / yukawa_coulomb with
+# k_cutoff, gaskell, gaskell_modified): when the cutoff is exactly the squared length of a lattice
+# shell ((2 pi/L)^2 for k_cutoff = 1; 4 k_F^2 = 8 (2 pi/L)^2 for gaskell at 14 electrons) the reference's
+# answer is decided by the rounding of ITS k-vector differences.  For these the pair tables are
+# formed with the reference's own floating-point arguments (UEG._pair_tables_exact); a table over
+# the integer |k|^2 -- what `trunc` (guard band 1 + 1e-5, ueg.py:793) may use -- would put a whole
+# shell on one side (seen before the exact path existed: 1e-3 relative in u_mat for yukawa / stg).
 
 
 @pytest.mark.parametrize("name,gamma,k_cutoff", UEG_CORRELATORS)
@@ -896,8 +891,7 @@ def test_ueg_every_correlator_matches_reference(cpu_abi, name, gamma, k_cutoff):
         np.testing.assert_array_equal(m.k_int(), g["small_kint"])
         V = m.eval_2b_integrals(correlator=getattr(m, name), sp=0, **{flag: True})
         ref = _dense(g[tag + "_" + flag + "_idx"], g[tag + "_" + flag + "_val"], nP)
-        tol = KNIFE_EDGE.get((name, gamma, k_cutoff, flag), 1e-10)
-        assert np.abs(V - ref).max() <= tol * max(np.abs(ref).max(), 1e-300), flag
+        assert np.abs(V - ref).max() <= 1e-10 * max(np.abs(ref).max(), 1e-300), flag
     ga, kc = float(g[tag + "_gamma_after"]), float(g[tag + "_kc_after"])
     assert (m.gamma is None and np.isnan(ga)) or m.gamma == ga
     assert (m.k_cutoff is None and np.isnan(kc)) or m.k_cutoff == kc
