@@ -364,7 +364,7 @@ def same_config_leg(cpu, steps_total, torch):
             "energy_gpu": e_gpu, "energy_cpu": cpu["energy"], "abs_energy_diff": abs(e_gpu - cpu["energy"]),
             "h2d_bytes_per_step": (t1h.numel() + t2h.numel()) * 8, "d2h_bytes_per_step": (t1h.numel() + t2h.numel()) * 8 + 64,
             "what": "same inputs, same start, same sweep count on both sides; GPU side through CCSD.sweep_host "
-                    "with host buffers (launch-latency bound at this size: ~500 kernels per sweep)"}
+                    "with host buffers (launch-latency bound at this size: ~170 kernels per sweep)"}
 
 
 def run_ours(args):
