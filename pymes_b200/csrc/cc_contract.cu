@@ -68,8 +68,6 @@ struct Params {
     // Tail launch (see pmb_contract): this launch covers the output tiles [tile_base, tile_base +
     // gridDim.x) only, split over k; partial sums go to ws[split][tile - tile_base][BM x BN].
     int tile_base, tail;
-    int dbg;                 // PMB_WS_DEBUG diagnostics (timing only, results are garbage): 1 = producers
-                             // publish stages without copying anything, 2 = B tiles only
     double *ws;
     TermDev t[PMB_MAX_TERMS];
     // generated A operand (never-materialised UEG integrals): term index or -1
@@ -774,12 +772,9 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
             const int krem = t.K - (g - t.kt_begin) * BK;
             const Gat gb = make_gat<BN, NP>(bs_base + (unsigned)(st * BK * LDB * 8), t.B, s_bn + ti * BN,
                                             ko + BK, t.b_kfast != 0, ptid);
-            if (p.dbg == 1) {
-                // diagnostics: nothing is copied, the stage is published as it is
-            } else if (ti == p.gen_term) {
+            if (ti == p.gen_term) {
                 // B first: its copies are in flight while the A tile is written
                 gat_issue_batched<PER_B, 8>(gb, krem);
-                if (p.dbg == 2) goto publish;
                 double *dst = As + st * BK * LDA + gk0 * LDA + gx;
                 if (gen_walk) {
                     // The tile column of this row is zero except, once in ~ext_s / 16 tiles, one element.
@@ -843,11 +838,10 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
             } else {
                 const Gat ga = make_gat<BM, NP>(as_base + (unsigned)(st * BK * LDA * 8), t.A, s_am + ti * BM, ko,
                                                 t.a_kfast != 0, ptid);
-                if (p.dbg != 2) gat_issue_batched<PER_A, 8>(ga, krem);
+                gat_issue_batched<PER_A, 8>(ga, krem);
                 gat_issue_batched<PER_B, 8>(gb, krem);
                 wk_dirty |= 0xffULL << (8 * st);          // a stored operand's tile now lives in this stage
             }
-        publish:
             if (p.gen_term >= 0) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_base + st * 8);
@@ -1339,14 +1333,6 @@ static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
     p.kt_limit = kt;
     p.tile_base = 0;
     p.tail = 0;
-    {
-        static int dbg = -1;
-        if (dbg < 0) {
-            const char *e = getenv("PMB_WS_DEBUG");
-            dbg = e ? atoi(e) : 0;
-        }
-        p.dbg = dbg;
-    }
     p.ws = nullptr;
     return 0;
 }
