@@ -105,6 +105,19 @@ def empty_stacked(shape_a, shape_b):
     return buf[:na].view(*shape_a), buf[na:].view(*shape_b)
 
 
+def empty_even_pitch(n0, n1, no):
+    """An [n0, n1, no, no] amplitude-shaped tensor whose (i,j) rows start on 16-byte boundaries: the
+    o^2 doubles of a row are followed by one pad double when o^2 is odd (o = 27: pitch 730).  The
+    contraction kernel copies such an operand 16 bytes at a time (`b_vec2`, cc_contract.cu); the
+    pad is zero and is never part of a result."""
+    oo = no * no
+    pitch = oo + (oo & 1)
+    buf = torch.empty((n0, n1, pitch), dtype=F64, device=device())
+    if pitch != oo:
+        buf[:, :, oo:].zero_()
+    return buf[:, :, :oo].view(n0, n1, no, no)
+
+
 def stacked_rows(A, B, k_shape):
     """If the contiguous tensors A and B lie back to back in one allocation (``empty_stacked``) and
     both end in the index pattern ``k_shape`` (the contracted indices of a common contraction),

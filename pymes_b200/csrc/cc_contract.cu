@@ -51,6 +51,7 @@ struct TermDev {
     long long a_mstr[PMB_MAX_DIMS], b_nstr[PMB_MAX_DIMS];
     double alpha;
     int a_kfast, b_kfast;
+    int b_vec2;              // B tile copied 16 bytes at a time (see make_gat_vec2)
     int kt_begin, nkt;
 };
 
@@ -235,6 +236,48 @@ __device__ __forceinline__ void gat_issue_batched(const Gat &g, int krem) {
         for (int j = 0; j < CHUNK; ++j) {
             const int it = c0 + j;
             cp_async8z(g.sdst + (unsigned)(it * g.dstep), g.base + off[j], (g.k0 + it * g.kinc < krem) ? 8 : 0);
+        }
+    }
+}
+
+// 16-byte form of the x-fast gather, for operands whose composite x index is DENSE in memory
+// (consecutive x are consecutive doubles), whose k strides are even and whose base is 16-byte
+// aligned -- tau of the ladder when it lives in a pitch-padded buffer ([v,v,736] for o = 27: a
+// 729-double pitch leaves every other row misaligned).  A thread owns a PAIR of columns and steps
+// k; half as many LDGSTS as the 8-byte form.
+__device__ __forceinline__ void cp_async16z(unsigned smem_addr, const double *gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_addr), "l"(gsrc), "r"(src_bytes));
+}
+template <int BX, int NT>
+__device__ __forceinline__ Gat make_gat_vec2(unsigned S, const double *__restrict__ G, const long long *s_x,
+                                             const long long *s_k, int tid) {
+    constexpr int LD = BX + SPAD;
+    constexpr int HX = BX / 2;
+    constexpr int KSTEP = NT / HX;
+    static_assert(NT % HX == 0 && BK % KSTEP == 0, "pairs of columns must tile the producer threads");
+    const int x = 2 * (tid % HX), k = tid / HX;
+    Gat g;
+    g.base = G + s_x[x];
+    g.tab = s_k + k;
+    g.tstep = KSTEP;
+    g.sdst = S + (unsigned)((k * LD + x) * 8);
+    g.dstep = KSTEP * LD * 8;
+    g.k0 = k;
+    g.kinc = KSTEP;
+    return g;
+}
+template <int PER, int CHUNK>
+__device__ __forceinline__ void gat_issue_vec2(const Gat &g, int krem) {
+    static_assert(PER % CHUNK == 0, "copies must split into whole chunks");
+#pragma unroll
+    for (int c0 = 0; c0 < PER; c0 += CHUNK) {
+        long long off[CHUNK];
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) off[j] = g.tab[(c0 + j) * g.tstep];
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) {
+            const int it = c0 + j;
+            cp_async16z(g.sdst + (unsigned)(it * g.dstep), g.base + off[j], (g.k0 + it * g.kinc < krem) ? 16 : 0);
         }
     }
 }
@@ -770,11 +813,16 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
             const TermDev &t = p.t[ti];
             const long long *ko = s_k + ((g - kt_lo) & (KRING - 1)) * 2 * BK;
             const int krem = t.K - (g - t.kt_begin) * BK;
-            const Gat gb = make_gat<BN, NP>(bs_base + (unsigned)(st * BK * LDB * 8), t.B, s_bn + ti * BN,
-                                            ko + BK, t.b_kfast != 0, ptid);
+            const Gat gb = t.b_vec2 ? make_gat_vec2<BN, NP>(bs_base + (unsigned)(st * BK * LDB * 8), t.B,
+                                                            s_bn + ti * BN, ko + BK, ptid)
+                                    : make_gat<BN, NP>(bs_base + (unsigned)(st * BK * LDB * 8), t.B, s_bn + ti * BN,
+                                                       ko + BK, t.b_kfast != 0, ptid);
             if (ti == p.gen_term) {
                 // B first: its copies are in flight while the A tile is written
-                gat_issue_batched<PER_B, 8>(gb, krem);
+                if (t.b_vec2)
+                    gat_issue_vec2<PER_B / 2, 8>(gb, krem);
+                else
+                    gat_issue_batched<PER_B, 8>(gb, krem);
                 double *dst = As + st * BK * LDA + gk0 * LDA + gx;
                 if (gen_walk) {
                     // The tile column of this row is zero except, once in ~ext_s / 16 tiles, one element.
@@ -839,7 +887,10 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
                 const Gat ga = make_gat<BM, NP>(as_base + (unsigned)(st * BK * LDA * 8), t.A, s_am + ti * BM, ko,
                                                 t.a_kfast != 0, ptid);
                 gat_issue_batched<PER_A, 8>(ga, krem);
-                gat_issue_batched<PER_B, 8>(gb, krem);
+                if (t.b_vec2)
+                    gat_issue_vec2<PER_B / 2, 8>(gb, krem);
+                else
+                    gat_issue_batched<PER_B, 8>(gb, krem);
                 wk_dirty |= 0xffULL << (8 * st);          // a stored operand's tile now lives in this stage
             }
             if (p.gen_term >= 0) {
@@ -1021,6 +1072,7 @@ static const TileCfg kCfg[] = {
     {128, 128, 384, 1.30}, {128, 128, 384, 1.00}};
 constexpr int kNumCfg = 7;
 
+static int g_no_vec2 = 0;          // tuning bit 128: 8-byte copies even where 16-byte ones are possible
 static int g_no_tail = 0;          // tuning bit 64: never cut the tail wave off (see tail_plan)
 static int g_gen_no_walk = 0;      // tuning bit 16: generated operands use the scanning producer
 static int g_gen_no_mraster = 0;   // tuning bit 32: keep the default tile order for generated operands
@@ -1308,6 +1360,19 @@ static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
         };
         t.a_kfast = kfast(s.nk, s.a_kstr, s.k_ext, d->nm, s.a_mstr);
         t.b_kfast = kfast(s.nk, s.b_kstr, s.k_ext, d->nn, s.b_nstr);
+        // 16-byte copies of B: N group dense in memory, even k strides, aligned base, and at least
+        // one contracted index (the tile loop then runs over real k offsets)
+        t.b_vec2 = 0;
+        if (!g_no_vec2 && d->nn >= 1 && s.nk >= 1 && !t.b_kfast && ((uintptr_t)s.B & 15) == 0) {
+            bool ok = true;
+            int64_t dense = 1;
+            for (int i = 0; i < d->nn && ok; ++i) {
+                ok = s.b_nstr[i] == dense;
+                dense *= d->n_ext[i];
+            }
+            for (int i = 0; i < s.nk && ok; ++i) ok = (s.b_kstr[i] % 2) == 0;
+            t.b_vec2 = ok ? 1 : 0;
+        }
         t.kt_begin = kt;
         t.nkt = (t.K + BK - 1) / BK;
         kt += t.nkt;
@@ -1389,6 +1454,7 @@ extern "C" void pmb_contract_set_tuning(int tile_config, int split_k) {
     g_gen_no_walk = tile_config >= 0 && (tile_config & 16);
     g_gen_no_mraster = tile_config >= 0 && (tile_config & 32);
     g_no_tail = tile_config >= 0 && (tile_config & 64);
+    g_no_vec2 = tile_config >= 0 && (tile_config & 128);
     g_force_cfg = tile_config >= 0 ? (tile_config & 15) : tile_config;
     g_force_split = split_k;
 }

@@ -282,7 +282,7 @@ class ShardedCCSD(ccsd.CCSD):
 
         def apply(T2, R):
             ct = bk.contract_terms
-            tau = bk.copy(T2)
+            tau = bk.axpby(1.0, T2, 0.0, bk.empty_even_pitch(T2.shape[0], T2.shape[1], T2.shape[2]))
             ct("abij", [(1.0, "ai", T1, "bj", T1)], out=tau, beta=1.0)
             with bk.timed("pp_ladder"):
                 ct("abij", [(1.0, "abcd", dV["abcd"], "cdij", tau)], out=R, beta=1.0)

@@ -836,3 +836,38 @@ def test_ueg_remaining_branches_match_reference(flag):
 @pytest.mark.parametrize("name,gamma,k_cutoff", host.UEG_CORRELATORS)
 def test_ueg_every_correlator_matches_reference(name, gamma, k_cutoff):
     host.test_ueg_every_correlator_matches_reference(None, name, gamma, k_cutoff)
+
+
+@pytest.mark.parametrize("no,nv", [(27, 40), (7, 50), (10, 33)])
+def test_sixteen_byte_operand_copies(no, nv):
+    """An [.,.,o,o] operand in an even-pitch buffer (backend.empty_even_pitch: o^2 = 729 -> pitch 730) is
+    copied into the tiles 16 bytes at a time by the warp-specialised kernel (b_vec2).  Same arithmetic
+    as the 8-byte copies: results are bit-identical to the run with tuning bit 128 (8-byte copies), to the
+    contiguous operand, and equal numpy to round-off; ragged last column tile, split-K and a second
+    (8-byte) term in the same launch included."""
+    from pymes_b200 import _lib, backend as bk
+    g = torch.Generator(device="cuda").manual_seed(5)
+    V = torch.randn(nv, nv, nv, nv, dtype=torch.float64, device="cuda", generator=g)
+    T = torch.randn(nv, nv, no, no, dtype=torch.float64, device="cuda", generator=g)
+    I = torch.randn(no, no, no, no, dtype=torch.float64, device="cuda", generator=g)
+    Tp = bk.axpby(1.0, T, 0.0, bk.empty_even_pitch(nv, nv, no))
+    assert torch.equal(Tp, T) and Tp.stride(1) % 2 == 0 and Tp.data_ptr() % 16 == 0
+    lib = _lib.load()
+    try:
+        lib.pmb_contract_set_tuning(5, 0)
+        plain = bk.contract("abcd,cdij->abij", V, T)
+        vec = bk.contract("abcd,cdij->abij", V, Tp)
+        two = bk.contract_terms("abij", [(0.5, "abcd", V, "cdij", Tp), (2.0, "abkl", T, "klij", I)])
+        lib.pmb_contract_set_tuning(5, 3)
+        vec_split = bk.contract("abcd,cdij->abij", V, Tp)
+        lib.pmb_contract_set_tuning(5 + 128, 0)
+        novec = bk.contract("abcd,cdij->abij", V, Tp)
+        two_novec = bk.contract_terms("abij", [(0.5, "abcd", V, "cdij", Tp), (2.0, "abkl", T, "klij", I)])
+        lib.pmb_contract_set_tuning(5 + 128, 3)
+        novec_split = bk.contract("abcd,cdij->abij", V, Tp)
+    finally:
+        lib.pmb_contract_set_tuning(-1, 0)
+    assert torch.equal(vec, novec) and torch.equal(vec, plain) and torch.equal(two, two_novec)
+    assert torch.equal(vec_split, novec_split)
+    want = V.cpu().numpy().reshape(nv * nv, -1) @ T.cpu().numpy().reshape(nv * nv, -1)
+    assert _rel(vec.cpu().numpy().reshape(nv * nv, -1), want) < 1e-13
