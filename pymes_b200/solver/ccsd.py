@@ -361,7 +361,9 @@ class CCSD(ccd.CCD):
         st["amps_host"] = None
         if amps is not None:
             if isinstance(amps[0], torch.Tensor):
-                T1, T2 = bk.asdev(amps[0]), bk.asdev(amps[1])
+                T1, T2 = bk.asdev(amps[0]), bk.asdev(amps[1])        # aliased: updated in place
+                if not (T1.is_contiguous() and T2.is_contiguous()):  # the elementwise kernels index them flat
+                    raise ValueError("amps given as tensors must be contiguous [nv,no] / [nv,nv,no,no]")
             else:
                 st["amps_host"] = amps
                 T1, T2 = bk.asdev(amps[0]).contiguous(), bk.asdev(amps[1]).contiguous()

@@ -670,6 +670,8 @@ def test_two_rank_nccl_parity(tmp_path):
     import sys
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
+    from pymes_b200 import backend as bk
+    assert float(bk.copy(torch.ones(3, 3, dtype=torch.float64, device="cuda")).sum()) == 9.0    # library loaded here too
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = tmp_path / "nccl_parity.json"
     port = 29700 + os.getpid() % 200
