@@ -409,6 +409,11 @@ class EOM_CCSD:
         if parallel not in ("rows", "vectors"):
             raise ValueError("parallel must be 'rows' or 'vectors'")
         self.algo_name = "EOM-CCSD"
+        # "scalar": the reference's correction vectors, r / (e_n - D_guess_n + 1e-5) with ONE number per
+        # root (eom_ccsd.py:140-141).  "diagonal" (extension, not the reference's iterates): the usual
+        # Davidson correction r / (e_n - diag(H-bar) + 1e-5) with the diagonal of get_diag_singles /
+        # get_diag_doubles -- what converges the 54-electron systems.
+        self.preconditioner = "scalar"
         self.comm = comm if parallel == "rows" else None
         self.vec_comm = comm if (parallel == "vectors" and comm is not None and comm.size > 1) else None
         self.max_rhs = 16                 # right-hand sides per batched sigma call (bounds the temporaries)
@@ -555,6 +560,12 @@ class EOM_CCSD:
             u1s.append(bk.asdev(A.reshape(nv, no)))
             u2s.append(bk.zeros(nv, nv, no, no))
         w1s, w2s = [], []
+        if self.preconditioner not in ("scalar", "diagonal"):
+            raise ValueError("preconditioner must be 'scalar' or 'diagonal'")
+        hdiag = None
+        if self.preconditioner == "diagonal":
+            dV = _as_dict_dev(dict_t_V_dressed)
+            hdiag = (diag_singles(no, fock, dV, T2).reshape(-1), diag_doubles(no, fock, dV, T2).reshape(-1))
         B = np.zeros((0, 0))
         e = np.zeros(n_excit)
         e_imag = np.zeros(n_excit)
@@ -590,11 +601,18 @@ class EOM_CCSD:
                 self.e_excit = e_old
             else:                                                      # expand, eom_ccsd.py:134-147
                 for n in range(n_excit):
-                    scale = 1.0 / (e[n] - D_ai[lowest[n]] + 1e-5)
-                    cw = list(v[:, n] * scale)
-                    cu = list(-e[n] * v[:, n] * scale)
-                    u1s.append(bk.lincomb(cw + cu, w1s + u1s[:m]))
-                    u2s.append(bk.lincomb(cw + cu, w2s + u2s[:m]))
+                    if hdiag is None:
+                        scale = 1.0 / (e[n] - D_ai[lowest[n]] + 1e-5)
+                        cw = list(v[:, n] * scale)
+                        cu = list(-e[n] * v[:, n] * scale)
+                        u1s.append(bk.lincomb(cw + cu, w1s + u1s[:m]))
+                        u2s.append(bk.lincomb(cw + cu, w2s + u2s[:m]))
+                    else:                                          # residual / (e_n - diag + 1e-5), elementwise
+                        cw, cu = list(v[:, n]), list(-e[n] * v[:, n])
+                        for us, ws, hd in ((u1s, w1s, hdiag[0]), (u2s, w2s, hdiag[1])):
+                            r = bk.lincomb(cw + cu, ws + us[:m])
+                            y, _ = bk.cdiv_shifted(hd, complex(e[n]), 1e-5, r.reshape(-1), r.reshape(-1))
+                            us.append(y.view(r.shape))
                 diff_e_norm = np.linalg.norm(self.e_excit - e)
                 self.e_excit = e
             if diff_e_norm < self.e_epsilon:

@@ -909,3 +909,36 @@ def test_trunc_mutates_its_array_argument_like_the_reference():
     np.testing.assert_array_equal(arg, g["trunc_arg_after"])
     np.testing.assert_allclose(res, g["trunc_res"], rtol=1e-15)
     assert m.trunc(0.2) == 0.0 and m.trunc(10.0) == -4.0 * np.pi / 100.0
+
+
+def test_davidson_diagonal_preconditioner_finds_eigenvalues(cpu_abi):
+    """Extension: EOM_CCSD.preconditioner = "diagonal" (r / (e - diag(H-bar) + 1e-5) instead of the
+    reference's one-number-per-root scaling, eom_ccsd.py:140).  Its roots are eigenvalues of the dense
+    H-bar (built column by column through the same sigma), the lowest one is the reference's, and it
+    may find LOWER further roots than the reference's iteration does (H2/3-21G: 0.4801 instead of 1.1646,
+    both eigenvalues: the singles-only start vectors of eom_ccsd.py:76-82 never reach the state)."""
+    from pymes_b200.integral.partition import part_2_body_int
+    from pymes_b200.solver import ccsd, eom_ccsd
+    for tag in ("LiH_321g", "H2_321g"):
+        g = golden("mol_" + tag)
+        no = int(g["n_elec"]) // 2
+        dV = part_2_body_int(no, _t(g["V"]))
+        cc = ccsd.CCSD(no)
+        T1, T2, fock = _t(g["ccsd_t1"]), _t(g["ccsd_t2"]), _t(g["fock"])
+        ft = cc.get_T1_dressed_fock(fock, T1, dV)
+        dVt = cc.get_T1_dressed_V(T1, dV)
+        roots = {}
+        for kind in ("scalar", "diagonal"):
+            eom = eom_ccsd.EOM_CCSD(no, n_excit=len(g["eom_e"]))
+            eom.preconditioner = kind
+            roots[kind] = np.sort(eom.solve(ft, dVt, T2))
+        np.testing.assert_allclose(roots["scalar"], np.sort(g["eom_e"]), rtol=0, atol=1e-8)
+        plan = eom.plan(ft, dVt, T2)
+        nv = T2.shape[0]
+        n = nv * no + nv * nv * no * no
+        H = _n(plan.apply_packed(_t(np.eye(n)))).T
+        ev = np.linalg.eigvals(H)
+        for r in roots["diagonal"]:
+            assert np.abs(ev - r).min() < 1e-7, (tag, r)
+        assert abs(roots["diagonal"][0] - roots["scalar"][0]) < 1e-7
+        assert np.all(roots["diagonal"] <= roots["scalar"] + 1e-7)

@@ -5,7 +5,7 @@
                   `trial` trial vectors = nodes x trial shifted linear systems, 2 real right-hand
                   sides each, advanced in lock-step through the batched sigma.
 
-    python tools/bench_excited.py davidson [cutoff=13] [roots=10] [max_iter=40]
+    python tools/bench_excited.py davidson [cutoff=13] [roots=10] [max_iter=40] [scalar|diagonal]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \\
         --master-port 29530 tools/bench_excited.py feast [cutoff=13] [nodes=16] [trial=32] [feast_iters=1] \\
         [e_c] [e_r] [max_systems=8] [krylov=20]
@@ -98,9 +98,11 @@ def run_davidson(argv, comm, log):
     cutoff = float(argv[0]) if len(argv) > 0 else 13.0
     roots = int(argv[1]) if len(argv) > 1 else 10
     max_iter = int(argv[2]) if len(argv) > 2 else 40
+    precond = argv[3] if len(argv) > 3 else "scalar"       # "scalar": the reference's; "diagonal": extension
     gs = ground_state(cutoff, log=log)
     no, nv = gs["no"], gs["nv"]
     eom = eom_ccsd.EOM_CCSD(no, n_excit=roots, comm=comm, parallel="vectors")
+    eom.preconditioner = precond
     eom.max_iter = max_iter
     eom.max_rhs = 4 if nv > 300 else 10
     t0 = time.perf_counter()
@@ -118,7 +120,7 @@ def run_davidson(argv, comm, log):
     # collapse; otherwise report the spread of the last two Ritz-value sets through e_excit)
     return {"config": "C4 EOM-CCSD Davidson, %d roots, TC-UEG 54e" % roots, "n_orb": gs["model"].n_orb, "n_occ": no,
             "n_virt": nv, "E_ccsd": gs["e_ccsd"], "ccsd_sweeps": gs["ccsd_sweeps"], "plan_seconds": t_plan,
-            "sigma": prof, "davidson_iterations": eom.iterations, "davidson_seconds": dt,
+            "preconditioner": precond, "sigma": prof, "davidson_iterations": eom.iterations, "davidson_seconds": dt,
             "converged": bool(eom.iterations < max_iter), "roots_Eh": [float(x) for x in np.sort(e)],
             "launches": bk.launch_count() - l0, "allocated_GB_peak": torch.cuda.max_memory_allocated() / 1e9
             if torch.cuda.is_available() else None}
