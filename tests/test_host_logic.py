@@ -942,3 +942,29 @@ def test_davidson_diagonal_preconditioner_finds_eigenvalues(cpu_abi):
             assert np.abs(ev - r).min() < 1e-7, (tag, r)
         assert abs(roots["diagonal"][0] - roots["scalar"][0]) < 1e-7
         assert np.all(roots["diagonal"] <= roots["scalar"] + 1e-7)
+
+
+def test_stacked_rows_and_even_pitch_helpers(cpu_abi):
+    """backend.empty_stacked / stacked_rows (two blocks as one operand) and empty_even_pitch (16-byte
+    aligned (i,j) rows): the views alias the right memory, and the negative cases are refused."""
+    from pymes_b200 import backend as bk
+    no, nb, nv = 3, 4, 5
+    A, B = bk.empty_stacked((no, nb, nv, nv), (nb, no, nv, nv))
+    A.copy_(_t(np.arange(A.numel(), dtype=float).reshape(A.shape)))
+    B.copy_(_t(-np.arange(B.numel(), dtype=float).reshape(B.shape)))
+    st = bk.stacked_rows(A, B, (nv, nv))
+    assert tuple(st.shape) == (2, no * nb, nv, nv)
+    assert torch.equal(st[0].reshape(-1), A.reshape(-1)) and torch.equal(st[1].reshape(-1), B.reshape(-1))
+    tau = _t(np.random.default_rng(0).standard_normal((nv, nv, 2, 2)))
+    W = bk.contract("grcd,cdij->grij", st, tau)
+    np.testing.assert_allclose(_n(W[0]).reshape(no, nb, 2, 2), np.einsum("kbcd,cdij->kbij", _n(A), _n(tau)), **TOL)
+    np.testing.assert_allclose(_n(W[1]).reshape(nb, no, 2, 2), np.einsum("alcd,cdij->alij", _n(B), _n(tau)), **TOL)
+    assert bk.stacked_rows(A, B.clone(), (nv, nv)) is None              # not adjacent
+    assert bk.stacked_rows(B, A, (nv, nv)) is None                      # wrong order
+    assert bk.stacked_rows(A, B, (nv, nv + 1)) is None                  # other contracted shape
+    with pytest.raises(ValueError):
+        bk.empty_stacked((2, 3), (4, 2))
+    for o in (3, 4):                                                   # o^2 odd -> one pad double; even -> none
+        t = bk.empty_even_pitch(5, 6, o)
+        assert tuple(t.shape) == (5, 6, o, o) and t.stride(1) % 2 == 0 and t.stride(3) == 1 and t.stride(2) == o
+        assert t.stride(1) == o * o + (o * o) % 2
