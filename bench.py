@@ -15,10 +15,20 @@ blocks per rank when N > 1.  `--dense-abcd` stores V_abcd instead (then the basi
 use --cutoff 18 -> 341 orbitals on one GPU).  Data are synthetic in the sense that nothing is
 read from disk; it is the physical TC-UEG Hamiltonian.
 
+The particle-particle ladder runs MOMENTUM-BLOCKED by default (`--ladder blocked`, SURVEY
+8(f).1): V_abcd as the matrix [(ab),(cd)] is block diagonal in the total momentum, and
+pmb_blocked_contract visits the diagonal blocks only -- 2 o^2 nnz(V_abcd) flop instead of
+2 o^2 v^4 (4.8e10 instead of 8.3e13 at 515 plane waves), same result to round-off.
+`--ladder dense` keeps the dense DMMA ladder with the operand generated in the producer warps
+(the round-1 / early round-2 configuration; its roofline is the pp-ladder one).
+
 Printed line: see the contract in the task statement; `value` is FP64 TFLOP/s computed from
-the ALGORITHMIC flop count of the reference's doubles residual
-F_CCD = 2o^2v^4 + 20o^3v^3 + 4o^4v^2 + 4o^2v^3 + 4o^3v^2 (T1-dressing flops are
-executed but not counted) divided by the measured time of a whole iteration.
+the ALGORITHMIC flop count of the doubles residual AS EXECUTED,
+F = F_CCD - 2o^2v^4 + 2o^2 nnz(V_abcd) with F_CCD = 2o^2v^4 + 20o^3v^3 + 4o^4v^2 + 4o^2v^3 + 4o^3v^2
+(T1-dressing flops are executed but not counted; F = F_CCD with `--ladder dense`),
+divided by the measured time of a whole iteration -- so it can never exceed the FP64 peak.
+`dense_equivalent_tflops` = F_CCD / time is what the reference's dense einsum formulation would
+have to sustain to finish the iteration in the same time.
 """
 import argparse
 import json
@@ -259,11 +269,14 @@ def synthetic_config(n_gpus, no, nv):
             "parallelism": "ab-block x%d" % n_gpus}
 
 
-def workload_config(n_gpus, no, cutoff=None, dense_abcd=False):
+def workload_config(n_gpus, no, cutoff=None, dense_abcd=False, blocked=False):
     cutoff = cutoff or CUTOFF_FOR_GPUS[n_gpus]
     return {"workload": "TC-UEG 54e rs=%.1f CCSD+DIIS iteration, plane-wave cutoff %g" % (RS, cutoff),
             "method": "CCSD", "correlator": "trunc k_c=%g" % K_CUTOFF, "n_occ": no,
-            "V_abcd": "stored in HBM" if dense_abcd else "never materialised (generated in the ladder kernel)",
+            "V_abcd": "stored in HBM" if dense_abcd else
+                      ("never materialised: compressed values (one candidate non-zero per dense row), pp ladder "
+                       "on the diagonal momentum blocks only (pmb_blocked_contract)" if blocked else
+                       "never materialised (generated in the ladder kernel)"),
             "l2_policy": "inputs_exceed_l2 (every T2-sized operand and o.v^3 block >> 126 MB L2)",
             "parallelism": "ab-block x%d" % n_gpus}
 
@@ -385,6 +398,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     plog.set_quiet(True)
+    blocked = args.ladder == "blocked" and args.workload == "ueg" and not args.dense_abcd
+    bk.set_blocked(blocked)
     no = N_ELE // 2
     cutoff = args.cutoff if args.cutoff else CUTOFF_FOR_GPUS[args.gpus]
     cal = calibrate(torch) if (rank == 0 and not args.no_calibration) else None
@@ -448,6 +463,8 @@ def run_ours(args):
 
     sampler = ClockSampler(local)
     bk.enable_timing(True)
+    if blocked:
+        bk.enable_trace(True)          # an event pair around every contraction launch (no synchronisation)
     launches0 = bk.launch_count()
     barrier()
     sampler.start()
@@ -463,30 +480,64 @@ def run_ours(args):
     launches = bk.launch_count() - launches0
     ms = ev0.elapsed_time(ev1) / args.steps
     regions = bk.timing_report()
+    trace = bk.trace_report() if blocked else []
+    bk.enable_trace(False)
     bk.enable_timing(False)
     e_final = e[0] + e[1] + e[2]
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    F = flops_ccd(no, nv, is_dcd=args.dcsd)
+    F_dense = flops_ccd(no, nv, is_dcd=args.dcsd)
+    F = F_dense
+    if blocked:
+        # flops as executed: the ladder visits the nnz candidate non-zeros of V_abcd only
+        _ro, _eo, _g0, g_rows, _e0, g_ents = ueg.momentum_groups(m.k_int(), m.imax, (no,) * 4, (nv,) * 4)
+        nnz_abcd = float((g_rows * g_ents).sum())
+        F = F_dense - 2.0 * no * no * float(nv) ** 4 + 2.0 * no * no * nnz_abcd
     value = F / (ms * 1e-3) / 1e12
 
-    # dominant kernel: the particle-particle ladder contraction (this rank's row block)
-    pp_ms = regions.get("pp_ladder", [])
     rows = getattr(cc, "local_rows", nv) if world > 1 else nv
-    pp_flops = 2.0 * rows * nv * nv * nv * no * no
-    pp_avg = sum(pp_ms) / len(pp_ms) if pp_ms else None
     peak = SM_COUNT * DMMA_FMA_PER_CLK_PER_SM * 2 * (clocks.get("sm_max_mhz") or 1965) * 1e6 / 1e12
-    roof = {"bound": "tensor",
-            "kernel": "contract_ws_kernel (pp ladder V_abcd.tau, DMMA.8x8x4%s)"
-                      % ("" if args.dense_abcd else "; V_abcd tiles generated by the producer warps"),
-            "achieved": (pp_flops / (pp_avg * 1e-3) / 1e12) if pp_avg else None,
-            "peak": peak, "unit": "TFLOP/s",
-            "peak_source": "FP64 tensor (DMMA) issue peak: 148 SM x 64 FMA/clk x 2 x sm_max_mhz; "
-                           "MEASURED_PEAKS.json has no FP64 entry (its bf16 figure does not apply)",
-            "traffic": None, "launches_timed": len(pp_ms), "ms_per_launch": pp_avg,
-            "flops_per_launch": pp_flops}
+    pp_ms = regions.get("pp_ladder", [])
+    pp_avg = sum(pp_ms) / len(pp_ms) if pp_ms else None
+    if blocked:
+        # dominant kernel now: contract_ws_kernel on the nine ring-type o^3v^3 contractions of
+        # ccd.py:189-204,233-240 (seven launches, one of them three terms wide), this rank's rows
+        ring_unit = 2.0 * rows * nv * nv * float(no) ** 3
+        ring = [(fl, t) for lab, fl, t in trace if "[" not in lab and fl >= 0.99 * ring_unit]
+        ring_flops, ring_ms = sum(fl for fl, _ in ring), sum(t for _, t in ring)
+        n_ring = len(ring)
+        roof = {"bound": "tensor",
+                "kernel": "contract_ws_kernel (ring-type contractions 2 o^3 v^3 of the doubles residual, DMMA.8x8x4; "
+                          "per launch = average over the %d launches of one iteration, the three-term launch "
+                          "counting its three products)" % (n_ring // max(args.steps, 1)),
+                "achieved": (ring_flops / (ring_ms * 1e-3) / 1e12) if ring_ms else None,
+                "peak": peak, "unit": "TFLOP/s",
+                "peak_source": "FP64 tensor (DMMA) issue peak: 148 SM x 64 FMA/clk x 2 x sm_max_mhz; "
+                               "MEASURED_PEAKS.json has no FP64 entry (its bf16 figure does not apply)",
+                "traffic": None, "launches_timed": n_ring, "ms_per_launch": ring_ms / n_ring if n_ring else None,
+                "flops_per_launch": ring_flops / n_ring if n_ring else None,
+                "share_of_step": ring_ms / (ms * args.steps) if ring_ms else None}
+        bl = [(fl, t) for lab, fl, t in trace if lab.endswith("abcd,cdij->abij [momentum-blocked]")]
+        if bl:
+            roof["pp_ladder_blocked"] = {
+                "kernel": "blocked_kernel (pmb_blocked_contract: V_abcd.tau on the diagonal momentum blocks)",
+                "ms_per_launch": sum(t for _, t in bl) / len(bl), "flops_per_launch_executed": bl[0][0],
+                "tflops_executed": sum(fl for fl, _ in bl) / (sum(t for _, t in bl) * 1e-3) / 1e12,
+                "dense_flops_replaced": 2.0 * rows * float(nv) ** 3 * no * no, "launches_timed": len(bl)}
+    else:
+        # dominant kernel: the particle-particle ladder contraction (this rank's row block)
+        pp_flops = 2.0 * rows * nv * nv * nv * no * no
+        roof = {"bound": "tensor",
+                "kernel": "contract_ws_kernel (pp ladder V_abcd.tau, DMMA.8x8x4%s)"
+                          % ("" if args.dense_abcd else "; V_abcd tiles generated by the producer warps"),
+                "achieved": (pp_flops / (pp_avg * 1e-3) / 1e12) if pp_avg else None,
+                "peak": peak, "unit": "TFLOP/s",
+                "peak_source": "FP64 tensor (DMMA) issue peak: 148 SM x 64 FMA/clk x 2 x sm_max_mhz; "
+                               "MEASURED_PEAKS.json has no FP64 entry (its bf16 figure does not apply)",
+                "traffic": None, "launches_timed": len(pp_ms), "ms_per_launch": pp_avg,
+                "flops_per_launch": pp_flops}
     roof["frac"] = roof["achieved"] / peak if roof["achieved"] else None
     if cal is not None:                 # second denominator: a library DGEMM measured in THIS run
         roof["peak_measured_dgemm"] = cal["dgemm_tflops"]
@@ -498,6 +549,8 @@ def run_ours(args):
                                           if roof["achieved"] else None)
     prof = os.path.join(ROOT, "profiles", "pp_ladder_traffic.json" if args.dense_abcd
                         else "pp_ladder_virtual_traffic.json")
+    if blocked:
+        prof = os.path.join(ROOT, "profiles", "r2_ring_traffic.json")
     if os.path.exists(prof) and world == 1:
         try:                            # ncu capture of the same launch (same v, whole row range)
             rec = json.load(open(prof))
@@ -535,10 +588,18 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(synthetic_config(args.gpus, no, nv) if synthetic_wl
-                           else workload_config(args.gpus, no, cutoff, args.dense_abcd), n_orb=nP, n_virt=nv,
+                           else workload_config(args.gpus, no, cutoff, args.dense_abcd, blocked), n_orb=nP, n_virt=nv,
                            **({"method": "DCSD"} if args.dcsd else {}),
                            flops_per_step=F, energy=e_final, build_seconds=t_build),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof}
+    if blocked:
+        line["config"]["flop_convention"] = (
+            "flops_per_step = doubles-residual flops AS EXECUTED: SURVEY 8(d) F_CCD = %.4e with the pp ladder's "
+            "2 o^2 v^4 = %.4e replaced by 2 o^2 nnz(V_abcd) = %.4e (momentum-blocked, nnz = %.0f)"
+            % (F_dense, 2.0 * no * no * float(nv) ** 4, 2.0 * no * no * nnz_abcd, nnz_abcd))
+        line["config"]["flops_per_step_dense_convention"] = F_dense
+        line["dense_equivalent_tflops"] = F_dense / (ms * 1e-3) / 1e12
+        line["e2e"]["dense_equivalent_tflops"] = F_dense / (e2e_ms * 1e-3) / 1e12
     if rank == 0:
         if args.gpus == 1 and not args.no_cpu and not synthetic_wl:
             cores = len(os.sched_getaffinity(0))
@@ -547,7 +608,7 @@ def run_ours(args):
             # the reference cannot hold this workload's V (563 GB): its time here is EXTRAPOLATED by
             # algorithmic flops from the sample that did run, not measured
             line["cpu_baseline"]["extrapolated_seconds_per_step_at_workload"] = \
-                F / (line["cpu_baseline"]["value"] * 1e12)
+                F_dense / (line["cpu_baseline"]["value"] * 1e12)
             # ... and the MEASURED same-config ratio: the GPU runs the sample problem itself
             del cc, dV
             torch.cuda.empty_cache()
@@ -575,6 +636,9 @@ def main():
                          "random non-hermitian integrals with a STORED dense V_abcd (fits 8 GPUs)")
     ap.add_argument("--occ", type=int, default=50, help="synthetic workload: occupied orbitals")
     ap.add_argument("--virt", type=int, default=500, help="synthetic workload: virtual orbitals")
+    ap.add_argument("--ladder", default="blocked", choices=["blocked", "dense"],
+                    help="blocked: V_abcd.tau (and V_iabc.tau, V_aibc.tau) on the diagonal momentum blocks only "
+                         "(pmb_blocked_contract); dense: the dense DMMA ladder with the generated operand")
     ap.add_argument("--dense-abcd", action="store_true",
                     help="store V_abcd in HBM instead of generating it in the ladder kernel")
     args = ap.parse_args()

@@ -57,6 +57,13 @@ class UegOperand(C.Structure):
                 ("k_axis", I32x4)]
 
 
+class Blocked(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("B", C.c_void_p), ("C", C.c_void_p), ("a_moff", C.c_void_p),
+                ("c_moff", C.c_void_p), ("a_koff", C.c_void_p), ("b_koff", C.c_void_p), ("tiles", C.c_void_p),
+                ("n_tiles", C.c_int32), ("n0_ext", C.c_int32), ("n1_ext", C.c_int32), ("_pad", C.c_int32),
+                ("b_n1str", C.c_int64), ("c_n1str", C.c_int64), ("alpha", C.c_double), ("beta", C.c_double)]
+
+
 _SIGS = {
     "pmb_version": (C.c_int, []),
     "pmb_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
@@ -94,6 +101,7 @@ _SIGS = {
                                       C.c_void_p]),
     "pmb_ueg_build_nz": (C.c_int, [C.POINTER(Ueg), C.c_void_p, C.c_void_p, C.c_void_p, I32x4, I32x4,
                                    C.c_void_p, C.c_void_p]),
+    "pmb_blocked_contract": (C.c_int, [C.POINTER(Blocked), C.c_void_p]),
     "pmb_synth_block": (C.c_int, [C.c_int, C.c_ulonglong, C.c_double, C.c_void_p, I32x4, I32x4, C.c_void_p,
                                   C.c_void_p]),
     "pmb_ueg_build_block": (C.c_int, [C.POINTER(Ueg), C.c_void_p, C.c_void_p, C.c_void_p, I32x4, I32x4,

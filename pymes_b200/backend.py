@@ -64,6 +64,11 @@ class GeneratedOperand:
         groups ordered (fastest first) as ``m_ord`` / ``k_ord``."""
         raise NotImplementedError
 
+    def blocked_lists(self):
+        """Block-diagonal structure of the operand as the matrix [(axis 0, axis 1), (axis 2, axis 3)]
+        for ``pmb_blocked_contract`` (see :func:`_blocked_term`), or None when the source has none."""
+        return None
+
 
 class LinearOperator:
     """Marker for objects that stand in for a tensor but are only ever APPLIED (e.g. the
@@ -522,6 +527,219 @@ def _try_gemv(out_sub, terms, out, beta):
     return out
 
 
+# Momentum-blocked evaluation of contractions whose row operand is a generated (momentum-
+# conserving) integral block: on by default, PYMES_B200_BLOCKED=0 or set_blocked(False) sends them
+# through the dense generated-operand path of pmb_contract instead (A/B runs, bench --ladder dense).
+_BLOCKED = [os.environ.get("PYMES_B200_BLOCKED", "1") != "0"]
+
+
+def set_blocked(flag):
+    old = _BLOCKED[0]
+    _BLOCKED[0] = bool(flag)
+    return old
+
+
+def blocked_enabled():
+    return _BLOCKED[0]
+
+
+def blocked_companion(t):
+    """The never-materialised twin of a STORED integral block (``UEG.eval_2b_blocks`` attaches one
+    to V_iabc / V_aibc: their compressed values are 1/v of the block), for the contractions that
+    can run momentum-blocked; None when there is none or the blocked path is switched off."""
+    return getattr(t, "_pmb_blocked", None) if _BLOCKED[0] else None
+
+
+def _column_groups(n_sub, ext, bstr, cstr):
+    """Split the column indices into (n0, n1): n0 the innermost indices that are dense and
+    unit-stride in BOTH B and C, n1 the rest flattened into one index.  Returns
+    ``(n0_ext, n1_ext, b_n1str, c_n1str)`` or None when the layouts do not allow it."""
+    idx = [ch for ch in n_sub if ext[ch] > 1]
+    if not idx:
+        return 1, 1, 0, 0
+    order = sorted(idx, key=lambda ch: (cstr[ch], ch))
+    if sorted(idx, key=lambda ch: (bstr[ch], ch)) != order:
+        return None
+    if bstr[order[0]] != 1 or cstr[order[0]] != 1:
+        return None
+    n0, i = ext[order[0]], 1
+    while i < len(order) and bstr[order[i]] == n0 and cstr[order[i]] == n0:
+        n0 *= ext[order[i]]
+        i += 1
+    if i == len(order):
+        return n0, 1, 0, 0
+    b1, c1, n1 = bstr[order[i]], cstr[order[i]], ext[order[i]]
+    i += 1
+    while i < len(order) and bstr[order[i]] == b1 * n1 and cstr[order[i]] == c1 * n1:
+        n1 *= ext[order[i]]
+        i += 1
+    if i != len(order):
+        return None
+    return n0, n1, b1, c1
+
+
+def tag_geom(t, geom):
+    """Attach the (p,q,r,s) geometry of a stored integral block to its tensor (see
+    ``model.ueg.MomentumGeom``); returns the tensor."""
+    t._pmb_geom = geom
+    return t
+
+
+def geom_of(t):
+    return getattr(t, "_pmb_geom", None) if isinstance(t, torch.Tensor) else None
+
+
+def narrow(t, dim, lo, n):
+    """``t.narrow(dim, lo, n)`` that keeps the geometry tag of a stored integral block."""
+    out = t.narrow(dim, lo, n)
+    g = geom_of(t)
+    if g is not None:
+        out._pmb_geom = g.narrow(dim, lo, n)
+    return out
+
+
+def copy_tagged(src):
+    """A copy of a stored integral block that IS the block (same values): keeps the tag."""
+    out = copy(src)
+    g = geom_of(src)
+    if g is not None:
+        out._pmb_geom = g
+    return out
+
+
+def _structured(x):
+    """Does ``x`` carry a block-diagonal momentum structure ``pmb_blocked_contract`` can use?"""
+    if isinstance(x, GeneratedOperand):
+        return x.blocked_lists() is not None
+    return geom_of(x) is not None
+
+
+def _blocked_term(out_sub, term):
+    """``(alpha, sa, S, sb, D, m_axes, k_axes)`` if this term can go to ``pmb_blocked_contract``:
+    S a momentum-structured 4-index operand (a generated block with block lists, or a stored
+    block with a geometry tag) with two of its indices in the output (``m_axes``, rows) and two
+    contracted with D (``k_axes``, entries); every other index of D an output index.  A generated
+    operand only in its native split (p,q | r,s).  Else None."""
+    if not _BLOCKED[0]:
+        return None
+    alpha, sa, A, sb, B = term
+    if isinstance(A, LinearOperator) or isinstance(B, LinearOperator):
+        return None
+    if not _structured(A):
+        if not _structured(B):
+            return None
+        sa, A, sb, B = sb, B, sa, A
+    if isinstance(B, GeneratedOperand):
+        return None
+    B = asdev(B)
+    if len(sa) != 4 or len(set(sa)) != 4 or len(set(sb)) != len(sb) or len(set(out_sub)) != len(out_sub):
+        return None
+    if B.dim() != len(sb) or A.dim() != 4:
+        return None
+    m_axes = tuple(i for i, ch in enumerate(sa) if ch in out_sub)
+    k_axes = tuple(i for i, ch in enumerate(sa) if ch not in out_sub)
+    if len(m_axes) != 2 or any(sa[i] in sb for i in m_axes) or any(sa[i] not in sb for i in k_axes):
+        return None
+    n_sub = [ch for ch in sb if ch not in sa]
+    if not n_sub or any(ch not in out_sub for ch in n_sub) or len(n_sub) + 2 != len(out_sub):
+        return None
+    if isinstance(A, GeneratedOperand) and (m_axes, k_axes) != ((0, 1), (2, 3)):
+        return None
+    return float(alpha), sa, A, sb, B, m_axes, k_axes
+
+
+def _run_blocked(out_sub, term, out, beta):
+    """One term through ``pmb_blocked_contract``; returns False when the operand layouts rule it
+    out (the caller then uses the dense path)."""
+    alpha, sa, A, sb, B, m_axes, k_axes = term
+    ext = dict(zip(sb, (int(n) for n in B.shape)))
+    if any(int(A.shape[i]) != ext[sa[i]] for i in k_axes):
+        raise ValueError("extent mismatch in %s,%s" % (sa, sb))
+    bstr, cstr = dict(zip(sb, B.stride())), dict(zip(out_sub, out.stride()))
+    cols = _column_groups([ch for ch in sb if ch not in sa], ext, bstr, cstr)
+    if cols is None:
+        return False
+    n0, n1, b1, c1 = cols
+    dev = device()
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    if isinstance(A, GeneratedOperand):
+        L = A.blocked_lists()
+        values, a_moff, a_koff = L["values"], L["a_moff"], L["a_koff"]
+    else:
+        L = geom_of(A).lists(m_axes, k_axes)
+        astr = A.stride()
+        akey = ("a", astr[m_axes[0]], astr[m_axes[1]], astr[k_axes[0]], astr[k_axes[1]])
+        aoffs = L["offsets"].get(akey)
+        if aoffs is None:
+            aoffs = (up(L["row_i0"] * akey[1] + L["row_i1"] * akey[2]), up(L["ent_j0"] * akey[3] + L["ent_j1"] * akey[4]))
+            L["offsets"][akey] = aoffs
+        values, (a_moff, a_koff) = A, aoffs
+    key = (cstr[sa[m_axes[0]]], cstr[sa[m_axes[1]]], bstr[sa[k_axes[0]]], bstr[sa[k_axes[1]]])
+    offs = L["offsets"].get(key)
+    if offs is None:
+        offs = (up(L["row_i0"] * key[0] + L["row_i1"] * key[1]), up(L["ent_j0"] * key[2] + L["ent_j1"] * key[3]))
+        L["offsets"][key] = offs
+    if beta == 0.0:
+        out.zero_()              # rows outside every group are part of the result: zero
+    d = _lib.Blocked()
+    d.A, d.B, d.C = values.data_ptr(), B.data_ptr(), out.data_ptr()
+    d.a_moff, d.a_koff = a_moff.data_ptr(), a_koff.data_ptr()
+    d.c_moff, d.b_koff = offs[0].data_ptr(), offs[1].data_ptr()
+    d.tiles, d.n_tiles = L["tiles"].data_ptr(), int(L["n_tiles"])
+    d.n0_ext, d.n1_ext, d.b_n1str, d.c_n1str = n0, n1, b1, c1
+    d.alpha, d.beta = alpha, float(beta)
+    trace = _timing["trace"]
+    if trace is not None:
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(torch.cuda.current_stream())
+    rc = _lib.load().pmb_blocked_contract(C.byref(d), _stream())
+    if trace is not None:
+        t1.record(torch.cuda.current_stream())
+        trace.append(("%s,%s->%s [momentum-blocked]" % (sa, sb, out_sub), 2.0 * L["nnz"] * n0 * n1, t0, t1))
+    _lib.check(rc, "pmb_blocked_contract")
+    return True
+
+
+def _try_blocked(out_sub, terms, out, beta):
+    """Terms with a momentum-structured operand (``_blocked_term``: a generated integral block or a
+    stored one with a geometry tag) are
+    evaluated by ``pmb_blocked_contract`` on the diagonal blocks only; the other terms of the same
+    call (e.g. the hole-hole ladder next to the particle-particle one, ccd.py:185-187) keep the
+    dense kernel.  Returns the result, or None when no term qualifies."""
+    picked = [(i, _blocked_term(out_sub, t)) for i, t in enumerate(terms)]
+    picked = [(i, t) for i, t in picked if t is not None]
+    if not picked:
+        return None
+    if out is None:
+        if beta != 0.0:
+            raise ValueError("beta != 0 needs an output tensor")
+        alpha, sa, A, sb, B, m_axes, _k = picked[0][1]
+        ext = dict(zip(sb, B.shape))
+        ext.update((sa[i], A.shape[i]) for i in m_axes)
+        out = zeros(*[int(ext[ch]) for ch in out_sub])
+        beta = 1.0               # fresh zeros: nothing to clear again
+    elif out.device != device():
+        raise RuntimeError("pymes_b200: output tensor lives on %s, the kernels write to %s "
+                           "(there is no CPU fallback)" % (out.device, device()))
+    done = set()
+    rest = [t for i, t in enumerate(terms) if i not in {j for j, _ in picked}]
+    if rest:
+        contract_terms(out_sub, rest, out=out, beta=beta)
+        beta = 1.0
+    for i, t in picked:
+        if _run_blocked(out_sub, t, out, beta):
+            done.add(i)
+            beta = 1.0
+    left = [terms[i] for i, _ in picked if i not in done]
+    if left:
+        old = set_blocked(False)
+        try:
+            contract_terms(out_sub, left, out=out, beta=beta)
+        finally:
+            set_blocked(old)
+    return out
+
+
 def contract_terms(out_sub, terms, out=None, beta=0.0):
     """out[out_sub] = beta*out + sum_t alpha_t * einsum(subA_t, subB_t -> out_sub).
 
@@ -535,6 +753,9 @@ def contract_terms(out_sub, terms, out=None, beta=0.0):
         raise RuntimeError("pymes_b200: output tensor lives on %s, the kernels write to %s "
                            "(there is no CPU fallback)" % (out.device, device()))
     res = _try_gemv(out_sub, terms, out, beta)
+    if res is not None:
+        return res
+    res = _try_blocked(out_sub, terms, out, beta)
     if res is not None:
         return res
     d, out, _operands = describe_contraction(out_sub, terms, out, beta)

@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libpymes_b200.so")
 STAMP = os.path.join(PKG, ".libpymes_b200.stamp")
 
-SOURCES = ["cc_contract.cu", "cc_elementwise.cu", "ueg_build.cu", "synth_build.cu", "c_api.cu"]
+SOURCES = ["cc_contract.cu", "cc_blocked.cu", "cc_elementwise.cu", "ueg_build.cu", "synth_build.cu", "c_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
               "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 

@@ -383,7 +383,12 @@ class UEG:
             if key in virtual:
                 out[key] = self.virtual_block(lo, ext, W0a=W0a, W1a=W1a, W0s=W0s)
             else:
-                out[key] = self.build_block(lo, ext, W0a=W0a, W1a=W1a, W0s=W0s, out=pre.get(key))
+                out[key] = bk.tag_geom(self.build_block(lo, ext, W0a=W0a, W1a=W1a, W0s=W0s, out=pre.get(key)),
+                                       MomentumGeom(self, lo, ext))
+                if key in BLOCKED_COMPANIONS:
+                    # stored AND available as compressed values (1/v of the block): V.tau of the
+                    # T1 dressing runs momentum-blocked (solver.ccsd.pair_with_tau)
+                    out[key]._pmb_blocked = self.virtual_block(lo, ext, W0a=W0a, W1a=W1a, W0s=W0s)
         return out
 
     # ------------------------------------------------- 3-body mean-field parts
@@ -508,6 +513,94 @@ class UEG:
         return -np.divide(4 * np.pi, k2 ** 2, out=np.zeros_like(k2), where=(k2 >= kc2))
 
 
+SIGNS = (1, 1, -1, -1)            # <pq|rs>: l(k_p) + l(k_q) - l(k_r) - l(k_s) = 0
+
+
+def momentum_groups(k_int, imax, lo, ext, m_axes=(0, 1), k_axes=(2, 3)):
+    """Block-diagonal structure of V[lo:lo+ext] as the matrix [rows, entries], rows = the two
+    axes ``m_axes`` of (p,q,r,s), entries = the other two (``k_axes``).  The reference finds
+    the one s of a (p,q,r) by looking up the LINEARISED vector k_q - (k_r - k_p) in its index map
+    (ueg.py:395-404: loc = n^2 (x + imax) + n (y + imax) + z + imax, n = 2 imax + 1, only the range
+    of loc is checked, not that of the components), so an element can be non-zero exactly where
+    l(k_p) + l(k_q) = l(k_r) + l(k_s) with l(k) = n^2 x + n y + z: the momentum-conserving
+    elements and the few aliased ones the reference produces as well (a component beyond imax
+    carries into the next digit).  With signs (+,+,-,-) for (p,q,r,s), a row and an entry can
+    meet where  sum_rows sign.l = - sum_entries sign.l ; rows and entries with the same key form a
+    group.  Returns ``(row_ord, ent_ord, g_row0, g_rows, g_ent0, g_ents)``: the permutations
+    that sort the rows i0*ext[m1]+i1 / the entries j0*ext[k1]+j1 by group (stable: index order
+    inside a group) and, per group present on BOTH sides, its first position and length in the two
+    sorted lists.  ``(g_rows * g_ents).sum()`` is the number of candidate non-zeros (54e / 515
+    plane waves, V_abcd: 3.3e7 of 5.7e10)."""
+    if sorted(tuple(m_axes) + tuple(k_axes)) != [0, 1, 2, 3]:
+        raise ValueError("row and entry axes must split (p,q,r,s)")
+    k = np.asarray(k_int).astype(np.int64)
+    n = 2 * int(imax) + 1
+    lin = n * n * k[:, 0] + n * k[:, 1] + k[:, 2]
+    l = [SIGNS[ax] * lin[lo[ax]:lo[ax] + ext[ax]] for ax in range(4)]
+    row_key = (l[m_axes[0]][:, None] + l[m_axes[1]][None, :]).reshape(-1)
+    ent_key = -(l[k_axes[0]][:, None] + l[k_axes[1]][None, :]).reshape(-1)
+    row_ord = np.argsort(row_key, kind="stable")
+    ent_ord = np.argsort(ent_key, kind="stable")
+    rk, r_first, r_cnt = np.unique(row_key[row_ord], return_index=True, return_counts=True)
+    ek, e_first, e_cnt = np.unique(ent_key[ent_ord], return_index=True, return_counts=True)
+    _common, ri, ei = np.intersect1d(rk, ek, assume_unique=True, return_indices=True)
+    return row_ord, ent_ord, r_first[ri], r_cnt[ri], e_first[ei], e_cnt[ei]
+
+
+def blocked_tiles(g_first, g_cnt, g_e0, g_en, tile_rows=64):
+    """Row tiles of ``pmb_blocked_contract``: every group's rows in equal pieces of whole 8-row
+    fragments, at most ``tile_rows`` each; {first row, rows, first entry, entries} per tile,
+    long groups first."""
+    pieces = -(-g_cnt // tile_rows)
+    size = -(-g_cnt // np.maximum(pieces, 1))
+    size = np.minimum(-(-size // 8) * 8, tile_rows)
+    pieces = -(-g_cnt // np.maximum(size, 1))
+    grp = np.repeat(np.arange(len(g_cnt)), pieces)
+    within = np.arange(len(grp)) - np.repeat(np.cumsum(pieces) - pieces, pieces)
+    t_m0 = g_first[grp] + within * size[grp]
+    t_mn = np.minimum(size[grp], g_cnt[grp] - within * size[grp])
+    tiles = np.stack([t_m0, t_mn, g_e0[grp], g_en[grp]], axis=1).astype(np.int32)
+    return np.ascontiguousarray(tiles[np.argsort(-tiles[:, 3], kind="stable")])
+
+
+class MomentumGeom:
+    """Where a STORED integral block sits in (p,q,r,s) orbital space: attached to the tensors
+    ``UEG.eval_2b_blocks`` returns (``backend.tag_geom``) so that contractions whose structured
+    operand is such a block can run on its diagonal momentum blocks (``pmb_blocked_contract``).
+    The structure is a property of the integral generator -- nothing is assumed about amplitudes."""
+
+    def __init__(self, model, lo, ext):
+        self.model, self.lo, self.ext = model, tuple(int(x) for x in lo), tuple(int(x) for x in ext)
+        self._lists = {}
+
+    def narrow(self, dim, lo, n):
+        new_lo, new_ext = list(self.lo), list(self.ext)
+        new_lo[dim] += int(lo)
+        new_ext[dim] = int(n)
+        return MomentumGeom(self.model, new_lo, new_ext)
+
+    def lists(self, m_axes=(0, 1), k_axes=(2, 3)):
+        """Host lists (numpy int64 index pairs of the rows / entries, sorted by group), the device
+        tile table and a cache for the offset tables derived from them."""
+        key = (tuple(m_axes), tuple(k_axes))
+        L = self._lists.get(key)
+        if L is None:
+            ext = self.ext
+            row_ord, ent_ord, g_first, g_cnt, g_e0, g_en = momentum_groups(
+                self.model.k_int(), self.model.imax, self.lo, ext, m_axes, k_axes)
+            tiles = blocked_tiles(g_first, g_cnt, g_e0, g_en)
+            L = dict(row_i0=(row_ord // ext[m_axes[1]]).astype(np.int64), row_i1=(row_ord % ext[m_axes[1]]).astype(np.int64),
+                     ent_j0=(ent_ord // ext[k_axes[1]]).astype(np.int64), ent_j1=(ent_ord % ext[k_axes[1]]).astype(np.int64),
+                     tiles=torch.from_numpy(tiles).to(bk.device()), n_tiles=len(tiles),
+                     nnz=int((g_cnt * g_en).sum()), n_groups=len(g_cnt), offsets={})
+            self._lists[key] = L
+        return L
+
+
+# stored blocks that also get a never-materialised twin (``backend.blocked_companion``)
+BLOCKED_COMPANIONS = ("iabc", "aibc")
+
+
 class VirtualBlock(bk.GeneratedOperand):
     """Sub-block ``V[lo:lo+ext]`` of the UEG integrals that exists only as its pair tables
     (``include/pymes_b200.h: pmb_ueg_operand_t``).  Usable as the row operand of a
@@ -550,6 +643,25 @@ class VirtualBlock(bk.GeneratedOperand):
             cache[key] = VirtualBlock(self.model, new_lo, new_ext, *self.tables, compressed=self.compressed,
                                       _packed=True)
         return cache[key]
+
+    def blocked_lists(self):
+        """The block as the matrix [(p,q),(r,s)] is block diagonal in the (linearised) total
+        momentum, see :func:`momentum_groups` (ueg.py:395-404).  Returns the lists of
+        :meth:`MomentumGeom.lists` plus the operand side of ``pmb_blocked_contract``: the compressed
+        values ``nz[p,q,r]`` and the row / entry offsets into them (the s index is implied by the
+        group).  Needs the compressed values; None otherwise."""
+        if self.nz is None:
+            return None
+        L = self.__dict__.get("_blocked")
+        if L is None:
+            geom = self.__dict__.setdefault("_geom", MomentumGeom(self.model, self.lo, self.shape))
+            L = dict(geom.lists((0, 1), (2, 3)))
+            ext, dev = self.shape, bk.device()
+            L["values"] = self.nz
+            L["a_moff"] = torch.from_numpy((L["row_i0"] * ext[1] + L["row_i1"]) * ext[2]).to(dev)
+            L["a_koff"] = torch.from_numpy(L["ent_j0"].copy()).to(dev)
+            self.__dict__["_blocked"] = L
+        return L
 
     def diag_pqpq(self):
         """D[p,q] = V[p,q,p,q] (the ``einsum("abab->ab")`` of eom_ccsd.py:262) without the dense

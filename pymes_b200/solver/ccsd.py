@@ -137,7 +137,8 @@ def dressed_fock(no, fock, T1, dV, shared=None):
 def dressed_block(key, T1, dV, skip_tau=False, shared=None):
     """One T1-dressed V block from the undressed dictionary.  ccsd.py:322-419.  ``shared``: the
     result of :func:`t1_shared` (needed by "iajb" / "iabj"; computed here when not given)."""
-    blk = bk.copy(dV[key])
+    # a block without dressing terms (V_ijab) IS the stored block: its copy keeps the geometry tag
+    blk = bk.copy(dV[key]) if V_TERMS[key] else bk.copy_tagged(dV[key])
     for coef, spec, source, is_tau in V_TERMS[key]:
         if skip_tau and is_tau:
             continue
@@ -180,6 +181,11 @@ def pair_with_tau(V_iabc, V_aibc, tau, no):
     ct = bk.contract_terms
     nv = tau.shape[0]
     nb = V_iabc.shape[1]
+    ca, cb = bk.blocked_companion(V_iabc), bk.blocked_companion(V_aibc)
+    if ca is not None and cb is not None:
+        # momentum-conserving blocks: only the diagonal blocks of [(k,b),(c,d)] / [(a,l),(c,d)]
+        # are visited (pmb_blocked_contract), from 1/v of the stored values
+        return (ct("kbij", [(1.0, "kbcd", ca, "cdij", tau)]), ct("alij", [(1.0, "alcd", cb, "cdij", tau)]))
     st = bk.stacked_rows(V_iabc, V_aibc, (nv, nv))
     if st is not None:
         W = bk.empty(2, no * nb, no, no)
@@ -238,8 +244,12 @@ class DressedLadder(bk.LinearOperator):
             V = self.V_abcd
             Va = V.rows(0, shard.lo, shard.na) if isinstance(V, bk.GeneratedOperand) else shard.rows(V, 0)
             Vaibc, T1a = shard.rows(self.V_aibc, 0), shard.rows(T1, 0)
+        # stored o.v^3 blocks with a never-materialised twin go momentum-blocked as well
+        ca, cb = bk.blocked_companion(self.V_iabc), bk.blocked_companion(self.V_aibc)
+        if cb is not None:
+            Vaibc = cb if shard is None else cb.rows(0, shard.lo, shard.na)
         ct(r + "abij", [(coef, "abcd", Va, r + "cdij", U)], out=out, beta=1.0)
-        W1 = ct(r + "kbij", [(1.0, "kbcd", self.V_iabc, r + "cdij", U)])
+        W1 = ct(r + "kbij", [(1.0, "kbcd", self.V_iabc if ca is None else ca, r + "cdij", U)])
         ct(r + "abij", [(-coef, "ak", T1a, r + "kbij", W1)], out=out, beta=1.0)
         del W1
         W2 = ct(r + "alij", [(1.0, "alcd", Vaibc, r + "cdij", U)])

@@ -338,6 +338,35 @@ class FakeLib:
             _window(_val(W1), nP * nP)[:] = w1.reshape(-1)
         return 0
 
+    def pmb_blocked_contract(self, dref, stream):
+        """Block-diagonal contraction, exactly as the header states it: per tile, the tile's rows
+        meet the tile's entries; columns n = n1 * n0_ext + n0."""
+        d = dref._obj
+        self.launches += 1
+        if d.n_tiles == 0:
+            return 0
+        ints = lambda ptr, n, ct: np.ctypeslib.as_array((ct * n).from_address(ptr))
+        tiles = ints(d.tiles, 4 * d.n_tiles, C.c_int32).reshape(-1, 4)
+        assert tiles[:, 1].min() >= 1 and tiles[:, 1].max() <= 64 and tiles[:, 3].min() >= 1
+        n_rows = int((tiles[:, 0] + tiles[:, 1]).max())
+        n_ent = int((tiles[:, 2] + tiles[:, 3]).max())
+        a_moff, c_moff = ints(d.a_moff, n_rows, C.c_int64), ints(d.c_moff, n_rows, C.c_int64)
+        a_koff, b_koff = ints(d.a_koff, n_ent, C.c_int64), ints(d.b_koff, n_ent, C.c_int64)
+        n = np.arange(d.n0_ext * d.n1_ext, dtype=np.int64)
+        bn = (n // d.n0_ext) * d.b_n1str + n % d.n0_ext
+        cn = (n // d.n0_ext) * d.c_n1str + n % d.n0_ext
+        seen = np.zeros(n_rows, dtype=bool)
+        for m0, mn, k0, kn in tiles:
+            assert not seen[m0:m0 + mn].any(), "a row belongs to two tiles"
+            seen[m0:m0 + mn] = True
+            A, _, _ = _gather(d.A, (a_moff[m0:m0 + mn, None] + a_koff[None, k0:k0 + kn]).reshape(-1))
+            B, _, _ = _gather(d.B, (b_koff[k0:k0 + kn, None] + bn[None, :]).reshape(-1))
+            offs = (c_moff[m0:m0 + mn, None] + cn[None, :]).reshape(-1)
+            old, win, lo = _gather(d.C, offs)
+            val = d.alpha * (A.reshape(mn, kn) @ B.reshape(kn, -1)).reshape(-1)
+            win[offs - lo] = val + (d.beta * old if d.beta != 0.0 else 0.0)
+        return 0
+
     def _generated(self, addr, m_ext, k_ext):
         """A[M,K] of a generated operand (pmb_ueg_operand_t): the block pmb_ueg_build_block
         would write, with its axes arranged as the M / K index groups (first listed fastest)."""

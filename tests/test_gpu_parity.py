@@ -433,6 +433,7 @@ def test_ueg_virtual_pp_ladder_bit_identical(n_ele, cutoff):
     g = torch.Generator(device="cuda").manual_seed(1)
     tau = torch.randn(nv, nv, no, no, dtype=torch.float64, device="cuda", generator=g)
     lib = _lib.load()
+    blocked_was = bk.set_blocked(False)      # this test is about the DENSE generated-operand path
     # +64: the tail wave is left alone.  A generated operand rasters the tiles m-fastest, a stored one
     # n-fastest, so a tail launch (54e / 93 plane waves: 210 tiles = 148 + 62) would k-split DIFFERENT
     # tiles in the two runs: equal to round-off then, not bit for bit (checked right below)
@@ -473,6 +474,23 @@ def test_ueg_virtual_pp_ladder_bit_identical(n_ele, cutoff):
         assert torch.equal(bk.contract("abcd,abij->cdij", raw, tau), bk.contract("abcd,abij->cdij", dense, tau))
     finally:
         lib.pmb_contract_set_tuning(-1, 0)
+        bk.set_blocked(blocked_was)
+    _virtual_ladder_default_checks(m, no, nv, virt, dense, tau, g, blocked=False)
+    _virtual_ladder_default_checks(m, no, nv, virt, dense, tau, g, blocked=True)
+
+
+def _virtual_ladder_default_checks(m, no, nv, virt, dense, tau, g, blocked):
+    """Default heuristics, dense generated operand (blocked=False) or the momentum-blocked kernel."""
+    from pymes_b200 import backend as bk
+    blocked_was = bk.set_blocked(blocked)
+    try:
+        _virtual_ladder_default_checks_body(m, no, nv, virt, dense, tau, g)
+    finally:
+        bk.set_blocked(blocked_was)
+
+
+def _virtual_ladder_default_checks_body(m, no, nv, virt, dense, tau, g):
+    from pymes_b200 import backend as bk
     # default heuristics (the dense block may pick another tile shape): round-off only
     ref = bk.contract("abcd,cdij->abij", dense, tau)
     got = bk.contract("abcd,cdij->abij", virt, tau)
@@ -491,6 +509,112 @@ def test_ueg_virtual_pp_ladder_bit_identical(n_ele, cutoff):
     bk.contract_terms("abij", [(1.0, "klij", I, "abkl", taul), (0.5, "abcd", dense[lo:lo + na], "cdij", tau)],
                       out=Rb, beta=1.0)
     assert _rel(Ra.cpu().numpy(), Rb.cpu().numpy()) < 1e-13
+
+
+@pytest.mark.parametrize("n_ele,cutoff", [(14, 5.0), (14, 9.0), (54, 7.0), (54, 10.0)])
+def test_momentum_blocked_contractions(n_ele, cutoff):
+    """pmb_blocked_contract (momentum-blocked path): the pp ladder and the two o.v^3
+    products of the T1 dressing on the diagonal momentum blocks only, against (i) the dense
+    generated-operand kernel, (ii) numpy on the materialised block; even-pitch tau, accumulation,
+    fresh output (rows without a group are zeros), batched right-hand sides, a row block, and the
+    executed flop count 2 nnz o^2.  54e / 147 plane waves: groups of up to 120 rows (two tiles)."""
+    from pymes_b200 import backend as bk
+    m = _tc_model(n_ele, cutoff)
+    no, nP = n_ele // 2, m.n_orb
+    nv = nP - no
+    parts = [("only_2b", m.trunc), ("effect_2b", m.trunc)]
+    blocks = m.eval_2b_blocks(no, ["abcd", "iabc", "aibc"], parts, virtual=("abcd",))
+    virt = blocks["abcd"]
+    L = virt.blocked_lists()
+    dense = virt.materialise()
+    assert L["nnz"] >= int((dense != 0).sum()) > 0 and L["nnz"] < dense.numel() // 4
+    g = torch.Generator(device="cuda").manual_seed(2)
+    rnd = lambda *s: torch.randn(*s, dtype=torch.float64, device="cuda", generator=g)
+    tau = bk.empty_even_pitch(nv, nv, no)
+    tau.copy_(rnd(nv, nv, no, no))
+    assert bk.blocked_enabled()
+    n0 = bk.launch_count()
+    got = bk.contract("abcd,cdij->abij", virt, tau)
+    assert bk.launch_count() - n0 == 1
+    old = bk.set_blocked(False)
+    try:
+        ref = bk.contract("abcd,cdij->abij", virt, tau)
+    finally:
+        bk.set_blocked(old)
+    assert _rel(got.cpu().numpy(), ref.cpu().numpy()) < 1e-13
+    # (the checker's products run as cuBLAS DGEMMs through torch: 3e11 flop each at 147 plane waves)
+    D2 = dense.reshape(nv * nv, nv * nv)
+    want = (D2 @ tau.reshape(nv * nv, -1)).cpu().numpy()
+    assert _rel(got.cpu().numpy().reshape(nv * nv, -1), want) < 1e-13
+    # fresh output over junk; accumulation with a coefficient
+    junk = rnd(nv, nv, no, no)
+    bk.contract("abcd,cdij->abij", virt, tau, out=junk)
+    assert torch.equal(junk, got)
+    R0 = rnd(nv, nv, no, no)
+    R = R0.clone()
+    bk.contract_terms("abij", [(-0.3, "abcd", virt, "cdij", tau)], out=R, beta=1.0)
+    assert _rel(R.cpu().numpy(), R0.cpu().numpy() - 0.3 * want.reshape(nv, nv, no, no)) < 1e-13
+    # batched right-hand sides (EOM sigma), row block
+    r = 3
+    U = rnd(r, nv, nv, no, no)
+    S = bk.contract_terms("rabij", [(1.0, "abcd", virt, "rcdij", U)])
+    wantU = torch.stack([D2 @ U[k].reshape(nv * nv, -1) for k in range(r)]).cpu().numpy()
+    assert _rel(S.cpu().numpy().reshape(r, nv * nv, -1), wantU) < 1e-13
+    lo, na = nv // 3, nv - nv // 3 - 1
+    part = bk.contract("abcd,cdij->abij", virt.rows(0, lo, na), tau)
+    assert torch.equal(part, got[lo:lo + na])
+    # the stored o.v^3 blocks carry a never-materialised twin: V_iabc.tau / V_aibc.tau
+    from pymes_b200.solver import ccsd
+    assert bk.blocked_companion(blocks["iabc"]) is not None and bk.blocked_companion(blocks["aibc"]) is not None
+    n0 = bk.launch_count()
+    W1, W2 = ccsd.pair_with_tau(blocks["iabc"], blocks["aibc"], tau, no)
+    assert bk.launch_count() - n0 == 2
+    old = bk.set_blocked(False)
+    try:
+        W1d, W2d = ccsd.pair_with_tau(blocks["iabc"], blocks["aibc"], tau, no)
+    finally:
+        bk.set_blocked(old)
+    assert _rel(W1.cpu().numpy(), W1d.cpu().numpy()) < 1e-13 and _rel(W2.cpu().numpy(), W2d.cpu().numpy()) < 1e-13
+    w1 = (blocks["iabc"].reshape(no * nv, -1) @ tau.reshape(nv * nv, -1)).cpu().numpy()
+    assert _rel(W1.cpu().numpy().reshape(no * nv, -1), w1) < 1e-13
+
+
+def test_momentum_blocked_ladder_long_groups():
+    """A group longer than the kernel's 512-entry offset window (several table refills per CTA) and
+    more than 64 rows per group: a synthetic block-diagonal operand driven through the C ABI
+    directly, against numpy."""
+    import ctypes as C
+    from pymes_b200 import _lib, backend as bk
+    rng = np.random.default_rng(11)
+    groups = [(130, 1100), (64, 513), (1, 1), (7, 40), (65, 16)]          # (rows, entries)
+    n0e, n1e = 45, 3
+    n_rows, n_ent = sum(g[0] for g in groups), sum(g[1] for g in groups)
+    A = rng.standard_normal((n_rows, 1100))                                 # A[row, local entry]
+    B = rng.standard_normal((n_ent, n1e, n0e + 3))                          # padded pitch
+    Cm = rng.standard_normal((n_rows, n1e, n0e))
+    perm = rng.permutation(n_rows)                                          # rows scattered in C
+    tiles, want = [], Cm.copy()
+    a_koff, r0, e0 = np.zeros(n_ent, dtype=np.int64), 0, 0
+    for nr, ne in groups:
+        a_koff[e0:e0 + ne] = np.arange(ne)
+        for t in range(0, nr, 64):
+            tiles.append((r0 + t, min(64, nr - t), e0, ne))
+        blk = A[r0:r0 + nr, :ne] @ B[e0:e0 + ne, :, :n0e].reshape(ne, -1)
+        want[perm[r0:r0 + nr]] = 0.5 * want[perm[r0:r0 + nr]] - 1.5 * blk.reshape(nr, n1e, n0e)
+        r0, e0 = r0 + nr, e0 + ne
+    dev = bk.device()
+    tt = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    Ad, Bd, Cd = tt(A), tt(B), tt(Cm)
+    tabs = [tt(np.arange(n_rows, dtype=np.int64) * 1100), tt(perm.astype(np.int64) * n1e * n0e), tt(a_koff),
+            tt(np.arange(n_ent, dtype=np.int64) * n1e * (n0e + 3)), tt(np.array(tiles, dtype=np.int32))]
+    d = _lib.Blocked()
+    d.A, d.B, d.C = Ad.data_ptr(), Bd.data_ptr(), Cd.data_ptr()
+    d.a_moff, d.c_moff, d.a_koff, d.b_koff, d.tiles = (t.data_ptr() for t in tabs)
+    d.n_tiles, d.n0_ext, d.n1_ext, d.b_n1str, d.c_n1str = len(tiles), n0e, n1e, n0e + 3, n0e
+    d.alpha, d.beta = -1.5, 0.5
+    _lib.check(_lib.load().pmb_blocked_contract(C.byref(d), bk._stream()), "pmb_blocked_contract")
+    torch.cuda.synchronize()
+    assert _rel(Cd.cpu().numpy(), want) < 1e-13
 
 
 def test_ueg_virtual_abcd_ccsd_matches_dense():

@@ -968,3 +968,201 @@ def test_stacked_rows_and_even_pitch_helpers(cpu_abi):
         t = bk.empty_even_pitch(5, 6, o)
         assert tuple(t.shape) == (5, 6, o, o) and t.stride(1) % 2 == 0 and t.stride(3) == 1 and t.stride(2) == o
         assert t.stride(1) == o * o + (o * o) % 2
+
+
+def test_momentum_blocked_contraction_host_logic(cpu_abi):
+    """``pmb_blocked_contract`` dispatch (the momentum-blocked path): the group /
+    tile lists of a VirtualBlock, the offset tables for several operand layouts (even-pitch tau,
+    batched right-hand sides, a row block, the o.v^3 pattern), the mixed call with a dense term,
+    beta = 0 on rows without any group, and the switch back to the dense generated-operand path."""
+    from pymes_b200 import backend as bk
+    from pymes_b200.model import ueg
+    m = ueg.UEG(14, 7, 7, 0.5)
+    m.init_single_basis(2.0)
+    m.gamma, m.k_cutoff = None, 1.0
+    nP, no = m.n_orb, 7
+    nv = nP - no
+    W0a, W1a = m.pair_tables("only_non_hermi_2b", m.trunc)
+    W0s, _ = m.pair_tables("effect_2b", m.trunc)
+    rng = np.random.default_rng(5)
+    virt = m.virtual_block((no,) * 4, (nv,) * 4, W0a=W0a, W1a=W1a, W0s=W0s)
+    dense = _n(virt.materialise())
+    L = virt.blocked_lists()
+    # the lists describe exactly the non-zero structure of the dense block
+    assert L["nnz"] >= np.count_nonzero(dense) > 0
+    tiles = _n(L["tiles"])
+    assert tiles[:, 1].max() <= 64 and (np.diff(tiles[:, 3]) <= 0).all()
+    covered = np.zeros((nv * nv, nv * nv), dtype=bool)
+    rows = L["row_i0"] * nv + L["row_i1"]
+    ents = L["ent_j0"] * nv + L["ent_j1"]
+    for m0, mn, k0, kn in tiles:
+        covered[np.ix_(rows[m0:m0 + mn], ents[k0:k0 + kn])] = True
+    assert not (dense.reshape(nv * nv, -1) != 0)[~covered].any()
+    assert covered.sum() == L["nnz"]
+
+    calls = {"blocked": 0, "dense": 0}
+    blocked0, dense0 = cpu_abi.pmb_blocked_contract, cpu_abi.pmb_contract
+    cpu_abi.pmb_blocked_contract = lambda *a: (calls.__setitem__("blocked", calls["blocked"] + 1), blocked0(*a))[1]
+    cpu_abi.pmb_contract = lambda *a: (calls.__setitem__("dense", calls["dense"] + 1), dense0(*a))[1]
+
+    # even-pitch tau (the ladder's operand in ccsd.tau_ladder), accumulate into R
+    tau = bk.empty_even_pitch(nv, nv, no)
+    tau.copy_(_t(rng.standard_normal((nv, nv, no, no))))
+    R0 = rng.standard_normal((nv, nv, no, no))
+    R = _t(R0.copy())
+    bk.contract_terms("abij", [(0.7, "abcd", virt, "cdij", tau)], out=R, beta=1.0)
+    np.testing.assert_allclose(_n(R), R0 + 0.7 * np.einsum("abcd,cdij->abij", dense, _n(tau)), rtol=0, atol=1e-13)
+    assert calls == {"blocked": 1, "dense": 0}
+    # fresh output (beta = 0): rows of momentum groups without entries come out as zeros
+    got = bk.contract("abcd,cdij->abij", virt, tau)
+    np.testing.assert_allclose(_n(got), np.einsum("abcd,cdij->abij", dense, _n(tau)), rtol=0, atol=1e-13)
+    junk = _t(rng.standard_normal((nv, nv, no, no)))
+    bk.contract("abcd,cdij->abij", virt, tau, out=junk)
+    np.testing.assert_allclose(_n(junk), _n(got), rtol=0, atol=0)
+    assert calls == {"blocked": 3, "dense": 0}
+    # batched right-hand sides (EOM sigma, ccsd.DressedLadder.apply)
+    U = _t(rng.standard_normal((3, nv, nv, no, no)))
+    S = _t(np.zeros((3, nv, nv, no, no)))
+    bk.contract_terms("rabij", [(-1.0, "abcd", virt, "rcdij", U)], out=S, beta=1.0)
+    np.testing.assert_allclose(_n(S), -np.einsum("abcd,rcdij->rabij", dense, _n(U)), rtol=0, atol=1e-13)
+    assert calls == {"blocked": 4, "dense": 0}
+    # a row block (one rank of a sharded run) and the o.v^3 pattern with an occupied row index
+    part = virt.rows(0, 2, 3)
+    got = bk.contract("abcd,cdij->abij", part, tau)
+    np.testing.assert_allclose(_n(got), np.einsum("abcd,cdij->abij", dense[2:5], _n(tau)), rtol=0, atol=1e-13)
+    v2 = m.virtual_block((0, no, no, no), (no, nv, nv, nv), W0a=W0a, W1a=W1a, W0s=W0s)
+    got = bk.contract("kbcd,cdij->kbij", v2, tau)
+    np.testing.assert_allclose(_n(got), np.einsum("kbcd,cdij->kbij", _n(v2.materialise()), _n(tau)),
+                               rtol=0, atol=1e-13)
+    v3 = m.virtual_block((no, 0, no, no), (nv, no, nv, nv), W0a=W0a, W1a=W1a, W0s=W0s)
+    got = bk.contract("alcd,cdij->alij", v3, tau)
+    np.testing.assert_allclose(_n(got), np.einsum("alcd,cdij->alij", _n(v3.materialise()), _n(tau)),
+                               rtol=0, atol=1e-13)
+    assert calls == {"blocked": 7, "dense": 0}
+    # mixed call: the hole-hole ladder keeps the dense kernel, the pp ladder is blocked (ccd.py:185-187)
+    I = _t(rng.standard_normal((no, no, no, no)))
+    T2 = _t(rng.standard_normal((nv, nv, no, no)))
+    R = _t(R0.copy())
+    bk.contract_terms("abij", [(1.0, "abkl", T2, "klij", I), (1.0, "abcd", virt, "cdij", T2)], out=R, beta=1.0)
+    want = R0 + np.einsum("abkl,klij->abij", _n(T2), _n(I)) + np.einsum("abcd,cdij->abij", dense, _n(T2))
+    np.testing.assert_allclose(_n(R), want, rtol=0, atol=1e-13)
+    assert calls == {"blocked": 8, "dense": 1}
+    # a column layout the blocked kernel does not take (output with (i,j) outermost): dense path
+    outp = bk.empty(no, no, nv, nv).permute(2, 3, 0, 1)
+    bk.contract("abcd,cdij->abij", virt, tau, out=outp)
+    np.testing.assert_allclose(_n(outp), np.einsum("abcd,cdij->abij", dense, _n(tau)), rtol=0, atol=1e-13)
+    assert calls == {"blocked": 8, "dense": 2}
+    # switched off: the generated-operand path of pmb_contract
+    old = bk.set_blocked(False)
+    try:
+        got = bk.contract("abcd,cdij->abij", virt, tau)
+    finally:
+        bk.set_blocked(old)
+    np.testing.assert_allclose(_n(got), np.einsum("abcd,cdij->abij", dense, _n(tau)), rtol=0, atol=1e-13)
+    assert calls == {"blocked": 8, "dense": 3} and bk.blocked_enabled()
+    # an operand without compressed values has no lists
+    raw = m.virtual_block((no,) * 4, (nv,) * 4, W0a=W0a, W1a=W1a, W0s=W0s, compressed=False)
+    assert raw.blocked_lists() is None
+    bk.contract("abcd,cdij->abij", raw, tau)
+    assert calls == {"blocked": 8, "dense": 4}
+
+
+def test_momentum_groups_follow_the_reference_index_lookup():
+    """The groups of ``momentum_groups`` are exactly the (p,q,r,s) the reference's index lookup can
+    hit (ueg.py:395-404), ALIASED vectors included: at 54e / 147 plane waves k_p + k_q - k_r has
+    components beyond imax whose linearisation lands on another basis vector, and the reference's
+    V is non-zero there too (it only range-checks the linear index)."""
+    from pymes_b200.model import ueg
+    m = ueg.UEG(54, 27, 27, 0.5)
+    m.init_single_basis(10.0)
+    no, nP = 27, m.n_orb
+    nv = nP - no
+    k = m.k_int().astype(np.int64)
+    n = 2 * m.imax + 1
+    for lo, ext in (((no,) * 4, (nv,) * 4), ((0, no, no, no), (no, nv, nv, nv)), ((no + 5, 0, no, no), (40, no, nv, nv))):
+        row_ord, ent_ord, g_r0, g_rn, g_e0, g_en = ueg.momentum_groups(k, m.imax, lo, ext)
+        # the reference's lookup, vectorised: s*(p,q,r) or -1
+        P, Q, R = (np.arange(lo[d], lo[d] + ext[d]) for d in range(3))
+        v = k[Q][None, :, None, :] - (k[R][None, None, :, :] - k[P][:, None, None, :]) + m.imax
+        loc = n * n * v[..., 0] + n * v[..., 1] + v[..., 2]
+        ok = (loc >= 0) & (loc < n ** 3)
+        s = np.where(ok, m.basis_indices_map[np.clip(loc, 0, n ** 3 - 1)], -1)
+        s = np.where((s >= lo[3]) & (s < lo[3] + ext[3]), s - lo[3], -1)
+        true_momentum = (np.abs(v - m.imax).max(axis=-1) <= m.imax) | (s < 0)
+        if lo == (no,) * 4:
+            assert not true_momentum.all()            # this basis does have aliased hits
+        # group id of every row / entry (-1: group absent on the other side)
+        row_gid = -np.ones(ext[0] * ext[1], dtype=np.int64)
+        ent_gid = -np.ones(ext[2] * ext[3], dtype=np.int64)
+        for g in range(len(g_rn)):
+            row_gid[row_ord[g_r0[g]:g_r0[g] + g_rn[g]]] = g
+            ent_gid[ent_ord[g_e0[g]:g_e0[g] + g_en[g]]] = g
+        hit = s >= 0
+        pi, qi, ri = np.nonzero(hit)
+        rows = pi * ext[1] + qi
+        ents = ri * ext[3] + s[hit]
+        assert (row_gid[rows] >= 0).all() and (row_gid[rows] == ent_gid[ents]).all()
+        assert int((g_rn * g_en).sum()) == int(hit.sum())      # and nothing else is visited
+
+
+def test_momentum_blocked_stored_blocks_host_logic(cpu_abi):
+    """Stored integral blocks carry a geometry tag (``UEG.eval_2b_blocks``): contractions that split
+    their four indices 2 + 2 between output and sum run on the diagonal momentum blocks for ANY
+    such split (the ring-type products of ccd.py:189-204,233-240 with V_ijab / V_iajb), including
+    narrowed row blocks; patterns the blocked kernel cannot take stay on the dense kernel."""
+    from pymes_b200 import backend as bk
+    from pymes_b200.model import ueg
+    from pymes_b200.solver import ccsd
+    m = ueg.UEG(14, 7, 7, 0.5)
+    m.init_single_basis(2.0)
+    m.gamma, m.k_cutoff = None, 1.0
+    nP, no = m.n_orb, 7
+    nv = nP - no
+    parts = [("only_non_hermi_2b", m.trunc), ("effect_2b", m.trunc)]
+    dV = m.eval_2b_blocks(no, ["ijab", "iajb", "iabj", "klij", "abic"], parts)
+    assert all(bk.geom_of(v) is not None for v in dV.values())
+    rng = np.random.default_rng(9)
+    T = _t(rng.standard_normal((nv, nv, no, no)))
+    calls = {"blocked": 0, "dense": 0}
+    blocked0, dense0 = cpu_abi.pmb_blocked_contract, cpu_abi.pmb_contract
+    cpu_abi.pmb_blocked_contract = lambda *a: (calls.__setitem__("blocked", calls["blocked"] + 1), blocked0(*a))[1]
+    cpu_abi.pmb_contract = lambda *a: (calls.__setitem__("dense", calls["dense"] + 1), dense0(*a))[1]
+
+    def check(spec, A, B, want_blocked, **kw):
+        b0, d0 = calls["blocked"], calls["dense"]
+        got = bk.contract(spec, A, B, **kw)
+        np.testing.assert_allclose(_n(got), kw.get("alpha", 1.0) * np.einsum(spec, _n(A), _n(B)), rtol=0, atol=1e-12)
+        assert (calls["blocked"] - b0, calls["dense"] - d0) == ((1, 0) if want_blocked else (0, 1)), spec
+
+    V_ijab, V_iajb, V_iabj = dV["ijab"], dV["iajb"], dV["iabj"]
+    check("klcd,dblj->cbkj", V_ijab, T, True)                 # Xai            ccd.py:202
+    check("klcd,adkj->alcj", V_ijab, T, True)                 # X1             ccd.py:189
+    check("klcd,daki->alci", V_ijab, T, True)                 # Xp             ccd.py:238
+    check("klcd,cdij->klij", V_ijab, T, True)                 # I_klij         ccd.py:180
+    check("kaic,cbkj->abij", V_iajb, T, True, alpha=-1.0)     # ring           ccd.py:233
+    check("kbic,ackj->abij", V_iajb, T, True)                 # ring           ccd.py:234
+    check("cbkj,kaic->abij", T, V_iajb, True)                 # structured operand given second
+    # column index (a,i) with i not unit-stride in T[a,c,i,k]: the blocked kernel does not take it
+    check("acik,kbcj->abij", T, V_iabj, False)
+    # one or three output indices on the integral block: not a 2 + 2 split
+    check("adkl,lkdc->ac", T, V_ijab, False)
+    check("abid,dj->abij", dV["abic"], _t(rng.standard_normal((nv, no))), False)
+    # row blocks keep their tag through backend.narrow (parallel.Shard.rows)
+    part = bk.narrow(V_ijab, 2, 2, 3)
+    assert bk.geom_of(part).lo[2] == no + 2 and bk.geom_of(part).ext[2] == 3
+    b0 = calls["blocked"]
+    got = bk.contract("klcd,dblj->cbkj", part, T)
+    np.testing.assert_allclose(_n(got), np.einsum("klcd,dblj->cbkj", _n(V_ijab)[:, :, 2:5], _n(T)), rtol=0, atol=1e-12)
+    assert calls["blocked"] == b0 + 1
+    # the undressed V_ijab "dressed" is a tagged copy; dressed blocks with T1 terms are not tagged
+    T1 = _t(rng.standard_normal((nv, no)))
+    full = m.eval_2b_blocks(no, ["ijab", "ijka", "ijak", "iajb", "iacb"] if False else ["ijab", "ijka"], parts)
+    assert bk.geom_of(ccsd.dressed_block("ijab", T1, full)) is not None
+    assert bk.geom_of(ccsd.dressed_block("ijka", T1, full)) is None
+    # accumulate into an existing tensor with a coefficient, multi-term call with a dense term
+    R0 = rng.standard_normal((nv, nv, no, no))
+    R = _t(R0.copy())
+    X = _t(rng.standard_normal((nv, no, nv, no)))
+    bk.contract_terms("abij", [(-1.0, "kaic", V_iajb, "cbkj", T), (1.0, "alci", X, "cblj", T)], out=R, beta=1.0)
+    want = R0 - np.einsum("kaic,cbkj->abij", _n(V_iajb), _n(T)) + np.einsum("alci,cblj->abij", _n(X), _n(T))
+    np.testing.assert_allclose(_n(R), want, rtol=0, atol=1e-12)
