@@ -490,11 +490,26 @@ def run_ours(args):
         ms = float(t.item())
     F_dense = flops_ccd(no, nv, is_dcd=args.dcsd)
     F = F_dense
+    blocked_products = {}
     if blocked:
-        # flops as executed: the ladder visits the nnz candidate non-zeros of V_abcd only
-        _ro, _eo, _g0, g_rows, _e0, g_ents = ueg.momentum_groups(m.k_int(), m.imax, (no,) * 4, (nv,) * 4)
-        nnz_abcd = float((g_rows * g_ents).sum())
-        F = F_dense - 2.0 * no * no * float(nv) ** 4 + 2.0 * no * no * nnz_abcd
+        # flops as executed: the products of F_CCD that ran momentum-blocked (known from the labels
+        # of rank 0's launches) count 2 nnz N instead of 2 M K N; nnz from the WHOLE problem's groups
+        ran = {lab.split(" [")[0] for lab, _f, _t in trace if "[momentum-blocked]" in lab}
+        O, Vr = (0, no), (no, nv)                     # (lo, extent) of an occupied / virtual axis
+        alg = {"abcd,cdij->abij": ((Vr, Vr, Vr, Vr), (0, 1), (2, 3), no * no),        # pp ladder  ccd.py:187
+               "klcd,cdij->klij": ((O, O, Vr, Vr), (0, 1), (2, 3), no * no),          # I_klij     ccd.py:180
+               "klcd,dblj->cbkj": ((O, O, Vr, Vr), (0, 2), (1, 3), nv * no),          # Xai        ccd.py:202
+               "klcd,adkj->alcj": ((O, O, Vr, Vr), (1, 2), (0, 3), nv * no),          # X1         ccd.py:189
+               "klcd,daki->alci": ((O, O, Vr, Vr), (1, 2), (0, 3), nv * no)}          # Xp         ccd.py:238
+        for lab, (axes, m_ax, k_ax, ncol) in alg.items():
+            if lab not in ran:
+                continue
+            lo4, ext4 = tuple(a[0] for a in axes), tuple(a[1] for a in axes)
+            _ro, _eo, _g0, g_rows, _e0, g_ents = ueg.momentum_groups(m.k_int(), m.imax, lo4, ext4, m_ax, k_ax)
+            nnz = float((g_rows * g_ents).sum())
+            dense = 2.0 * ext4[0] * ext4[1] * ext4[2] * ext4[3] * ncol
+            blocked_products[lab] = {"dense_flops": dense, "executed_flops": 2.0 * nnz * ncol, "nnz": nnz}
+            F -= dense - 2.0 * nnz * ncol
     value = F / (ms * 1e-3) / 1e12
 
     rows = getattr(cc, "local_rows", nv) if world > 1 else nv
@@ -594,9 +609,10 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof}
     if blocked:
         line["config"]["flop_convention"] = (
-            "flops_per_step = doubles-residual flops AS EXECUTED: SURVEY 8(d) F_CCD = %.4e with the pp ladder's "
-            "2 o^2 v^4 = %.4e replaced by 2 o^2 nnz(V_abcd) = %.4e (momentum-blocked, nnz = %.0f)"
-            % (F_dense, 2.0 * no * no * float(nv) ** 4, 2.0 * no * no * nnz_abcd, nnz_abcd))
+            "flops_per_step = doubles-residual flops AS EXECUTED: SURVEY 8(d) F_CCD = %.4e, with every product "
+            "that ran momentum-blocked (blocked_products: integral block x amplitudes, on the diagonal momentum "
+            "blocks only) counted as 2 nnz N instead of 2 M K N" % F_dense)
+        line["config"]["blocked_products"] = blocked_products
         line["config"]["flops_per_step_dense_convention"] = F_dense
         line["dense_equivalent_tflops"] = F_dense / (ms * 1e-3) / 1e12
         line["e2e"]["dense_equivalent_tflops"] = F_dense / (e2e_ms * 1e-3) / 1e12

@@ -679,7 +679,7 @@ def _run_blocked(out_sub, term, out, beta):
     if offs is None:
         offs = (up(L["row_i0"] * key[0] + L["row_i1"] * key[1]), up(L["ent_j0"] * key[2] + L["ent_j1"] * key[3]))
         L["offsets"][key] = offs
-    if beta == 0.0:
+    if beta == 0.0 and not L["rows_covered"]:
         out.zero_()              # rows outside every group are part of the result: zero
     d = _lib.Blocked()
     d.A, d.B, d.C = values.data_ptr(), B.data_ptr(), out.data_ptr()
@@ -716,8 +716,7 @@ def _try_blocked(out_sub, terms, out, beta):
         alpha, sa, A, sb, B, m_axes, _k = picked[0][1]
         ext = dict(zip(sb, B.shape))
         ext.update((sa[i], A.shape[i]) for i in m_axes)
-        out = zeros(*[int(ext[ch]) for ch in out_sub])
-        beta = 1.0               # fresh zeros: nothing to clear again
+        out = empty(*[int(ext[ch]) for ch in out_sub])
     elif out.device != device():
         raise RuntimeError("pymes_b200: output tensor lives on %s, the kernels write to %s "
                            "(there is no CPU fallback)" % (out.device, device()))

@@ -592,7 +592,9 @@ class MomentumGeom:
             L = dict(row_i0=(row_ord // ext[m_axes[1]]).astype(np.int64), row_i1=(row_ord % ext[m_axes[1]]).astype(np.int64),
                      ent_j0=(ent_ord // ext[k_axes[1]]).astype(np.int64), ent_j1=(ent_ord % ext[k_axes[1]]).astype(np.int64),
                      tiles=torch.from_numpy(tiles).to(bk.device()), n_tiles=len(tiles),
-                     nnz=int((g_cnt * g_en).sum()), n_groups=len(g_cnt), offsets={})
+                     nnz=int((g_cnt * g_en).sum()), n_groups=len(g_cnt), offsets={},
+                     # every row meets at least one entry: a fresh output needs no clearing
+                     rows_covered=int(g_cnt.sum()) == ext[m_axes[0]] * ext[m_axes[1]])
             self._lists[key] = L
         return L
 

@@ -579,6 +579,52 @@ def test_momentum_blocked_contractions(n_ele, cutoff):
     assert _rel(W1.cpu().numpy().reshape(no * nv, -1), w1) < 1e-13
 
 
+@pytest.mark.parametrize("n_ele,cutoff", [(14, 5.0), (54, 7.0), (54, 10.0)])
+def test_momentum_blocked_stored_blocks(n_ele, cutoff):
+    """Stored integral blocks with a geometry tag: every 2 + 2 split of the ring-type products of the
+    doubles residual (ccd.py:180,189,202,233,234,238) runs on the diagonal momentum blocks and equals
+    the dense kernel and a cuBLAS product of the same operands; narrowed row blocks (sharded runs);
+    fresh outputs whose rows are not all covered."""
+    from pymes_b200 import backend as bk
+    m = _tc_model(n_ele, cutoff)
+    no, nP = n_ele // 2, m.n_orb
+    nv = nP - no
+    parts = [("only_2b", m.trunc), ("effect_2b", m.trunc)]
+    dV = m.eval_2b_blocks(no, ["ijab", "iajb"], parts)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    T = torch.randn(nv, nv, no, no, dtype=torch.float64, device="cuda", generator=g)
+    lo, na = nv // 3, nv - nv // 3 - 1
+    cases = [("klcd,dblj->cbkj", dV["ijab"], T), ("klcd,adkj->alcj", dV["ijab"], T),
+             ("klcd,daki->alci", dV["ijab"], T), ("klcd,cdij->klij", dV["ijab"], T),
+             ("kaic,cbkj->abij", dV["iajb"], T), ("kbic,ackj->abij", dV["iajb"], T),
+             # row blocks as one rank of a sharded run sees them (parallel.Shard.rows)
+             ("klcd,dblj->cbkj", bk.narrow(dV["ijab"], 2, lo, na), T),
+             ("klcd,adkj->alcj", dV["ijab"], T[lo:lo + na]),
+             ("klcd,daki->alci", dV["ijab"], T[:, lo:lo + na]),
+             ("kaic,cbkj->abij", bk.narrow(dV["iajb"], 1, lo, na), T)]
+    for spec, A, B in cases:
+        bk.enable_trace(True)
+        got = bk.contract(spec, A, B)
+        labels = [lab for lab, _f, _t in bk.trace_report()]
+        bk.enable_trace(False)
+        assert len(labels) == 1 and labels[0].endswith("[momentum-blocked]"), (spec, labels)
+        old = bk.set_blocked(False)
+        try:
+            ref = bk.contract(spec, A, B)
+        finally:
+            bk.set_blocked(old)
+        want = torch.einsum(spec, A, B)
+        assert _rel(got.cpu().numpy(), ref.cpu().numpy()) < 1e-13, spec
+        assert _rel(got.cpu().numpy(), want.cpu().numpy()) < 1e-13, spec
+    # accumulation with a coefficient into the ring sum, next to a dense term
+    X = torch.randn(nv, no, nv, no, dtype=torch.float64, device="cuda", generator=g)
+    R0 = torch.randn(nv, nv, no, no, dtype=torch.float64, device="cuda", generator=g)
+    R = R0.clone()
+    bk.contract_terms("abij", [(-1.0, "kaic", dV["iajb"], "cbkj", T), (1.0, "alci", X, "cblj", T)], out=R, beta=1.0)
+    want = R0 - torch.einsum("kaic,cbkj->abij", dV["iajb"], T) + torch.einsum("alci,cblj->abij", X, T)
+    assert _rel(R.cpu().numpy(), want.cpu().numpy()) < 1e-13
+
+
 def test_momentum_blocked_ladder_long_groups():
     """A group longer than the kernel's 512-entry offset window (several table refills per CTA) and
     more than 64 rows per group: a synthetic block-diagonal operand driven through the C ABI
