@@ -571,6 +571,9 @@ def run_ours(args):
             rec = json.load(open(prof))
             if rec.get("n_virt", nv) == nv:
                 roof["traffic"] = rec.get("dram_bytes_per_launch")
+                if blocked and rec.get("flops_per_launch") and roof.get("flops_per_launch"):
+                    # the capture is ONE product (2 o^3 v^3); the average launch here is 1.5 products
+                    roof["traffic"] *= roof["flops_per_launch"] / rec["flops_per_launch"]
                 roof["traffic_source"] = os.path.relpath(prof, ROOT)
         except Exception:               # noqa: BLE001
             pass

@@ -107,7 +107,8 @@ int pmb_contract(const pmb_contract_t *d, void *ws, size_t ws_bytes,
 /* tuning/diagnostic knobs: force a tile configuration (-1 = heuristic; bits   */
 /* 0-2 the configuration, +8 flips the copy interleaving, +16 makes generated  */
 /* operands use the scanning producer instead of the non-zero walker, +32 keeps */
-/* the n-fastest tile order for launches with a generated operand) and         */
+/* the n-fastest tile order for launches with a generated operand, +256 keeps   */
+/* it for stored operands too instead of the banded order) and                 */
 /* a split-K factor (0 = heuristic).                                          */
 void pmb_contract_set_tuning(int tile_config, int split_k);
 /* L2 budget (bytes) for one operand's k window; contractions whose smaller      */

@@ -64,6 +64,7 @@ struct Params {
     double beta;
     int tiles_m, tiles_n;
     int raster_m_fast;       // consecutive CTAs walk m inside one column of tiles (see launch_ws)
+    int raster_group;        // > 1: consecutive CTAs walk m inside a band of that many tile rows (tile_coords)
     int total_ktiles, ktiles_per_split, nsplit;
     int kt_base, kt_limit;   // k-tile window of this launch (K-panel), [0, total_ktiles) if not panelled
     // Tail launch (see pmb_contract): this launch covers the output tiles [tile_base, tile_base +
@@ -133,6 +134,32 @@ __device__ __forceinline__ double gen_value(const Params &p, long long e) {
     return ueg_value(p.gen_ueg, p.gen_W0a, p.gen_W1a, p.gen_W0s, (int)(e >> (3 * kGenFieldBits)) & kGenFieldMask,
                      (int)(e >> (2 * kGenFieldBits)) & kGenFieldMask, (int)(e >> kGenFieldBits) & kGenFieldMask,
                      (int)e & kGenFieldMask);
+}
+
+// Output tile of the `tile`-th CTA.  Three orders:
+//   n fastest (default of the single-role kernels),
+//   m fastest (generated A operand: a wave streams one column of B tiles together),
+//   banded   (stored operands, warp-specialised kernel): bands of `raster_group` tile rows, m fastest
+//            inside a band.  A wave of 148 CTAs then covers ~12 x 12 tiles and shares 12 A row panels
+//            and 12 B column panels through L2, instead of one A panel and 103 B panels: the ring-type
+//            contraction at v = 488 moved 187 GB of DRAM traffic per launch n-fastest (45 x its
+//            algorithmic 4.2 GB; ncu, profiles/r2_ring_ncu.md).
+__device__ __forceinline__ void tile_coords(const Params &p, int tile, int &tile_m, int &tile_n) {
+    if (p.raster_m_fast) {
+        tile_n = tile / p.tiles_m;
+        tile_m = tile % p.tiles_m;
+    } else if (p.raster_group > 1) {
+        const int per = p.raster_group * p.tiles_n;
+        const int band = tile / per;
+        const int first = band * p.raster_group;
+        const int rows = min(p.raster_group, p.tiles_m - first);
+        const int in = tile - band * per;
+        tile_n = in / rows;
+        tile_m = first + in - tile_n * rows;
+    } else {
+        tile_n = tile % p.tiles_n;
+        tile_m = tile / p.tiles_n;
+    }
 }
 
 __device__ __forceinline__ long long decomp(int idx, int nd, const int *ext,
@@ -625,8 +652,8 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32 + kWsProducerThreads, 1)
     // stream the same k range of B at the same time: B is read from HBM once per wave instead
     // of once per CTA (ncu: 2.64 TB -> see profiles/ for the pp ladder at v = 488).
     const int tile = (int)blockIdx.x + p.tile_base;
-    const int tile_n = p.raster_m_fast ? tile / p.tiles_m : tile % p.tiles_n;
-    const int tile_m = p.raster_m_fast ? tile % p.tiles_m : tile / p.tiles_n;
+    int tile_m, tile_n;
+    tile_coords(p, tile, tile_m, tile_n);
     const int m0 = tile_m * BM, n0 = tile_n * BN;
     const int mrem = p.M - m0, nrem = p.N - n0;
     const int kt_lo = p.kt_base + blockIdx.y * p.ktiles_per_split;
@@ -1040,8 +1067,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constan
 __global__ void __launch_bounds__(256) tail_reduce_kernel(const __grid_constant__ Params p) {
     constexpr int BT = 128;
     const int tile = (int)blockIdx.x + p.tile_base;
-    const int tile_n = p.raster_m_fast ? tile / p.tiles_m : tile % p.tiles_n;
-    const int tile_m = p.raster_m_fast ? tile % p.tiles_m : tile / p.tiles_n;
+    int tile_m, tile_n;
+    tile_coords(p, tile, tile_m, tile_n);
     const int m0 = tile_m * BT, n0 = tile_n * BT;
     const int mrem = min(BT, p.M - m0), nrem = min(BT, p.N - n0);
     const size_t stride = (size_t)gridDim.x * BT * BT;
@@ -1076,6 +1103,8 @@ static int g_no_vec2 = 0;          // tuning bit 128: 8-byte copies even where 1
 static int g_no_tail = 0;          // tuning bit 64: never cut the tail wave off (see tail_plan)
 static int g_gen_no_walk = 0;      // tuning bit 16: generated operands use the scanning producer
 static int g_gen_no_mraster = 0;   // tuning bit 32: keep the default tile order for generated operands
+static int g_no_band_raster = 0;   // tuning bit 256: n-fastest tile order for stored operands (see tile_coords)
+constexpr int kRasterBand = 12;    // 12 x 12.3 tiles per wave of 148 CTAs
 static int g_force_cfg = -1;
 static int g_force_split = 0;
 // L2 budget for one operand's k window (0 = no windows).  The warp-specialised kernel runs
@@ -1389,6 +1418,8 @@ static int build_params(const pmb_contract_t *d, Params &p, int &cfg) {
     p.tiles_m = (int)((M + kCfg[cfg].bm - 1) / kCfg[cfg].bm);
     p.tiles_n = (int)((N + kCfg[cfg].bn - 1) / kCfg[cfg].bn);
     p.raster_m_fast = p.gen_term >= 0 && !g_gen_no_mraster;
+    p.raster_group = (cfg >= 5 && p.gen_term < 0 && !g_no_band_raster && p.tiles_m > kRasterBand &&
+                      p.tiles_n > kRasterBand) ? kRasterBand : 0;
     if (g_force_split > 0) nsplit = g_force_split;
     if (nsplit > kt) nsplit = kt;
     if (nsplit < 1) nsplit = 1;
@@ -1455,6 +1486,7 @@ extern "C" void pmb_contract_set_tuning(int tile_config, int split_k) {
     g_gen_no_mraster = tile_config >= 0 && (tile_config & 32);
     g_no_tail = tile_config >= 0 && (tile_config & 64);
     g_no_vec2 = tile_config >= 0 && (tile_config & 128);
+    g_no_band_raster = tile_config >= 0 && (tile_config & 256);
     g_force_cfg = tile_config >= 0 ? (tile_config & 15) : tile_config;
     g_force_split = split_k;
 }

@@ -49,6 +49,14 @@ out = {"n_orb": m.n_orb, "n_occ": no, "n_virt": nv, "E_ccsd_after_sweeps": sum(e
        "plan_ms": t0.elapsed_time(t1), "hoist_flops": plan.hoist_flops,
        "flops_per_vector": plan.flops_per_vector, "direct_groups": n_direct, "twostep_groups": n_two,
        "ladder_flops_per_vector": 2.0 * no**2 * nv**4, "batches": []}
+# with the ladder momentum-blocked (backend.blocked_enabled, virtual V_abcd) the executed count replaces
+# 2 o^2 v^4 by 2 o^2 nnz(V_abcd); `tflops` below is computed from the EXECUTED flops
+flops_exec = plan.flops_per_vector
+if virtual and bk.blocked_enabled():
+    g = ueg.momentum_groups(m.k_int(), m.imax, (no,) * 4, (nv,) * 4)
+    nnz = float((g[3] * g[5]).sum())
+    flops_exec = plan.flops_per_vector - 2.0 * no**2 * nv**4 + 2.0 * no**2 * nnz
+    out.update(ladder="momentum-blocked (pmb_blocked_contract)", nnz_abcd=nnz, flops_per_vector_executed=flops_exec)
 torch.manual_seed(0)
 r = 1
 while r <= max_batch:
@@ -65,7 +73,8 @@ while r <= max_batch:
     torch.cuda.synchronize()
     ms = t0.elapsed_time(t1) / reps
     out["batches"].append({"r": r, "ms": ms, "ms_per_rhs": ms / r,
-                           "tflops": plan.flops_per_vector * r / ms / 1e9,
+                           "tflops": flops_exec * r / ms / 1e9,
+                           "tflops_dense_equivalent": plan.flops_per_vector * r / ms / 1e9,
                            "launches": (bk.launch_count() - before) // reps})
     print("r=%3d  %9.2f ms  %8.2f ms/rhs  %6.2f TFLOP/s" % (r, ms, ms / r, out["batches"][-1]["tflops"]),
           file=sys.stderr, flush=True)

@@ -12,6 +12,9 @@ from pymes_b200 import backend as bk
 nv = int(sys.argv[1]) if len(sys.argv) > 1 else 488
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 no = 27
+if os.environ.get("PYMES_B200_TUNING"):        # e.g. 261 = configuration 5 + 256: n-fastest tile order (A/B)
+    from pymes_b200 import _lib
+    _lib.load().pmb_contract_set_tuning(int(os.environ["PYMES_B200_TUNING"]), 0)
 g = torch.Generator(device="cuda").manual_seed(0)
 V = torch.randn(no, nv, no, nv, dtype=torch.float64, device="cuda", generator=g)
 T = torch.randn(nv, nv, no, no, dtype=torch.float64, device="cuda", generator=g)
