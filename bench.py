@@ -520,7 +520,8 @@ def run_ours(args):
         # dominant kernel now: contract_ws_kernel on the nine ring-type o^3v^3 contractions of
         # ccd.py:189-204,233-240 (seven launches, one of them three terms wide), this rank's rows
         ring_unit = 2.0 * rows * nv * nv * float(no) ** 3
-        ring = [(fl, t) for lab, fl, t in trace if "[" not in lab and fl >= 0.99 * ring_unit]
+        ring = [(fl, t) for lab, fl, t in trace
+                if "[momentum-blocked]" not in lab and "[gemv]" not in lab and fl >= 0.99 * ring_unit]
         ring_flops, ring_ms = sum(fl for fl, _ in ring), sum(t for _, t in ring)
         n_ring = len(ring)
         roof = {"bound": "tensor",
