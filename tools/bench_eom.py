@@ -49,14 +49,21 @@ out = {"n_orb": m.n_orb, "n_occ": no, "n_virt": nv, "E_ccsd_after_sweeps": sum(e
        "plan_ms": t0.elapsed_time(t1), "hoist_flops": plan.hoist_flops,
        "flops_per_vector": plan.flops_per_vector, "direct_groups": n_direct, "twostep_groups": n_two,
        "ladder_flops_per_vector": 2.0 * no**2 * nv**4, "batches": []}
-# with the ladder momentum-blocked (backend.blocked_enabled, virtual V_abcd) the executed count replaces
-# 2 o^2 v^4 by 2 o^2 nnz(V_abcd); `tflops` below is computed from the EXECUTED flops
+# with momentum-blocked products (backend.blocked_enabled) fewer flops are executed than the plan's dense
+# count: one traced application (an event pair per launch, backend.enable_trace) sums what actually ran
 flops_exec = plan.flops_per_vector
-if virtual and bk.blocked_enabled():
-    g = ueg.momentum_groups(m.k_int(), m.imax, (no,) * 4, (nv,) * 4)
-    nnz = float((g[3] * g[5]).sum())
-    flops_exec = plan.flops_per_vector - 2.0 * no**2 * nv**4 + 2.0 * no**2 * nnz
-    out.update(ladder="momentum-blocked (pmb_blocked_contract)", nnz_abcd=nnz, flops_per_vector_executed=flops_exec)
+if bk.blocked_enabled():
+    U1 = torch.randn(1, nv, no, dtype=torch.float64, device="cuda")
+    U2 = torch.randn(1, nv, nv, no, no, dtype=torch.float64, device="cuda")
+    plan.apply(U1, U2)
+    bk.enable_trace(True)
+    plan.apply(U1, U2)
+    tr = bk.trace_report()
+    bk.enable_trace(False)
+    flops_exec = float(sum(fl for _lab, fl, _ms in tr))
+    out.update(blocked_launches=sum(1 for lab, _f, _m in tr if "[momentum-blocked]" in lab),
+               flops_per_vector_executed=flops_exec)
+    del U1, U2
 torch.manual_seed(0)
 r = 1
 while r <= max_batch:
