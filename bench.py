@@ -15,17 +15,23 @@ blocks per rank when N > 1.  `--dense-abcd` stores V_abcd instead (then the basi
 use --cutoff 18 -> 341 orbitals on one GPU).  Data are synthetic in the sense that nothing is
 read from disk; it is the physical TC-UEG Hamiltonian.
 
-The particle-particle ladder runs MOMENTUM-BLOCKED by default (`--ladder blocked`, SURVEY
-8(f).1): V_abcd as the matrix [(ab),(cd)] is block diagonal in the total momentum, and
-pmb_blocked_contract visits the diagonal blocks only -- 2 o^2 nnz(V_abcd) flop instead of
-2 o^2 v^4 (4.8e10 instead of 8.3e13 at 515 plane waves), same result to round-off.
-`--ladder dense` keeps the dense DMMA ladder with the operand generated in the producer warps
-(the round-1 / early round-2 configuration; its roofline is the pp-ladder one).
+Products of a UEG integral block with amplitudes run MOMENTUM-BLOCKED by default (`--ladder
+blocked`): as a matrix the block is block diagonal in the (linearised) total
+momentum, and pmb_blocked_contract visits the diagonal blocks only -- the particle-particle
+ladder 2 o^2 nnz(V_abcd) flop instead of 2 o^2 v^4 (5.2e10 instead of 8.3e13 at 515 plane
+waves), likewise V_iabc.tau / V_aibc.tau, I_klij and the three ring intermediates built from
+the stored V_ijab; same results to round-off.  Products of amplitudes with intermediates or
+T1-dressed blocks stay on the dense DMMA kernel (nothing is assumed about amplitudes).
+`--ladder dense` switches the blocked path off altogether: the dense DMMA ladder with the
+operand generated in the producer warps (the round-1 / early round-2 configuration; its
+roofline is the pp-ladder one).
 
 Printed line: see the contract in the task statement; `value` is FP64 TFLOP/s computed from
 the ALGORITHMIC flop count of the doubles residual AS EXECUTED,
-F = F_CCD - 2o^2v^4 + 2o^2 nnz(V_abcd) with F_CCD = 2o^2v^4 + 20o^3v^3 + 4o^4v^2 + 4o^2v^3 + 4o^3v^2
-(T1-dressing flops are executed but not counted; F = F_CCD with `--ladder dense`),
+F = F_CCD - sum over the blocked products of (2 M K N - 2 nnz N), with
+F_CCD = 2o^2v^4 + 20o^3v^3 + 4o^4v^2 + 4o^2v^3 + 4o^3v^2
+(SURVEY 8d; T1-dressing flops are executed but not counted; F = F_CCD with `--ladder dense`;
+the per-product counts are printed in config.blocked_products),
 divided by the measured time of a whole iteration -- so it can never exceed the FP64 peak.
 `dense_equivalent_tflops` = F_CCD / time is what the reference's dense einsum formulation would
 have to sustain to finish the iteration in the same time.
