@@ -14,13 +14,14 @@ Q (generalised eigenproblem H_proj c = lambda B c), trial space grown until n_tr
 
 What is different is how the linear systems are solved.  The reference runs scipy's
 GCROT(m,k) once per system, i.e. 8 x n_trial sequential Krylov solvers, each calling the
-62-term sigma for one complex vector.  Here ALL systems advance in lock-step through a
-right-preconditioned restarted GMRES (same preconditioner 1/(z - diag + 0.01), same
-relative tolerance 1e-4, same restart length 20 and outer limit ``ls_max_iter``): every
-Krylov step makes ONE batched sigma call whose right-hand sides are the real and imaginary
-parts of the current vector of every unconverged system (H-bar is real, so a complex vector
-is two real ones).  With an empty recycle space GCROT's first cycle IS this GMRES cycle; both
-stop at the same residual norm, so the solutions agree to the solver tolerance.
+62-term sigma for one complex vector.  Here ALL systems advance in lock-step through the same
+GCROT(m,k) (``_solve_group``: inner flexible GMRES cycles of m + max(k - |CU|, 0) steps -- 40
+in the first cycle -- with the same right preconditioner 1/(z - diag + 0.01), the same relative
+tolerance 1e-4, the same recycling of (c, u) pairs with the oldest dropped beyond k = m = 20 and
+the same outer limit ``ls_max_iter``): every Krylov step makes ONE batched sigma call whose
+right-hand sides are the real and imaginary parts of the current vector of every unconverged
+system (H-bar is real, so a complex vector is two real ones).  Systems that converge within the
+first cycle reproduce scipy's iterate to rounding.
 """
 import time
 
@@ -129,7 +130,8 @@ class FEAST_EOM_CCSD(EOM_CCSD):
         self.linear_solver = "Jacobi"
         self.ls_max_iter = 20
         self.ls_tol = 1e-4           # gcrotmk(tol=1e-4), feast:346
-        self.ls_restart = 20         # scipy's default m
+        self.ls_restart = 20         # scipy's default m (inner steps per cycle once the recycle space is full)
+        self.ls_recycle = None       # scipy's k: recycled (c, u) pairs kept; None = m, like gcrotmk(k=None)
         self.n_nodes = 8             # feast:97
         self.max_rhs = 64            # real right-hand sides per batched sigma call
         self.max_systems = None      # systems advanced together (None: all); bounds the Krylov memory
@@ -160,9 +162,10 @@ class FEAST_EOM_CCSD(EOM_CCSD):
         """Solve (z_s - hscale * H-bar) x_s = rhs_s for every s (``rhs``: list of flat device
         vectors, real tensors or complex ``_CVec``; ``zs``: complex shifts; ``hscale``: a complex
         scalar, 1 for FEAST, i*dt for the real-time propagator of rt_eom_ccsd.py).
-        Right-preconditioned restarted GMRES advanced in lock-step over groups of at most
-        ``max_systems`` systems (each system keeps ``ls_restart + 1`` complex Krylov vectors);
-        returns the list of complex solutions (_CVec)."""
+        The reference's GCROT(m,k) (``_solve_group``) advanced in lock-step over groups of at most
+        ``max_systems`` systems (each system keeps up to ``ls_restart + ls_recycle + 1`` complex
+        Krylov vectors and ``ls_recycle`` recycled pairs); returns the list of complex solutions
+        (_CVec)."""
         group = self.max_systems or len(zs)
         out, res = [], []
         for lo in range(0, len(zs), group):
@@ -173,8 +176,26 @@ class FEAST_EOM_CCSD(EOM_CCSD):
         return out
 
     def _solve_group(self, plan, diag, zs, rhs, hscale):
+        """GCROT(m,k) as scipy runs it for the reference (``gcrotmk(A, b, x0=0, M=M, maxiter=ls_max_iter,
+        tol=1e-4)``, feast:346; scipy/sparse/linalg/_isolve/_gcrotmk.py, m = 20, k = m, truncate =
+        'oldest'), for every system of the group in lock-step.  Per outer iteration and system:
+
+        * an inner flexible GMRES cycle of ``ml = m + max(k - len(CU), 0)`` steps at most (40 in the
+          first cycle, when nothing has been recycled yet) on ``r / |r|`` with the right
+          preconditioner, every new direction first projected off the recycled C vectors
+          (coefficients B), stopped when the estimated residual drops below ``tol |b|``;
+        * ``u = Z y - U (B y)``, ``c = V (H y)`` normalised to ``|c| = 1``, ``x += <c, r> u``,
+          ``r -= <c, r> c`` (the residual is carried by this recurrence and recomputed from x only
+          when it signals convergence, as scipy does), ``(c, u)`` appended to the recycle space,
+          the oldest pair dropped beyond k.
+
+        With an empty recycle space the first cycle is a plain right-preconditioned GMRES(40): a
+        system that converges within it -- every system of the fixtures -- reproduces scipy's
+        iterate to rounding (LiH: 7e-15 relative; FEAST eigenvalues of a seeded run: 3e-14 Eh)."""
         nsys = len(zs)
         hscale = complex(hscale)
+        m_inner = self.ls_restart
+        k_keep = m_inner if self.ls_recycle is None else int(self.ls_recycle)
         first = rhs[0].re if isinstance(rhs[0], _CVec) else rhs[0]
         zero = torch.zeros_like(first)
         rhs = [b if isinstance(b, _CVec) else _CVec(b, zero) for b in rhs]
@@ -182,31 +203,61 @@ class FEAST_EOM_CCSD(EOM_CCSD):
         x = [None] * nsys
         res = list(rhs)                                     # x0 = 0 -> r0 = b
         rnorm = list(bnorm)
+        CU = [[] for _ in range(nsys)]                      # recycled (c, u) pairs per system
         active = [s for s in range(nsys) if bnorm[s] > 0]
+
+        def apply_op(vecs_s, vecs):
+            """(z_s - hscale H-bar) v for a list of systems / vectors."""
+            HV = self._sigma_c(plan, vecs)
+            out = []
+            for s, v, hv in zip(vecs_s, vecs, HV):
+                if hscale == 1.0:
+                    out.append(_caxpy(_CVec(bk.lincomb([-1.0], [hv.re]), bk.lincomb([-1.0], [hv.im])), [zs[s]], [v]))
+                else:
+                    out.append(_caxpy(_CVec(zero, zero), [zs[s], -hscale], [v, hv]))
+            return out
+
         for _outer in range(self.ls_max_iter):
+            # scipy's loop head: a residual (from the recurrence) at the tolerance is recomputed from x
+            # before it ends the solve
+            check = [s for s in active if rnorm[s] <= self.ls_tol * bnorm[s] and x[s] is not None]
+            if check:
+                AX = apply_op(check, [x[s] for s in check])
+                for s, ax in zip(check, AX):
+                    res[s] = _caxpy(rhs[s], [-1.0 + 0j], [ax])
+                del AX
+                for s, rn in zip(check, _norms([res[s] for s in check])):
+                    rnorm[s] = rn
             active = [s for s in active if rnorm[s] > self.ls_tol * bnorm[s]]
             if not active:
                 break
+            ml = {s: m_inner + max(k_keep - len(CU[s]), 0) for s in active}
             V = {s: [_CVec(bk.lincomb([1.0 / rnorm[s]], [res[s].re]), bk.lincomb([1.0 / rnorm[s]], [res[s].im]))]
                  for s in active}
-            H = {s: np.zeros((self.ls_restart + 1, self.ls_restart), dtype=complex) for s in active}
+            H = {s: np.zeros((ml[s] + 1, ml[s]), dtype=complex) for s in active}
+            B = {s: np.zeros((len(CU[s]), ml[s]), dtype=complex) for s in active}
             y = {}
             running = list(active)
-            for j in range(self.ls_restart):
+            for j in range(max(ml.values())):
                 if not running:
                     break
                 P = [_CVec(*bk.cdiv_shifted(diag, zs[s], 0.01, V[s][j].re, V[s][j].im)) for s in running]
-                HP = self._sigma_c(plan, P)
-                W = []
-                for s, p, hp in zip(running, P, HP):
-                    if hscale == 1.0:
-                        W.append(_caxpy(_CVec(bk.lincomb([-1.0], [hp.re]), bk.lincomb([-1.0], [hp.im])), [zs[s]], [p]))
-                    else:
-                        W.append(_caxpy(_CVec(zero, zero), [zs[s], -hscale], [p, hp]))
-                del P, HP
-                # Gram-Schmidt with one refinement.  Every pass launches the dot products of ALL
-                # running systems, reads them back together, then launches all the updates: the
-                # host waits for the device three times per Krylov step, not per system and dot.
+                W = apply_op(running, P)
+                del P
+                # GCROT projection off the recycled C vectors, then Gram-Schmidt against V with one
+                # refinement.  Every pass launches the dot products of ALL running systems, reads them
+                # back together, then launches all the updates: the host waits for the device a fixed
+                # number of times per Krylov step, not per system and dot.
+                if any(CU[s] for s in running):
+                    for _ in range(2):
+                        pend = [_cdots_launch([c for c, _u in CU[s]], w) if CU[s] else None
+                                for s, w in zip(running, W)]
+                        for n, (s, pd) in enumerate(zip(running, pend)):
+                            if pd is None:
+                                continue
+                            h = _cdots_finish(pd)
+                            W[n] = _caxpy(W[n], list(-h), [c for c, _u in CU[s]])
+                            B[s][:, j] += h
                 for _ in range(2):
                     pend = [_cdots_launch(V[s], w) for s, w in zip(running, W)]
                     hs = [_cdots_finish(pd) for pd in pend]
@@ -222,26 +273,46 @@ class FEAST_EOM_CCSD(EOM_CCSD):
                     ys, *_ = np.linalg.lstsq(H[s][:j + 2, :j + 1], e1, rcond=None)
                     y[s] = ys
                     est = np.linalg.norm(e1 - H[s][:j + 2, :j + 1] @ ys)
-                    if est > self.ls_tol * bnorm[s] and hn > 1e-14 * rnorm[s] and j + 1 < self.ls_restart:
+                    ok = hn > 1e-14 * rnorm[s]
+                    if ok:                                  # v_{j+1}: needed for c = V (H y) as well
                         V[s].append(_CVec(bk.lincomb([1.0 / hn], [w.re]), bk.lincomb([1.0 / hn], [w.im])))
+                    if est > self.ls_tol * bnorm[s] and ok and j + 1 < ml[s]:
                         nxt.append(s)
                 del W
                 running = nxt
-            # x += M (V y); true residual for the next cycle
-            upd = []
+            # outer update: u = M (V y) - U (B y), c = V (H y), normalised; x += <c,r> u, r -= <c,r> c
+            cxs, uxs = [], []
             for s in active:
                 k = len(y[s])
                 vy = _caxpy(_CVec(zero, zero), list(y[s]), V[s][:k])
-                d = _CVec(*bk.cdiv_shifted(diag, zs[s], 0.01, vy.re, vy.im))
-                x[s] = d if x[s] is None else _caxpy(x[s], [1.0 + 0j], [d])
-                upd.append(s)
+                ux = _CVec(*bk.cdiv_shifted(diag, zs[s], 0.01, vy.re, vy.im))
+                if CU[s]:
+                    ux = _caxpy(ux, list(-(B[s][:, :k] @ y[s])), [u for _c, u in CU[s]])
+                hy = H[s][:k + 1, :k] @ y[s]
+                nv_ = min(len(V[s]), k + 1)                 # after a breakdown v_{k} does not exist (its weight is ~0)
+                cxs.append(_caxpy(_CVec(zero, zero), list(hy[:nv_]), V[s][:nv_]))
+                uxs.append(ux)
             del V
-            HX = self._sigma_c(plan, [x[s] for s in upd])
-            for s, hx in zip(upd, HX):
-                res[s] = _caxpy(rhs[s], [-zs[s], hscale], [x[s], hx])
-            del HX
-            for s, rn in zip(upd, _norms([res[s] for s in upd])):
+            cn = _norms(cxs)
+            upd = []
+            for n, s in enumerate(active):
+                if not (cn[n] > 0 and np.isfinite(cn[n])):
+                    continue                                # scipy: "cannot update, so skip it"
+                a_ = 1.0 / cn[n]
+                cxs[n] = _CVec(bk.lincomb([a_], [cxs[n].re]), bk.lincomb([a_], [cxs[n].im]))
+                uxs[n] = _CVec(bk.lincomb([a_], [uxs[n].re]), bk.lincomb([a_], [uxs[n].im]))
+                upd.append((n, s))
+            gam = [_cdots_launch([cxs[n]], res[s]) for n, s in upd]
+            for (n, s), pd in zip(upd, gam):
+                g_ = _cdots_finish(pd)[0]
+                res[s] = _caxpy(res[s], [-g_], [cxs[n]])
+                x[s] = _caxpy(x[s] if x[s] is not None else _CVec(zero, zero), [g_], [uxs[n]])
+                while len(CU[s]) >= k_keep and CU[s]:
+                    del CU[s][0]
+                CU[s].append((cxs[n], uxs[n]))
+            for (n, s), rn in zip(upd, _norms([res[s] for _n, s in upd])):
                 rnorm[s] = rn
+            del cxs, uxs
         return ([xs if xs is not None else _CVec(zero, zero) for xs in x],
                 [rn / bn if bn > 0 else 0.0 for rn, bn in zip(rnorm, bnorm)])
 

@@ -8,7 +8,7 @@ One step maps a state Y = (u_singles, u_doubles) to
 
 followed by ``normalize_amps`` (rt_eom_ccsd.py:92-124).  The eight shifted systems are the same
 kind FEAST solves, with H-bar scaled by i*dt: they run together through the lock-step batched
-GMRES of ``FEAST_EOM_CCSD.solve_shifted_systems`` (one batched sigma call per Krylov step), with
+GCROT(m,k) of ``FEAST_EOM_CCSD.solve_shifted_systems`` (one batched sigma call per Krylov step), with
 the reference's diagonal preconditioner 1/(Z_e - diag + 0.01) (feast_eom_ccsd.py:341-342).
 
 The reference class cannot run at HEAD (it calls the ctf-era ``.to_nparray()`` on numpy arrays,

@@ -124,6 +124,10 @@ def test_feast_batched_systems_and_seeded_iteration():
     host.test_feast_batched_systems_and_seeded_iteration(None)
 
 
+def test_feast_gcrot_matches_scipy_over_many_cycles():
+    host.test_feast_gcrot_matches_scipy_over_many_cycles(None)
+
+
 # --------------------------------------------------------------------------
 # contraction engine: every tile configuration, both load mappings, ragged edges,
 # split-K, multi-term accumulation, strided views

@@ -239,7 +239,7 @@ def test_sharded_feast_linear_solve_world2(cpu_abi):
     for rank, q1, q2, resid in res:
         assert resid < 1e-4
         err = np.sqrt(np.sum(abs(q1 - gf["q1"]) ** 2) + np.sum(abs(q2 - gf["q2"]) ** 2)) / nrm
-        assert err < 1e-6, err
+        assert err < 1e-10, err
 
 
 # --------------------------------------------------------------------------

@@ -150,6 +150,7 @@ def run_feast(argv, comm, log):
     fe.max_systems = max_systems
     fe.max_rhs = 2 * max_systems
     fe.ls_restart = krylov
+    fe.ls_recycle = 0                  # no recycle space: the single cycle below is `krylov` steps long
     fe.ls_max_iter = 1                 # one GMRES cycle per system: bounded cost, residuals are reported
     np.random.seed(7)
     t0 = time.perf_counter()
