@@ -571,13 +571,19 @@ class MomentumGeom:
 
     def __init__(self, model, lo, ext):
         self.model, self.lo, self.ext = model, tuple(int(x) for x in lo), tuple(int(x) for x in ext)
-        self._lists = {}
+        self._lists, self._narrowed = {}, {}
 
     def narrow(self, dim, lo, n):
-        new_lo, new_ext = list(self.lo), list(self.ext)
-        new_lo[dim] += int(lo)
-        new_ext[dim] = int(n)
-        return MomentumGeom(self.model, new_lo, new_ext)
+        """Geometry of ``block.narrow(dim, lo, n)`` (cached: a sharded sweep narrows the same blocks
+        every iteration, and the lists / device tables hang off the geometry object)."""
+        key = (int(dim), int(lo), int(n))
+        sub = self._narrowed.get(key)
+        if sub is None:
+            new_lo, new_ext = list(self.lo), list(self.ext)
+            new_lo[dim] += int(lo)
+            new_ext[dim] = int(n)
+            sub = self._narrowed[key] = MomentumGeom(self.model, new_lo, new_ext)
+        return sub
 
     def lists(self, m_axes=(0, 1), k_axes=(2, 3)):
         """Host lists (numpy int64 index pairs of the rows / entries, sorted by group), the device
