@@ -379,6 +379,32 @@ typedef struct {
 } pmb_blocked_t;
 int pmb_blocked_contract(const pmb_blocked_t *d, pmb_stream_t stream);
 
+/* A UEG integral block times a ONE-index contraction (T1 dressing products       */
+/* "abid,dj->abij", "abcj,ci->abij", "iabc,cj->iabj", "iacb,cj->iajb",           */
+/* ccsd.py:322-419):                                                            */
+/*   out[..] = beta * out[..] + alpha * val[x] * D[idx[x] * d_ystr + j * d_jstr]  */
+/* for every output element (x0,x1,x2,j); x = x0*x_str[0] + x1*x_str[1] +         */
+/* x2*x_str[2] addresses the tables val[x] = V[x0,x1,x2 | y*] and idx[x] = y*      */
+/* (the one orbital the reference's lookup ueg.py:395-404 finds on the summed     */
+/* axis, local index, or -1).  `out` is C-contiguous with extents ext[0..3]       */
+/* (slowest first); role[d] in {0,1,2,3} says which of x0, x1, x2, j output       */
+/* dimension d is.  HBM-bound: one pass over the output instead of one over the   */
+/* o.v^3 block.                                                                  */
+typedef struct {
+    const double *val;
+    const int32_t *idx;
+    const double *D;
+    double *out;
+    int32_t ext[4];
+    int32_t role[4];
+    int64_t x_str[3];
+    int64_t d_ystr;
+    int64_t d_jstr;
+    double alpha;
+    double beta;
+} pmb_gather_t;
+int pmb_gather_expand(const pmb_gather_t *d, pmb_stream_t stream);
+
 /* ------------------------------------------------------------------------ */
 /* Synthetic non-hermitian integrals (BASELINE.json configs[2]; SURVEY 8(d) C3   */
 /* recipe): out[np][nq][nr][ns] = V[lo[0]+.., lo[1]+.., lo[2]+.., lo[3]+..] with  */

@@ -64,6 +64,12 @@ class Blocked(C.Structure):
                 ("b_n1str", C.c_int64), ("c_n1str", C.c_int64), ("alpha", C.c_double), ("beta", C.c_double)]
 
 
+class Gather(C.Structure):
+    _fields_ = [("val", C.c_void_p), ("idx", C.c_void_p), ("D", C.c_void_p), ("out", C.c_void_p),
+                ("ext", I32x4), ("role", I32x4), ("x_str", C.c_int64 * 3), ("d_ystr", C.c_int64),
+                ("d_jstr", C.c_int64), ("alpha", C.c_double), ("beta", C.c_double)]
+
+
 _SIGS = {
     "pmb_version": (C.c_int, []),
     "pmb_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
@@ -102,6 +108,7 @@ _SIGS = {
     "pmb_ueg_build_nz": (C.c_int, [C.POINTER(Ueg), C.c_void_p, C.c_void_p, C.c_void_p, I32x4, I32x4,
                                    C.c_void_p, C.c_void_p]),
     "pmb_blocked_contract": (C.c_int, [C.POINTER(Blocked), C.c_void_p]),
+    "pmb_gather_expand": (C.c_int, [C.POINTER(Gather), C.c_void_p]),
     "pmb_synth_block": (C.c_int, [C.c_int, C.c_ulonglong, C.c_double, C.c_void_p, I32x4, I32x4, C.c_void_p,
                                   C.c_void_p]),
     "pmb_ueg_build_block": (C.c_int, [C.POINTER(Ueg), C.c_void_p, C.c_void_p, C.c_void_p, I32x4, I32x4,

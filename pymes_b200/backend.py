@@ -700,6 +700,81 @@ def _run_blocked(out_sub, term, out, beta):
     return True
 
 
+# T1 dressing products of a stored UEG block with ONE summed index ("abid,dj->abij", ...): gathers
+# over the partner tables instead of a pass over the o.v^3 block (pmb_gather_expand).
+_GATHER = [os.environ.get("PYMES_B200_T1_GATHER", "1") != "0"]
+
+
+def set_gather(flag):
+    old = _GATHER[0]
+    _GATHER[0] = bool(flag)
+    return old
+
+
+def _try_gather(out_sub, terms, out, beta):
+    """``out[x0,x1,x2,j] = beta*out + alpha * sum_y S[x0,x1,x2|y] D[y,j]`` for a stored, tagged UEG
+    integral block S (three of its indices in the output, one summed) and a two-index D (T1): one
+    candidate y per (x0,x1,x2), so the product is an HBM-bound pass over the output
+    (``pmb_gather_expand``).  Returns the result or None when the pattern / layouts do not apply."""
+    if not (_BLOCKED[0] and _GATHER[0]) or len(terms) != 1 or len(out_sub) != 4 or len(set(out_sub)) != 4:
+        return None
+    alpha, sa, A, sb, B = terms[0]
+    if geom_of(A) is None:
+        sa, A, sb, B = sb, B, sa, A
+    g = geom_of(A)
+    if g is None or isinstance(B, (GeneratedOperand, LinearOperator)) or len(sa) != 4 or len(sb) != 2:
+        return None
+    if len(set(sa)) != 4 or len(set(sb)) != 2 or not A.is_contiguous():
+        return None
+    B = asdev(B)
+    if B.dim() != 2 or geom_of(B) is not None:
+        return None
+    ys = [ch for ch in sa if ch in sb]
+    if len(ys) != 1 or ys[0] in out_sub:
+        return None
+    y = ys[0]
+    j = sb[1 - sb.index(y)]
+    xs = [ch for ch in sa if ch != y]
+    if j in sa or set(xs) | {j} != set(out_sub):
+        return None
+    ext = dict(zip(sa, (int(n) for n in A.shape)))
+    if int(B.shape[sb.index(y)]) != ext[y]:
+        raise ValueError("extent mismatch in %s,%s" % (sa, sb))
+    ext[j] = int(B.shape[sb.index(j)])
+    shape = tuple(ext[ch] for ch in out_sub)
+    if out is None:
+        if beta != 0.0:
+            raise ValueError("beta != 0 needs an output tensor")
+        out = empty(*shape)
+    elif tuple(out.shape) != shape:
+        raise ValueError("output shape %s != %s" % (tuple(out.shape), shape))
+    elif not out.is_contiguous():
+        return None
+    elif out.device != device():
+        raise RuntimeError("pymes_b200: output tensor lives on %s, the kernels write to %s "
+                           "(there is no CPU fallback)" % (out.device, device()))
+    tab = g.partner_tables(A, sa.index(y))
+    d = _lib.Gather()
+    d.val, d.idx, d.D, d.out = tab["val"].data_ptr(), tab["idx"].data_ptr(), B.data_ptr(), out.data_ptr()
+    xe = tab["ext"]
+    for k, ch in enumerate(out_sub):
+        d.ext[k] = ext[ch]
+        d.role[k] = 3 if ch == j else xs.index(ch)
+    d.x_str[0], d.x_str[1], d.x_str[2] = xe[1] * xe[2], xe[2], 1
+    d.d_ystr, d.d_jstr = B.stride(sb.index(y)), B.stride(sb.index(j))
+    d.alpha, d.beta = float(alpha), float(beta)
+    trace = _timing["trace"]
+    if trace is not None:
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(torch.cuda.current_stream())
+    rc = _lib.load().pmb_gather_expand(C.byref(d), _stream())
+    if trace is not None:
+        t1.record(torch.cuda.current_stream())
+        trace.append(("%s,%s->%s [momentum-gather]" % (sa, sb, out_sub), 2.0 * out.numel(), t0, t1))
+    _lib.check(rc, "pmb_gather_expand")
+    return out
+
+
 def _try_blocked(out_sub, terms, out, beta):
     """Terms with a momentum-structured operand (``_blocked_term``: a generated integral block or a
     stored one with a geometry tag) are
@@ -752,6 +827,9 @@ def contract_terms(out_sub, terms, out=None, beta=0.0):
         raise RuntimeError("pymes_b200: output tensor lives on %s, the kernels write to %s "
                            "(there is no CPU fallback)" % (out.device, device()))
     res = _try_gemv(out_sub, terms, out, beta)
+    if res is not None:
+        return res
+    res = _try_gather(out_sub, terms, out, beta)
     if res is not None:
         return res
     res = _try_blocked(out_sub, terms, out, beta)

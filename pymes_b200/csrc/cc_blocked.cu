@@ -210,3 +210,69 @@ extern "C" int pmb_blocked_contract(const pmb_blocked_t *d, pmb_stream_t stream)
     count_launch();
     return cuda_status();
 }
+
+// ---------------------------------------------------------------------------
+// pmb_gather_expand: a momentum-conserving integral block times a ONE-index contraction.
+//
+// out[x0,x1,x2,j] (+)= alpha * sum_y V[x0,x1,x2 | y] * D[y, j] has, for a UEG block, exactly one
+// candidate y per (x0,x1,x2) -- the orbital the reference's index lookup finds (ueg.py:395-404).  With
+// the values val[x] = V[x, y*(x)] and partners idx[x] = y*(x) (or -1) tabulated once per block and
+// summed axis, the product is an HBM-bound pass over the OUTPUT: 8 B written (16 with beta != 0)
+// per element, 12 B of table per (x0,x1,x2), instead of a pass over the o.v^3 block (25 GB at
+// v = 488).  These are the T1 dressing products "abid,dj->abij", "abcj,ci->abij", "iabc,cj->iabj",
+// "iacb,cj->iajb" of ccsd.py:322-419.  One thread per output element in output memory order (the
+// output is C-contiguous); `role` says which output dimension is x0 / x1 / x2 / j.
+// ---------------------------------------------------------------------------
+namespace pmb {
+namespace {
+
+// I = unsigned when the output has fewer than 2^31 elements (32-bit index arithmetic), else long long
+template <typename I>
+__global__ void __launch_bounds__(256) gather_expand_kernel(const __grid_constant__ pmb_gather_t p) {
+    const I e3 = (I)p.ext[3], e2 = (I)p.ext[2], e1 = (I)p.ext[1];
+    const long long total = (long long)p.ext[0] * p.ext[1] * p.ext[2] * p.ext[3];
+    const bool rd = p.beta != 0.0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        I c[4];
+        I q = (I)e;
+        c[3] = q % e3; q /= e3;
+        c[2] = q % e2; q /= e2;
+        c[1] = q % e1;
+        c[0] = q / e1;
+        long long xoff = 0, j = 0;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            if (p.role[d] == 3) j = (long long)c[d];
+            else xoff += (long long)c[d] * p.x_str[p.role[d]];
+        }
+        const int t = __ldg(p.idx + xoff);
+        double v = 0.0;
+        if (t >= 0) v = p.alpha * __ldg(p.val + xoff) * __ldg(p.D + (long long)t * p.d_ystr + j * p.d_jstr);
+        if (rd) v += p.beta * p.out[e];
+        p.out[e] = v;
+    }
+}
+
+}  // namespace
+}  // namespace pmb
+
+extern "C" int pmb_gather_expand(const pmb_gather_t *d, pmb_stream_t stream) {
+    if (!d || !d->val || !d->idx || !d->D || !d->out) return PMB_E_BADARG;
+    long long total = 1;
+    int seen = 0;
+    for (int k = 0; k < 4; ++k) {
+        if (d->ext[k] < 1 || d->role[k] < 0 || d->role[k] > 3) return PMB_E_BADARG;
+        seen |= 1 << d->role[k];
+        total *= d->ext[k];
+    }
+    if (seen != 15) return PMB_E_BADARG;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 32LL * kSmCount) blocks = 32LL * kSmCount;
+    if (total < (1LL << 31))
+        gather_expand_kernel<unsigned><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*d);
+    else
+        gather_expand_kernel<long long><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*d);
+    count_launch();
+    return cuda_status();
+}

@@ -585,6 +585,42 @@ class MomentumGeom:
             sub = self._narrowed[key] = MomentumGeom(self.model, new_lo, new_ext)
         return sub
 
+    def partner_tables(self, S, y_axis):
+        """For the stored block ``S`` (contiguous, this geometry) and one summed axis ``y_axis``:
+        ``idx[x0,x1,x2]`` = the local index along that axis of the ONE orbital the reference's lookup
+        can pair with the other three indices (``l_y = -sign_y * sum_others sign.l``, see
+        :func:`momentum_groups`), or -1, and ``val[x0,x1,x2] = S[x0,x1,x2 | idx]`` (0 where there is
+        none) -- what ``pmb_gather_expand`` reads instead of the block.  (x0,x1,x2) are the other
+        three axes in S's own order.  Device tensors, cached per (block memory, axis)."""
+        key = ("partner", int(S.data_ptr()), int(y_axis))
+        tab = self._lists.get(key)
+        if tab is None:
+            k = self.model.k_int().astype(np.int64)
+            n = 2 * int(self.model.imax) + 1
+            lin = n * n * k[:, 0] + n * k[:, 1] + k[:, 2]
+            lo, ext = self.lo, self.ext
+            others = [ax for ax in range(4) if ax != y_axis]
+            l = [SIGNS[ax] * lin[lo[ax]:lo[ax] + ext[ax]] for ax in others]
+            want = -SIGNS[y_axis] * (l[0][:, None, None] + l[1][None, :, None] + l[2][None, None, :])
+            ly = lin[lo[y_axis]:lo[y_axis] + ext[y_axis]]
+            order = np.argsort(ly)
+            pos = np.searchsorted(ly[order], want.reshape(-1))
+            pos = np.minimum(pos, len(ly) - 1)
+            hit = ly[order][pos] == want.reshape(-1)
+            idx = np.where(hit, order[pos], -1).astype(np.int32)
+            # flat position in S (C order of its own shape) of (x0,x1,x2 | idx)
+            stride = [int(np.prod(ext[ax + 1:])) for ax in range(4)]
+            grid = np.meshgrid(*[np.arange(ext[ax], dtype=np.int64) for ax in others], indexing="ij")
+            flat = sum(g * stride[ax] for g, ax in zip(grid, others)).reshape(-1)
+            flat = flat + np.maximum(idx, 0).astype(np.int64) * stride[y_axis]
+            dev = bk.device()
+            idx_d = torch.from_numpy(idx).to(dev)
+            val = torch.index_select(S.reshape(-1), 0, torch.from_numpy(flat).to(dev))
+            val = torch.where(idx_d >= 0, val, torch.zeros_like(val))
+            tab = self._lists[key] = dict(idx=idx_d, val=val, ext=tuple(ext[ax] for ax in others),
+                                          others=tuple(others), n_hit=int(hit.sum()), keep=S)
+        return tab
+
     def lists(self, m_axes=(0, 1), k_axes=(2, 3)):
         """Host lists (numpy int64 index pairs of the rows / entries, sorted by group), the device
         tile table and a cache for the offset tables derived from them."""

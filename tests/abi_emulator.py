@@ -367,6 +367,32 @@ class FakeLib:
             win[offs - lo] = val + (d.beta * old if d.beta != 0.0 else 0.0)
         return 0
 
+    def pmb_gather_expand(self, dref, stream):
+        """out[x0,x1,x2,j] = beta*out + alpha * val[x] * D[idx[x], j], as the header states it."""
+        d = dref._obj
+        self.launches += 1
+        ext = [d.ext[i] for i in range(4)]
+        role = [d.role[i] for i in range(4)]
+        assert sorted(role) == [0, 1, 2, 3]
+        grids = np.meshgrid(*[np.arange(e, dtype=np.int64) for e in ext], indexing="ij")
+        xoff = np.zeros(ext, dtype=np.int64)
+        j = None
+        for dim, r in enumerate(role):
+            if r == 3:
+                j = grids[dim]
+            else:
+                xoff += grids[dim] * d.x_str[r]
+        n_tab = int(xoff.max()) + 1
+        val = _window(d.val, n_tab)
+        idx = np.ctypeslib.as_array((C.c_int32 * n_tab).from_address(d.idx))
+        t = idx[xoff]
+        doff = np.where(t >= 0, t, 0) * d.d_ystr + j * d.d_jstr
+        Dv, _, _ = _gather(d.D, doff.reshape(-1))
+        new = np.where(t.reshape(-1) >= 0, d.alpha * val[xoff].reshape(-1) * Dv, 0.0)
+        out = _window(d.out, int(np.prod(ext)))
+        out[:] = new + (d.beta * out if d.beta != 0.0 else 0.0)
+        return 0
+
     def _generated(self, addr, m_ext, k_ext):
         """A[M,K] of a generated operand (pmb_ueg_operand_t): the block pmb_ueg_build_block
         would write, with its axes arranged as the M / K index groups (first listed fastest)."""

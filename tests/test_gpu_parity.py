@@ -629,6 +629,49 @@ def test_momentum_blocked_stored_blocks(n_ele, cutoff):
     assert _rel(R.cpu().numpy(), want.cpu().numpy()) < 1e-13
 
 
+@pytest.mark.parametrize("n_ele,cutoff", [(14, 5.0), (54, 7.0), (54, 10.0)])
+def test_momentum_gather_t1_products(n_ele, cutoff):
+    """pmb_gather_expand: products of a stored UEG o.v^3 block with T1 over ONE summed index, through
+    the partner tables, against the dense kernel and a torch einsum of the same operands -- with a
+    RANDOM T1 (T1 vanishes identically in the UEG, so the lock-step tests cannot see these values)."""
+    from pymes_b200 import backend as bk
+    m = _tc_model(n_ele, cutoff)
+    no, nP = n_ele // 2, m.n_orb
+    nv = nP - no
+    parts = [("only_2b", m.trunc), ("effect_2b", m.trunc)]
+    lo, na = nv // 3, nv - nv // 3 - 1
+    dV = m.eval_2b_blocks(no, ["abic", "abci", "iabc"], parts)
+    loc = m.eval_2b_blocks(no, ["abic", "abci", "iabc"], parts,
+                           ranges={"abic": {0: (no + lo, na)}, "abci": {0: (no + lo, na)}, "iabc": {1: (no + lo, na)}})
+    g = torch.Generator(device="cuda").manual_seed(4)
+    T1 = torch.randn(nv, no, dtype=torch.float64, device="cuda", generator=g)
+    old = bk.set_gather(True)
+    try:
+        for blocks in (dV, loc):
+            for spec, key in (("abid,dj->abij", "abic"), ("abcj,ci->abij", "abci"), ("iabc,cj->iabj", "iabc"),
+                              ("iacb,cj->iajb", "iabc")):
+                A = blocks[key]
+                bk.enable_trace(True)
+                got = bk.contract(spec, A, T1)
+                labels = [lab for lab, _f, _t in bk.trace_report()]
+                bk.enable_trace(False)
+                assert len(labels) == 1 and labels[0].endswith("[momentum-gather]"), (spec, labels)
+                bk.set_gather(False)
+                ref = bk.contract(spec, A, T1)
+                bk.set_gather(True)
+                want = torch.einsum(spec, A, T1)
+                assert float(want.abs().max()) > 0
+                assert _rel(got.cpu().numpy(), ref.cpu().numpy()) < 1e-13, spec
+                assert _rel(got.cpu().numpy(), want.cpu().numpy()) < 1e-13, spec
+        R0 = torch.randn(nv, nv, no, no, dtype=torch.float64, device="cuda", generator=g)
+        R = R0.clone()
+        bk.contract_terms("abij", [(-0.5, "abcj", dV["abci"], "ci", T1)], out=R, beta=1.0)
+        want = R0 - 0.5 * torch.einsum("abcj,ci->abij", dV["abci"], T1)
+        assert _rel(R.cpu().numpy(), want.cpu().numpy()) < 1e-13
+    finally:
+        bk.set_gather(old)
+
+
 def test_momentum_blocked_ladder_long_groups():
     """A group longer than the kernel's 512-entry offset window (several table refills per CTA) and
     more than 64 rows per group: a synthetic block-diagonal operand driven through the C ABI

@@ -1189,7 +1189,11 @@ def test_momentum_blocked_stored_blocks_host_logic(cpu_abi):
     check("acik,kbcj->abij", T, V_iabj, False)
     # one or three output indices on the integral block: not a 2 + 2 split
     check("adkl,lkdc->ac", T, V_ijab, False)
-    check("abid,dj->abij", dV["abic"], _t(rng.standard_normal((nv, no))), False)
+    old_gather = bk.set_gather(False)      # (with it on, this one-summed-index product goes to pmb_gather_expand)
+    try:
+        check("abid,dj->abij", dV["abic"], _t(rng.standard_normal((nv, no))), False)
+    finally:
+        bk.set_gather(old_gather)
     # row blocks keep their tag through backend.narrow (parallel.Shard.rows)
     part = bk.narrow(V_ijab, 2, 2, 3)
     assert bk.geom_of(part).lo[2] == no + 2 and bk.geom_of(part).ext[2] == 3
@@ -1209,3 +1213,71 @@ def test_momentum_blocked_stored_blocks_host_logic(cpu_abi):
     bk.contract_terms("abij", [(-1.0, "kaic", V_iajb, "cbkj", T), (1.0, "alci", X, "cblj", T)], out=R, beta=1.0)
     want = R0 - np.einsum("kaic,cbkj->abij", _n(V_iajb), _n(T)) + np.einsum("alci,cblj->abij", _n(X), _n(T))
     np.testing.assert_allclose(_n(R), want, rtol=0, atol=1e-12)
+
+
+def test_momentum_gather_t1_products_host_logic(cpu_abi):
+    """``pmb_gather_expand``: the T1 dressing products of a stored UEG block with ONE summed index
+    (ccsd.py:322-419: "abid,dj->abij", "abcj,ci->abij", "iabc,cj->iabj", "iacb,cj->iajb") through
+    the partner tables (one candidate orbital per (x0,x1,x2), ueg.py:395-404), against the dense
+    kernel and numpy, with a RANDOM T1 (in the UEG itself T1 vanishes identically, so the UEG
+    lock-step tests cannot see these values); row blocks of a sharded run; the dressed V_abij and
+    the shared X3 / X4 of a CCSD sweep with the path on and off."""
+    from pymes_b200 import backend as bk
+    from pymes_b200.model import ueg
+    from pymes_b200.solver import ccsd
+    from pymes_b200.integral.partition import KEYS
+    m = ueg.UEG(14, 7, 7, 0.5)
+    m.init_single_basis(2.0)
+    m.gamma, m.k_cutoff = None, 1.0
+    nP, no = m.n_orb, 7
+    nv = nP - no
+    parts = [("only_non_hermi_2b", m.trunc), ("effect_2b", m.trunc)]
+    dV = m.eval_2b_blocks(no, list(KEYS), parts)
+    rng = np.random.default_rng(12)
+    T1 = _t(rng.standard_normal((nv, no)))
+    calls = {"gather": 0, "dense": 0}
+    g0, d0 = cpu_abi.pmb_gather_expand, cpu_abi.pmb_contract
+    cpu_abi.pmb_gather_expand = lambda *a: (calls.__setitem__("gather", calls["gather"] + 1), g0(*a))[1]
+    cpu_abi.pmb_contract = lambda *a: (calls.__setitem__("dense", calls["dense"] + 1), d0(*a))[1]
+    old = bk.set_gather(True)
+    try:
+        cases = [("abid,dj->abij", "abic"), ("abcj,ci->abij", "abci"), ("iabc,cj->iabj", "iabc"),
+                 ("iacb,cj->iajb", "iabc"), ("dj,abid->abij", "abic")]
+        for spec, key in cases:
+            first_is_v = spec.split(",")[0] != "dj"
+            A, B = (dV[key], T1) if first_is_v else (T1, dV[key])
+            n0 = calls["gather"]
+            got = bk.contract(spec, A, B)
+            assert calls["gather"] == n0 + 1, spec
+            np.testing.assert_allclose(_n(got), np.einsum(spec, _n(A), _n(B)), rtol=0, atol=1e-13)
+        # the tables hold exactly the non-zero structure of the block
+        tab = bk.geom_of(dV["abic"]).partner_tables(dV["abic"], 3)
+        assert tab["n_hit"] >= np.count_nonzero(_n(dV["abic"])) > 0
+        # coefficient + accumulation into an existing tensor (a row of the dressed V_abij)
+        R0 = rng.standard_normal((nv, nv, no, no))
+        R = _t(R0.copy())
+        bk.contract_terms("abij", [(-0.5, "abcj", dV["abci"], "ci", T1)], out=R, beta=1.0)
+        np.testing.assert_allclose(_n(R), R0 - 0.5 * np.einsum("abcj,ci->abij", _n(dV["abci"]), _n(T1)),
+                                   rtol=0, atol=1e-13)
+        # local row blocks as one rank of a sharded run builds them
+        loc = m.eval_2b_blocks(no, ["abic", "iabc"], parts,
+                               ranges={"abic": {0: (no + 2, 3)}, "iabc": {1: (no + 2, 3)}})
+        got = bk.contract("abid,dj->abij", loc["abic"], T1)
+        np.testing.assert_allclose(_n(got), np.einsum("abid,dj->abij", _n(dV["abic"])[2:5], _n(T1)), rtol=0, atol=1e-13)
+        got = bk.contract("iacb,cj->iajb", loc["iabc"], T1)
+        np.testing.assert_allclose(_n(got), np.einsum("iacb,cj->iajb", _n(dV["iabc"])[:, 2:5], _n(T1)), rtol=0, atol=1e-13)
+        # not the pattern: two summed indices, a non-contiguous output -> other kernels
+        n0 = calls["gather"]
+        bk.contract("abid,dj->abij", dV["abic"], T1, out=bk.empty(no, no, nv, nv).permute(2, 3, 0, 1))
+        assert calls["gather"] == n0
+        # the CCSD building blocks that issue these products, path on vs off
+        on = (ccsd.t1_shared(T1, dV), ccsd.dressed_block("abij", T1, dV, skip_tau=True))
+        n_on = calls["gather"]
+        bk.set_gather(False)
+        off = (ccsd.t1_shared(T1, dV), ccsd.dressed_block("abij", T1, dV, skip_tau=True))
+        assert calls["gather"] == n_on and n_on >= n0 + 4
+        for k in ("X3", "X4", "G3", "G4"):
+            np.testing.assert_allclose(_n(on[0][k]), _n(off[0][k]), rtol=0, atol=1e-12)
+        np.testing.assert_allclose(_n(on[1]), _n(off[1]), rtol=0, atol=1e-12)
+    finally:
+        bk.set_gather(old)
