@@ -52,7 +52,8 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     if shutil.which("gcc") is None:
         pytest.skip("no gcc")
     pairs = {"pmb_term_t": _lib.Term, "pmb_contract_t": _lib.Contract, "pmb_bdot_t": _lib.Bdot,
-             "pmb_gemv_t": _lib.Gemv, "pmb_ueg_t": _lib.Ueg, "pmb_ueg_operand_t": _lib.UegOperand}
+             "pmb_gemv_t": _lib.Gemv, "pmb_ueg_t": _lib.Ueg, "pmb_ueg_operand_t": _lib.UegOperand,
+             "pmb_blocked_t": _lib.Blocked, "pmb_gather_t": _lib.Gather}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "pymes_b200.h"', "int main(void) {"]
     for cname, cls in pairs.items():
         lines.append('printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
