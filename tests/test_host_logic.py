@@ -1282,3 +1282,54 @@ def test_momentum_gather_t1_products_host_logic(cpu_abi):
         np.testing.assert_allclose(_n(on[1]), _n(off[1]), rtol=0, atol=1e-12)
     finally:
         bk.set_gather(old)
+
+
+def test_momentum_groups_cover_every_nonzero_for_every_split():
+    """Every non-zero of the oracle-built TC-UEG V_pqrs (the reference's triple loop restated,
+    oracle/ueg_oracle.py) lies inside the groups of ``momentum_groups`` -- for all six ways of
+    splitting (p,q,r,s) into two row and two entry axes and for random sub-blocks (what the geometry
+    tags of stored blocks and their narrowed row blocks rely on) -- and the partner tables of
+    ``pmb_gather_expand`` name exactly the non-zero's position for each of the four summed axes."""
+    import itertools
+    from oracle import ueg_oracle as uo
+    from pymes_b200.model import ueg
+    mo = uo.UEG(14, 1.0).init_single_basis(3.0)
+    mo.k_cutoff, mo.gamma = 2.0, None
+    _fock, V = mo.tc_hamiltonian(7)
+    nP = V.shape[0]
+    m = ueg.UEG(14, 7, 7, 1.0)
+    m.init_single_basis(3.0)
+    assert m.n_orb == nP and np.array_equal(m.k_int(), mo.kint)
+    k, imax = m.k_int(), m.imax
+    rng = np.random.default_rng(0)
+    blocks = [((0,) * 4, (nP,) * 4)]
+    for _ in range(4):
+        lo = rng.integers(0, nP - 3, size=4)
+        ext = [int(rng.integers(2, nP - l + 1)) for l in lo]
+        blocks.append((tuple(int(x) for x in lo), tuple(ext)))
+    n_checked = 0
+    for lo, ext in blocks:
+        blk = V[lo[0]:lo[0] + ext[0], lo[1]:lo[1] + ext[1], lo[2]:lo[2] + ext[2], lo[3]:lo[3] + ext[3]]
+        nz = np.argwhere(blk != 0)
+        for m_axes in itertools.combinations(range(4), 2):
+            k_axes = tuple(ax for ax in range(4) if ax not in m_axes)
+            row_ord, ent_ord, g_r0, g_rn, g_e0, g_en = ueg.momentum_groups(k, imax, lo, ext, m_axes, k_axes)
+            row_gid = -np.ones(ext[m_axes[0]] * ext[m_axes[1]], dtype=np.int64)
+            ent_gid = -np.ones(ext[k_axes[0]] * ext[k_axes[1]], dtype=np.int64)
+            for g in range(len(g_rn)):
+                row_gid[row_ord[g_r0[g]:g_r0[g] + g_rn[g]]] = g
+                ent_gid[ent_ord[g_e0[g]:g_e0[g] + g_en[g]]] = g
+            rows = nz[:, m_axes[0]] * ext[m_axes[1]] + nz[:, m_axes[1]]
+            ents = nz[:, k_axes[0]] * ext[k_axes[1]] + nz[:, k_axes[1]]
+            assert (row_gid[rows] >= 0).all() and (row_gid[rows] == ent_gid[ents]).all(), (lo, ext, m_axes)
+            n_checked += len(nz)
+        # one candidate partner per triple, on every axis
+        n = 2 * imax + 1
+        lin = (n * n * k[:, 0] + n * k[:, 1] + k[:, 2]).astype(np.int64)
+        for y in range(4):
+            others = [ax for ax in range(4) if ax != y]
+            l = [ueg.SIGNS[ax] * lin[lo[ax]:lo[ax] + ext[ax]] for ax in range(4)]
+            want = -ueg.SIGNS[y] * (l[others[0]][nz[:, others[0]]] + l[others[1]][nz[:, others[1]]]
+                                    + l[others[2]][nz[:, others[2]]])
+            assert np.array_equal(ueg.SIGNS[y] * l[y][nz[:, y]], want), (lo, ext, y)     # raw l(k_y)
+    assert n_checked > 10000
