@@ -20,8 +20,10 @@ blocked`): as a matrix the block is block diagonal in the (linear
 momentum, and pmb_blocked_contract visits the diagonal blocks only -- the particle-particle
 ladder 2 o^2 nnz(V_abcd) flop instead of 2 o^2 v^4 (5.2e10 instead of 8.3e13 at 515 plane
 waves), likewise V_iabc.tau / V_aibc.tau, I_klij and the three ring intermediates built from
-the stored V_ijab; same results to round-off.  Products of amplitudes with intermediates or
-T1-dressed blocks stay on the dense DMMA kernel (nothing is assumed about amplitudes).
+the stored V_ijab; the T1 products of the o.v^3 blocks over one summed index read partner
+tables instead of the blocks (pmb_gather_expand); same results to round-off.  Products of
+amplitudes with intermediates or T1-dressed blocks stay on the dense DMMA kernel (nothing is
+assumed about amplitudes).
 `--ladder dense` switches the blocked path off altogether: the dense DMMA ladder with the
 operand generated in the producer warps (the round-1 / early round-2 configuration; its
 roofline is the pp-ladder one).
