@@ -350,6 +350,39 @@ def calibrate(torch):
     return out
 
 
+def dense_ladder_probe(bk, torch, V_abcd, T2, peak, dgemm=None):
+    """One launch of the DENSE particle-particle ladder V_abcd.tau on the FP64 tensor cores (operand
+    generated in the producer warps, this rank's rows), timed with CUDA events after one warm-up launch:
+    the north_star's pp-ladder roofline target, measured in the same run as the default (momentum-
+    blocked) iteration.  Outside the timed region; never part of `value`."""
+    old = bk.set_blocked(False)
+    try:
+        nv, no = int(T2.shape[0]), int(T2.shape[2])
+        rows = int(V_abcd.shape[0])
+        tau = bk.axpby(1.0, T2, 0.0, bk.empty_even_pitch(nv, nv, no))
+        R = bk.zeros(rows, nv, no, no)
+        term = [(1.0, "abcd", V_abcd, "cdij", tau)]
+        bk.contract_terms("abij", term, out=R, beta=1.0)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record(torch.cuda.current_stream())
+        bk.contract_terms("abij", term, out=R, beta=1.0)
+        ev1.record(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        flops = 2.0 * rows * float(nv) ** 3 * no * no
+        out = {"kernel": "contract_ws_kernel (dense pp ladder V_abcd.tau, DMMA.8x8x4; V_abcd tiles generated by the "
+                         "producer warps): one launch after one warm-up, outside the timed region",
+               "ms_per_launch": ms, "flops_per_launch": flops, "achieved": flops / (ms * 1e-3) / 1e12,
+               "unit": "TFLOP/s", "peak": peak}
+        out["frac"] = out["achieved"] / peak
+        if dgemm:
+            out["frac_of_measured_dgemm"] = out["achieved"] / dgemm
+        return out
+    finally:
+        bk.set_blocked(old)
+
+
 def same_config_leg(cpu, steps_total, torch):
     """The problem the CPU leg timed (TC-UEG 54e in `cpu['n_orb']` plane waves), through the public
     API with HOST buffers on this GPU: numpy Fock / V_pqrs in, `steps_total` CCSD+DIIS sweeps with the
@@ -611,6 +644,15 @@ def run_ours(args):
                   "block), one iteration, amplitudes and energies back; the static operator (Fock, V "
                   "blocks) stays in HBM; bytes are per rank"}
 
+    if blocked and not args.no_dense_ladder:
+        # the dense DMMA ladder next to the blocked one, same run (every rank its rows; no collective)
+        try:
+            roof["pp_ladder_dense"] = dense_ladder_probe(bk, torch, dV["abcd"], cc._st["T2"], peak,
+                                                         cal["dgemm_tflops"] if cal is not None else None)
+        except Exception as exc:        # noqa: BLE001 -- a diagnostic must not cost the bench line
+            roof["pp_ladder_dense"] = {"error": repr(exc)}
+        barrier()
+
     line = {"metric": "ccsd_iteration_fp64_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -667,6 +709,9 @@ def main():
     ap.add_argument("--ladder", default="blocked", choices=["blocked", "dense"],
                     help="blocked: V_abcd.tau (and V_iabc.tau, V_aibc.tau) on the diagonal momentum blocks only "
                          "(pmb_blocked_contract); dense: the dense DMMA ladder with the generated operand")
+    ap.add_argument("--no-dense-ladder", action="store_true",
+                    help="skip the one extra launch of the dense DMMA ladder (roofline.pp_ladder_dense) after the "
+                         "timed region of a --ladder blocked run")
     ap.add_argument("--dense-abcd", action="store_true",
                     help="store V_abcd in HBM instead of generating it in the ladder kernel")
     args = ap.parse_args()
